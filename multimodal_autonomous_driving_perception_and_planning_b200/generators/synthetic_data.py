@@ -1,0 +1,142 @@
+"""Synthetic road-scene frames for the lane-detection path.
+
+Re-creation of the reference's ``SyntheticDataGenerator`` whose source is gone from the
+reference tree (only ``/root/reference/data/generators/__pycache__/synthetic_data.cpython-312.pyc``
+survives; behavioural spec in SURVEY.md Appendix B).  Frames are bit-identical to that
+bytecode's output (tests/test_generator.py checks sha256 fixtures taken from it).
+
+All drawing uses cv2 on the host: the frames are the *input fixture* of the path, produced
+once and uploaded; generation is never inside a timed region.  Pixel constants are absolute
+(they do not scale with resolution), exactly as in the reference.
+
+New here (BASELINE.json "data/generators: batched synthetic multi-camera frames"):
+``generate_batch`` and ``multi_camera_batch`` return ``uint8[N,H,W,3]`` / ``uint8[S,T,H,W,3]``
+stacks; camera ``s`` of a rig is the same scene generator started at ``frame_count = s*1000``.
+"""
+from __future__ import annotations
+
+from typing import Iterator, Optional
+
+import cv2
+import numpy as np
+
+_VEHICLE_COLORS = [(0, 100, 200), (200, 50, 50), (50, 200, 50), (200, 200, 50)]
+
+
+class SyntheticDataGenerator:
+    def __init__(self, width: int = 640, height: int = 480, fps: float = 30.0):
+        self.width = width
+        self.height = height
+        self.fps = fps
+        self.dt = 1.0 / fps
+        self.frame_count = 0
+
+    # ------------------------------------------------------------------ scene layers
+    def generate_road_frame(self) -> np.ndarray:
+        w, h = self.width, self.height
+        half = h // 2
+        img = np.zeros((h, w, 3), dtype=np.uint8)
+        for y in range(half):
+            r = y / half
+            cv2.line(img, (0, y), (w, y), (int(200 - 80 * r), int(180 - 60 * r), int(255 - 55 * r)), 1)
+        cv2.rectangle(img, (0, half), (w, h), (60, 60, 60), -1)
+        vp_x = w // 2 + int(20 * np.sin(self.frame_count * 0.02))
+        vp_y = half
+        road = np.array([[vp_x, vp_y], [50, h], [w - 50, h]], dtype=np.int32)
+        cv2.fillPoly(img, [road], (80, 80, 80))
+        self._draw_lane_markings(img, vp_x, vp_y)
+        self._draw_environment(img, half)
+        return img
+
+    def _draw_lane_markings(self, img, vp_x, vp_y):
+        h = self.height
+        n = 10
+        scroll = (self.frame_count * 5) % (h // n)
+
+        def row(t):
+            return min(int(vp_y + (h - vp_y) * t) + scroll, h)
+
+        for i in range(n):
+            ya, yb = row(i / n), row((i + 0.5) / n)
+            if ya >= vp_y and yb >= vp_y:
+                cv2.line(img, (vp_x, ya), (vp_x, yb), (255, 255, 200), 2)
+        for side in (-1, 1):
+            spread = side * 150
+            for i in range(n):
+                t1, t2 = i / n, (i + 0.6) / n
+                cv2.line(img, (int(vp_x + spread * t1), row(t1)), (int(vp_x + spread * t2), row(t2)),
+                         (255, 255, 255), 2)
+
+    def _draw_environment(self, img, horizon_y):
+        w, h = self.width, self.height
+        for i in range(5):
+            t = (i + 0.5) / 5
+            base = int(horizon_y + (h - horizon_y) * t * 0.8)
+            inset = int(30 + 50 * t)
+            tall = int(30 + 40 * t)
+            for x in (inset, w - inset):
+                cv2.line(img, (x, base), (x, base - tall), (80, 50, 30), 2)
+                cv2.circle(img, (x, base - tall - 10), int(15 * t + 5), (50, 120, 50), -1)
+
+    def generate_vehicle(self, frame, x, y, scale=1.0, color=(0, 100, 200)):
+        bw, bh = int(60 * scale), int(40 * scale)
+        cv2.rectangle(frame, (x - bw // 2, y - bh // 2), (x + bw // 2, y + bh // 2), color, -1)
+        cv2.rectangle(frame, (x - bw // 2, y - bh // 2), (x + bw // 2, y + bh // 2), (0, 0, 0), 1)
+        cv2.rectangle(frame, (x - bw // 3, y - bh // 2), (x + bw // 3, y - bh // 4), (100, 100, 100), -1)
+        rad = int(8 * scale)
+        cv2.circle(frame, (x - bw // 3, y + bh // 2), rad, (30, 30, 30), -1)
+        cv2.circle(frame, (x + bw // 3, y + bh // 2), rad, (30, 30, 30), -1)
+        return frame
+
+    def generate_frame_with_vehicles(self) -> np.ndarray:
+        w, h = self.width, self.height
+        frame = self.generate_road_frame()
+        # The reference reseeds NumPy's legacy global RNG every frame; a private RandomState
+        # with the same seed yields the same draws without clobbering global state.
+        rs = np.random.RandomState(self.frame_count % 100)
+        for i in range(rs.randint(2, 5)):
+            t = rs.uniform(0.2, 0.9)
+            y = int(h // 2 + (h // 2) * t)
+            lane = rs.choice([-80, 0, 80])
+            x = w // 2 + int(lane * t) + rs.randint(-20, 20)
+            x += int(30 * np.sin(self.frame_count * 0.05 + i))
+            self.generate_vehicle(frame, x, y, 0.3 + 0.7 * t, _VEHICLE_COLORS[i % 4])
+        self.frame_count += 1
+        return frame
+
+    def generate_video_stream(self, num_frames: int = 300) -> Iterator[np.ndarray]:
+        self.frame_count = 0
+        for _ in range(num_frames):
+            yield self.generate_frame_with_vehicles()
+
+    def reset(self):
+        self.frame_count = 0
+
+    # ------------------------------------------------------------------ batched forms (new)
+    def generate_batch(self, num_frames: int, start_frame: Optional[int] = None,
+                       out: Optional[np.ndarray] = None) -> np.ndarray:
+        """``uint8[num_frames,H,W,3]`` of consecutive frames (optionally from ``start_frame``)."""
+        if start_frame is not None:
+            self.frame_count = start_frame
+        if out is None:
+            out = np.empty((num_frames, self.height, self.width, 3), np.uint8)
+        for i in range(num_frames):
+            out[i] = self.generate_frame_with_vehicles()
+        return out
+
+
+def multi_camera_batch(num_streams: int, frames_per_stream: int, width: int = 1920, height: int = 1080,
+                       phase: int = 1000, period: Optional[int] = None) -> np.ndarray:
+    """``uint8[S,T,H,W,3]``: camera ``s`` is the scene generator started at ``frame_count = s*phase``.
+
+    ``period`` (optional) generates only that many distinct frames per stream and tiles them in
+    time -- for benchmarks whose input only has to be synthetic and larger than L2, not unique.
+    """
+    out = np.empty((num_streams, frames_per_stream, height, width, 3), np.uint8)
+    distinct = frames_per_stream if period is None else min(period, frames_per_stream)
+    for s in range(num_streams):
+        gen = SyntheticDataGenerator(width, height)
+        gen.generate_batch(distinct, start_frame=s * phase, out=out[s, :distinct])
+        for t in range(distinct, frames_per_stream):
+            out[s, t] = out[s, t % distinct]
+    return out
