@@ -1,0 +1,309 @@
+#!/usr/bin/env python
+"""Headline benchmark: 1080p lane-detect frames/s on N B200s (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+A "step" is one pass of the whole hot path (K1 blur+hist, K2 Canny+hysteresis, ROI compaction,
+K4 HoughLinesP, K5 fit/EMA/offset, result copy-back) over one batch of synthetic 1920x1080 frames
+per GPU (BASELINE config 2: 256 frames on one B200).  Scaling is weak: every rank processes its own
+camera streams with no collective on the data path; the per-frame records are gathered to rank 0
+with one NCCL gather per step (BASELINE config 3 semantics).
+
+value   frames/s with the frames already resident in HBM when the timed region starts.
+e2e     frames/s through the public API (LaneDetector.detect_batch) with HOST (pinned) frames:
+        host->device copy and device->host records inside the timed region.
+roofline  K1 (fused gray+blur+histogram), algorithmic 4 B/px (3 B/px BGR read + 1 B/px plane write,
+        SURVEY.md 8d) over its CUDA-event time measured live on the launching stream.
+cpu_baseline  the reference's OpenCV path (oracle/cv2_pipeline.py: the reference call sequence on
+        the same cv2/numpy) on this box's host cores, bounded sample.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+H, W = 1080, 1920
+ALGO_BYTES_PER_FRAME = 4 * H * W
+
+
+# ------------------------------------------------------------------------------------ CPU arm
+def _cpu_worker(args):
+    """One host core: the reference's cv2 path over its own camera stream (cv2 threads = 1)."""
+    stream, n_frames, width, height = args
+    import cv2
+    cv2.setNumThreads(1)
+    from multimodal_autonomous_driving_perception_and_planning_b200.generators import SyntheticDataGenerator
+    from oracle.cv2_pipeline import Cv2LaneOracle
+    distinct = min(n_frames, 16)
+    frames = SyntheticDataGenerator(width, height).generate_batch(distinct, start_frame=stream * 1000)
+    det = Cv2LaneOracle()
+    for i in range(3):
+        det.detect(frames[i % distinct])
+    det.reset()
+    t0 = time.perf_counter()
+    found = 0
+    for i in range(n_frames):
+        lf, rf = det.detect(frames[i % distinct])
+        det.offset(width, lf, rf)
+        found += (lf is not None) + (rf is not None)
+    return n_frames, time.perf_counter() - t0, found
+
+
+def cpu_reference_fps(frames_per_worker, workers=None):
+    import multiprocessing as mp
+    workers = workers or os.cpu_count() or 1
+    ctx = mp.get_context("fork")
+    with ctx.Pool(workers) as pool:
+        res = pool.map(_cpu_worker, [(s, frames_per_worker, W, H) for s in range(workers)])
+    total = sum(r[0] for r in res)
+    slowest = max(r[1] for r in res)
+    return total / slowest, workers, total, slowest
+
+
+def cpu_info():
+    model = "unknown"
+    try:
+        for line in open("/proc/cpuinfo"):
+            if line.startswith("model name"):
+                model = line.split(":", 1)[1].strip()
+                break
+    except OSError:
+        pass
+    import cv2
+    return {"cpu_model": model, "os_cpu_count": os.cpu_count(), "cv2": cv2.__version__, "numpy": np.__version__}
+
+
+# ------------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.lines = []
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "100",
+                 "-i", str(index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append((time.perf_counter(), line.strip()))
+
+    def stop(self, t0, t1):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+        rows = [l for (t, l) in self.lines if t0 <= t <= t1] or [l for (_, l) in self.lines[-3:]]
+        for l in rows:
+            p = [x.strip() for x in l.split(",")]
+            try:
+                sm.append(float(p[0])); mx.append(float(p[1]))
+            except (ValueError, IndexError):
+                continue
+            for name, v in zip(names, p[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------ main
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--frames", type=int, default=256, help="frames per GPU per step")
+    ap.add_argument("--distinct", type=int, default=64, help="distinct generator frames per stream (tiled in time)")
+    ap.add_argument("--cpu-frames", type=int, default=256, help="CPU baseline sample: frames per host core")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world > 1:
+        args.gpus = world
+
+    base = {"metric": "1080p lane-detect frames/s", "unit": "frames/s", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "data": "synthetic (SyntheticDataGenerator 1920x1080, per-stream phase 1000)"}
+    workload = (f"batch of {args.frames} synthetic 1920x1080 frames per GPU (BASELINE configs[1]; "
+                f"{args.distinct} distinct generator frames per stream tiled in time), full detect path")
+
+    # ---------------------------------------------------------------- reference arm (CPU, rank 0 only)
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        for _ in range(min(args.warmup, 1)):
+            cpu_reference_fps(8)
+        vals = []
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            fps, cores, total, slowest = cpu_reference_fps(max(args.cpu_frames // 4, 16))
+            vals.append((fps, total, slowest))
+        fps = sum(v[1] for v in vals) / sum(v[2] for v in vals)
+        sample = (f"{vals[0][1]} frames/step ({vals[0][1] // cores} per core) of the same 1080p generator streams, "
+                  f"{cores} processes x cv2.setNumThreads(1), sequential detect() per stream")
+        out = dict(base, impl="reference", value=fps, ms_per_step=1e3 * sum(v[2] for v in vals) / args.steps,
+                   dtype="u8/int32/f64", config={"workload": workload, "host": cpu_info()},
+                   cpu_baseline={"value": fps, "unit": "frames/s", "cores": cores, "kind": "port", "sample": sample},
+                   e2e={"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                   wall_s=time.perf_counter() - t0)
+        print(json.dumps(out))
+        return
+
+    # ---------------------------------------------------------------- CPU baseline first (before CUDA init)
+    cpu_baseline = None
+    if rank == 0 and args.gpus == 1:
+        fps, cores, total, slowest = cpu_reference_fps(args.cpu_frames)
+        cpu_baseline = {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port",
+                        "sample": f"{total} frames ({args.cpu_frames} per core x {cores} processes, cv2 threads=1 each) "
+                                  f"of the same 1080p generator streams in {slowest:.1f} s; "
+                                  f"oracle/cv2_pipeline.py = the reference call sequence on cv2 {cpu_info()['cv2']}",
+                        "host": cpu_info()}
+
+    import torch
+    import torch.distributed as dist
+    from multimodal_autonomous_driving_perception_and_planning_b200 import LaneDetector, _native, multi_camera_batch
+
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    # ---- inputs: this rank's camera stream(s); generated on the host with cv2, uploaded once
+    n = args.frames
+    host = multi_camera_batch(1, n, W, H, period=args.distinct)[0] if world == 1 else None
+    if world > 1:
+        from multimodal_autonomous_driving_perception_and_planning_b200 import SyntheticDataGenerator
+        host = np.empty((n, H, W, 3), np.uint8)
+        d = min(args.distinct, n)
+        SyntheticDataGenerator(W, H).generate_batch(d, start_frame=rank * 1000, out=host[:d])
+        for t in range(d, n):
+            host[t] = host[t % d]
+    pinned = torch.from_numpy(host).pin_memory()
+    frames_dev = pinned.to(dev, non_blocking=False)
+    torch.cuda.synchronize()
+
+    det = LaneDetector(device=local, max_batch=n)
+    ctx = det._context(H, W, n)                           # native context for n frames per call
+    stream = torch.cuda.ExternalStream(ctx.stream(), device=dev)
+    prev_fit = np.zeros((1, 2, 3), np.float64)
+    prev_valid = np.zeros((1, 2), np.uint8)
+    rec_bytes = _native.RECORD_DTYPE.itemsize * n
+    gather_buf = None
+    if world > 1:
+        gather_buf = [torch.empty(rec_bytes, dtype=torch.uint8, device=dev) for _ in range(world)] if rank == 0 else None
+
+    def step():
+        recs = ctx.detect(frames_dev.data_ptr(), n, True, None, 1, prev_fit, prev_valid, 0.7, 1 - 0.7)
+        if world > 1:
+            t = torch.from_numpy(recs.view(np.uint8)).to(dev)
+            dist.gather(t, gather_buf, dst=0)
+        return recs
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        recs = step()
+    found = int(recs["side"]["valid"].sum())
+
+    # ---- timed region: value (device-resident inputs)
+    ctx.set_profiling(True)
+    stage_sum = {k: 0.0 for k in _native.STAGE_NAMES}
+    launches = 0
+    sampler = ClockSampler(local) if rank == 0 else None
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
+    e0.record(stream)
+    for _ in range(args.steps):
+        step()
+        ms, ln = ctx.stage_ms()
+        for k in stage_sum:
+            stage_sum[k] += ms[k]
+        launches += sum(ln.values())
+    e1.record(stream)
+    barrier()
+    t1 = time.perf_counter()
+    clocks = sampler.stop(t0, t1) if sampler else None
+    dev_ms = e0.elapsed_time(e1)
+    ctx.set_profiling(False)
+    if world > 1:
+        tm = torch.tensor([dev_ms], device=dev)
+        dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+        dev_ms = float(tm.item())
+    value = args.gpus * n * args.steps / (dev_ms / 1e3)
+
+    # ---- e2e: public API with host (pinned) frames, H2D + records D2H inside the timed region
+    host_frames = pinned.numpy()
+    det.reset()
+    for _ in range(2):
+        det.detect_batch(host_frames)
+    barrier()
+    t2 = time.perf_counter()
+    for _ in range(args.steps):
+        lanes = det.detect_batch(host_frames)
+        off = det.get_lane_center_offset(W, *lanes[-1])
+    barrier()
+    e2e_s = time.perf_counter() - t2
+    if world > 1:
+        tm = torch.tensor([e2e_s], device=dev)
+        dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+        e2e_s = float(tm.item())
+    e2e_val = args.gpus * n * args.steps / e2e_s
+
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except OSError:
+            pass
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        k1_ms = stage_sum["blur_hist"] / args.steps
+        achieved = n * ALGO_BYTES_PER_FRAME / (k1_ms / 1e3) / 1e9 if k1_ms > 0 else 0.0
+        out = dict(base, value=value, ms_per_step=dev_ms / args.steps, dtype="u8/int32/f64",
+                   config={"workload": workload, "frames_per_gpu_per_step": n, "resolution": [W, H],
+                           "l2_policy": "inputs larger than L2 (1.6 GB of frames per step vs 126 MB L2)",
+                           "parallelism": f"stream-sharded x{args.gpus}, NCCL gather of records only"},
+                   roofline={"bound": "hbm", "kernel": "K1 blur_hist (gray + 5x5 blur + histogram)",
+                             "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                             "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 (of fallback)",
+                             "traffic": None, "ms_per_launch": k1_ms,
+                             "algorithmic_bytes_per_launch": n * ALGO_BYTES_PER_FRAME},
+                   stage_ms_per_step={k: v / args.steps for k, v in stage_sum.items()},
+                   e2e={"value": e2e_val, "unit": "frames/s", "h2d_bytes_per_step": int(host_frames.nbytes),
+                        "d2h_bytes_per_step": int(rec_bytes), "api": "LaneDetector.detect_batch(numpy pinned)"},
+                   gpu_launches=launches, clocks=clocks, lanes_found_last_step=found,
+                   last_offset=None if off is None else float(off))
+        if cpu_baseline:
+            out["cpu_baseline"] = cpu_baseline
+        print(json.dumps(out))
+    det.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

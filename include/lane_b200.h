@@ -1,0 +1,162 @@
+/*
+ * lane_b200.h -- C ABI of the B200-native batched lane-detection path.
+ *
+ * Drop-in boundary for ONE hot path of the reference:
+ *   /root/reference/src/perception/lane_detector.py:178-218  LaneDetector.detect
+ *   /root/reference/src/perception/lane_detector.py:253-272  LaneDetector.get_lane_center_offset
+ * The reference has no FFI of its own (pure Python over cv2/numpy); the entry points below
+ * are what a ctypes binding inside lane_detector.py binds.  Each one
+ * names the reference lines it replaces.
+ *
+ * Conventions: plain pointers and sizes only; every function returns 0 on success or a
+ * negative lane_status code, never throws; the library never frees or reallocates caller
+ * memory; one context per (device, stream); a context is not re-entrant.  All device work
+ * of a call is enqueued on the context's stream; the blocking calls synchronise that
+ * stream before returning.
+ */
+#ifndef LANE_B200_H
+#define LANE_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define LANE_API __attribute__((visibility("default")))
+#else
+#define LANE_API
+#endif
+
+#define LANE_B200_ABI_VERSION 1
+#define LANE_NUM_POINTS 50          /* lane_detector.py:164  np.linspace(.., .., 50) */
+
+typedef enum lane_status {
+    LANE_OK = 0,
+    LANE_ERR_INVALID = -1,          /* bad argument (shape, null pointer, batch too large) */
+    LANE_ERR_CUDA = -2,             /* a CUDA runtime call or kernel failed; see lane_last_error */
+    LANE_ERR_NO_DEVICE = -3,        /* no usable sm_100 device: there is NO CPU fallback */
+    LANE_ERR_STATE = -4,            /* ROI / LUT not set before detect */
+    LANE_ERR_UNSUPPORTED = -5       /* frame larger than this build supports */
+} lane_status;
+
+/* One side of one frame -- mirrors LaneLine (lane_detector.py:13-19). */
+typedef struct lane_side {
+    int32_t valid;                  /* 0 => the reference returns None for this side */
+    int32_t n_lines;                /* segments that fed the fit (confidence = min(1, n/10)) */
+    double raw[3];                  /* np.polyfit(y, x, 2) output, highest power first (:156) */
+    double coeffs[3];               /* after the EMA with the previous fit (:159-161) -> LaneLine.polynomial */
+    double confidence;              /* :171 */
+    int32_t points[LANE_NUM_POINTS][2]; /* (x, y) int32, truncation toward zero (:164-167) -> LaneLine.points */
+} lane_side;
+
+/* Result record of one frame. */
+typedef struct lane_record {
+    lane_side side[2];              /* 0 = left, 1 = right (:206-216) */
+    double offset;                  /* get_lane_center_offset (:253-272); meaningful iff offset_valid */
+    int32_t offset_valid;
+    int32_t median_x2;              /* 2 * np.median(blurred) (:79) */
+    int32_t low, high;              /* Canny thresholds (:80-81) */
+    int32_t n_edges;                /* non-zero pixels of the full-frame Canny map (:83) */
+    int32_t n_roi_points;           /* non-zero pixels after the ROI mask (:89) */
+    int32_t n_segments;             /* segments HoughLinesP returned (:94-101) */
+    int32_t hysteresis_rounds;      /* propagation rounds the frame needed (diagnostic) */
+    int32_t flags;                  /* LANE_FLAG_* */
+    int32_t reserved;
+} lane_record;
+
+#define LANE_FLAG_SEGMENTS_TRUNCATED 1   /* more segments than max_segments: extra ones dropped */
+#define LANE_FLAG_POINTS_TRUNCATED 2     /* a side had more than LANE_MAX_SIDE_SEGMENTS segments */
+
+typedef struct lane_ctx lane_ctx;
+
+/* ---- lifetime ------------------------------------------------------------------------ */
+/* Replaces LaneDetector.__init__ (lane_detector.py:35-45) for a fixed frame size.
+ * max_batch frames of height x width BGR can be processed per call.  max_segments bounds the
+ * HoughLinesP output kept per frame (0 => default 256). */
+LANE_API int lane_ctx_create(int device, int height, int width, int max_batch, int max_segments, lane_ctx **out);
+LANE_API void lane_ctx_destroy(lane_ctx *ctx);
+/* Message of the last failure on this context (or of the last failed create when ctx is NULL). */
+LANE_API const char *lane_last_error(const lane_ctx *ctx);
+LANE_API int lane_abi_version(void);
+
+/* ---- static per-detector inputs ------------------------------------------------------- */
+/* ROI mask produced once on the host by cv2.fillPoly (lane_detector.py:47-64): uint8[height*width],
+ * non-zero = inside.  Replaces the per-frame _get_roi_mask/_apply_roi (:86-90). */
+LANE_API int lane_set_roi_mask(lane_ctx *ctx, const uint8_t *mask);
+/* low/high Canny thresholds for every possible 2*median (index 0..510), filled by evaluating the
+ * reference's own float64 expressions (lane_detector.py:80-81). */
+LANE_API int lane_set_threshold_lut(lane_ctx *ctx, const uint8_t *low511, const uint8_t *high511);
+/* HoughLinesP literals (lane_detector.py:94-101); defaults 50, 50, 150. */
+LANE_API int lane_set_hough_params(lane_ctx *ctx, int threshold, int min_line_length, int max_line_gap);
+/* smoothing_factor and (1 - smoothing_factor) exactly as the host evaluates them (:159-161). */
+LANE_API int lane_set_smoothing(lane_ctx *ctx, double factor, double one_minus_factor);
+/* Keep per-stage intermediates of the next detect calls for the lane_debug_* taps (costs memory traffic). */
+LANE_API int lane_set_debug(lane_ctx *ctx, int keep_intermediates);
+
+/* ---- the hot path --------------------------------------------------------------------- */
+/* Replaces n sequential LaneDetector.detect calls (lane_detector.py:178-218) plus
+ * get_lane_center_offset (:253-272).
+ *   frames            uint8 [n][height][width][3] BGR, C-contiguous; host memory when
+ *                     frames_on_device == 0 (copied inside the call), device memory otherwise.
+ *   stream_id         host int32[n], camera stream of each frame (NULL => all stream 0); frames of
+ *                     one stream must appear in temporal order.
+ *   n_streams         number of streams S.
+ *   prev_fit          host double [S][2][3], in/out: prev_left_fit / prev_right_fit per stream (:43-44).
+ *   prev_valid        host uint8 [S][2], in/out: 0 => None.
+ *   out               host lane_record[n].
+ * Blocking: returns after the records are in `out`. */
+LANE_API int lane_detect_batch(lane_ctx *ctx, const uint8_t *frames, int frames_on_device, int n,
+                      const int32_t *stream_id, int n_streams, double *prev_fit, uint8_t *prev_valid,
+                      lane_record *out);
+
+/* Asynchronous split of the above for pipelined callers: enqueue (device frames only; records
+ * land in an internal pinned buffer), then collect.  The EMA state travels as above at collect. */
+LANE_API int lane_detect_enqueue(lane_ctx *ctx, const uint8_t *frames_dev, int n, const int32_t *stream_id,
+                        int n_streams, const double *prev_fit, const uint8_t *prev_valid);
+LANE_API int lane_detect_collect(lane_ctx *ctx, double *prev_fit, uint8_t *prev_valid, lane_record *out);
+
+/* The context's CUDA stream (cudaStream_t as void*), so callers can record events on it. */
+LANE_API void *lane_ctx_stream(lane_ctx *ctx);
+/* Use a caller-owned stream (cudaStream_t) instead of the context's own. */
+LANE_API int lane_ctx_set_stream(lane_ctx *ctx, void *cuda_stream);
+
+/* ---- measurement ---------------------------------------------------------------------- */
+#define LANE_STAGE_H2D 0
+#define LANE_STAGE_BLUR_HIST 1      /* K1: gray + 5x5 blur + histogram */
+#define LANE_STAGE_CANNY 2          /* K2: thresholds + Sobel + NMS + hysteresis */
+#define LANE_STAGE_COMPACT 3        /* ROI mask + ordered point list */
+#define LANE_STAGE_PPHT 4           /* K4: HoughLinesP */
+#define LANE_STAGE_FIT 5            /* K5: split + polyfit + EMA + points + offset */
+#define LANE_STAGE_D2H 6
+#define LANE_NUM_STAGES 7
+/* When enabled, CUDA events bracket every stage of the next calls. */
+LANE_API int lane_set_profiling(lane_ctx *ctx, int enabled);
+/* Device time (ms) of each stage in the last completed call, and kernel launches it made. */
+LANE_API int lane_get_stage_ms(lane_ctx *ctx, float ms[LANE_NUM_STAGES], int32_t launches[LANE_NUM_STAGES]);
+
+/* ---- verification taps (need lane_set_debug(ctx, 1) before the detect call) ------------ */
+#define LANE_TAP_BLUR 1             /* uint8 [H][W]   cv2.GaussianBlur output (:72) */
+#define LANE_TAP_HIST 2             /* uint32[256]    histogram behind np.median (:79) */
+#define LANE_TAP_CLASS 3            /* uint8 [H][W]   0 none / 1 weak / 2 strong before hysteresis */
+#define LANE_TAP_EDGES 4            /* uint8 [H][W]   cv2.Canny output 0/255 (:83) */
+#define LANE_TAP_POINTS 5           /* int32 [n_roi_points][2] (x,y) row-major order of masked edges (:89) */
+#define LANE_TAP_SEGMENTS 6         /* int32 [n_segments][4] HoughLinesP output (:94-101) */
+#define LANE_TAP_GRAY 7             /* uint8 [H][W]   cv2.cvtColor output (:69); recomputed on demand */
+/* Copies tap `what` of frame `frame_index` of the last batch to host memory; *bytes_written is set. */
+LANE_API int lane_debug_tap(lane_ctx *ctx, int what, int frame_index, void *host_out, size_t capacity,
+                   size_t *bytes_written);
+
+/* Standard Hough accumulator (BASELINE.json north-star add-on; what cv2.HoughLines(img,1,pi/180,t)
+ * votes into) of the ROI-masked edge map of frame `frame_index` of the last batch:
+ * int32 [182][2*(W+H)+3] with cv2's one-cell padding.  peaks (optional): int32 triples
+ * (rho_index, angle_index, votes) of local maxima above `threshold` in cv2's output order. */
+LANE_API int lane_hough_accumulator(lane_ctx *ctx, int frame_index, int32_t *accum_host, int threshold,
+                           int32_t *peaks_host, int max_peaks, int *n_peaks);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LANE_B200_H */

@@ -1,0 +1,8 @@
+"""B200-native batched lane detection: a drop-in for the lane-detection hot path of
+bhavyageethika/multimodal_autonomous_driving_perception_and_planning
+(``src/perception/lane_detector.py``).  See DESIGN.md / INTEGRATION.md at the repo root."""
+from .generators import SyntheticDataGenerator, multi_camera_batch
+from .perception import LaneDetector, LaneLine
+
+__all__ = ["LaneDetector", "LaneLine", "SyntheticDataGenerator", "multi_camera_batch"]
+__version__ = "0.1.0"

@@ -1,0 +1,522 @@
+// C-ABI shim over the lane-detection kernels: context, device buffers, stage sequencing.
+// Entry points are declared (with the reference lines they replace) in include/lane_b200.h.
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "lane_common.cuh"
+
+void lane_upload_sample_rows(int H);
+
+static thread_local std::string g_create_error;
+
+struct lane_ctx {
+    int device = 0;
+    int max_batch = 0;
+    LaneGeom g{};
+    LaneHoughParams hp{50, 50, 150};
+    double smooth = 0.7, one_minus_smooth = 1 - 0.7;
+    bool have_roi = false, have_lut = false, debug = false, profiling = false;
+    bool own_stream = true;
+    cudaStream_t st = nullptr;
+    std::string err;
+
+    // device buffers
+    uint8_t *d_frames = nullptr;      // staging for host frames (lazy)
+    uint8_t *d_blur = nullptr, *d_cls = nullptr, *d_cls_dbg = nullptr, *d_roi = nullptr, *d_pmask = nullptr;
+    uint8_t *d_gray_dbg = nullptr;
+    uint32_t *d_hist = nullptr, *d_points = nullptr, *d_points_dbg = nullptr;
+    uint8_t *d_lut = nullptr;         // low[511] | high[511]
+    int4 *d_thr = nullptr;
+    int *d_seedsA = nullptr, *d_seedsB = nullptr, *d_seed_count = nullptr;
+    int seed_cap = 0;
+    int *d_n_edges = nullptr, *d_n_points = nullptr, *d_rounds = nullptr, *d_n_lines = nullptr;
+    int32_t *d_accum = nullptr, *d_lines = nullptr;
+    LaneFitScratch fit{};
+    int *d_stream_id = nullptr;
+    double *d_prev_fit = nullptr;
+    uint8_t *d_prev_valid = nullptr;
+    int stream_cap = 0;
+    lane_record *d_records = nullptr, *h_records = nullptr;   // h_records pinned
+    double *h_prev_fit = nullptr;
+    uint8_t *h_prev_valid = nullptr;
+    int32_t *d_std_accum = nullptr;
+    int2 *d_peaks = nullptr;
+    int *d_n_peaks = nullptr;
+    int peaks_cap = 0;
+
+    // last call
+    const uint8_t *last_frames_dev = nullptr;
+    int last_n = 0, last_streams = 0;
+    bool in_flight = false;
+    cudaEvent_t ev[LANE_NUM_STAGES + 1] = {};
+    float stage_ms[LANE_NUM_STAGES] = {};
+    int32_t stage_launches[LANE_NUM_STAGES] = {};
+    bool timed = false;
+};
+
+namespace {
+
+int fail(lane_ctx *c, int code, const char *fmt, ...)
+{
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    if (c) c->err = buf; else g_create_error = buf;
+    return code;
+}
+
+#define CU(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess)                                                                     \
+            return fail(c, LANE_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), \
+                        __FILE__, __LINE__);                                                       \
+    } while (0)
+
+template <typename T>
+cudaError_t dalloc(T **p, size_t count)
+{
+    return cudaMalloc((void **)p, std::max<size_t>(count, 1) * sizeof(T) + 64);
+}
+
+void free_all(lane_ctx *c)
+{
+    cudaSetDevice(c->device);
+    void *ptrs[] = {c->d_frames, c->d_blur, c->d_cls, c->d_cls_dbg, c->d_roi, c->d_pmask, c->d_gray_dbg, c->d_hist,
+                    c->d_points, c->d_points_dbg, c->d_lut, c->d_thr, c->d_seedsA, c->d_seedsB, c->d_seed_count,
+                    c->d_n_edges, c->d_n_points, c->d_rounds, c->d_n_lines, c->d_accum, c->d_lines, c->fit.raw,
+                    c->fit.side_n, c->fit.side_flags, c->d_stream_id, c->d_prev_fit, c->d_prev_valid,
+                    c->d_records, c->d_std_accum, c->d_peaks, c->d_n_peaks};
+    for (void *p : ptrs)
+        if (p) cudaFree(p);
+    if (c->h_records) cudaFreeHost(c->h_records);
+    if (c->h_prev_fit) cudaFreeHost(c->h_prev_fit);
+    if (c->h_prev_valid) cudaFreeHost(c->h_prev_valid);
+    for (auto &e : c->ev)
+        if (e) cudaEventDestroy(e);
+    if (c->own_stream && c->st) cudaStreamDestroy(c->st);
+}
+
+int ensure_streams(lane_ctx *c, int S)
+{
+    if (S <= c->stream_cap) return LANE_OK;
+    if (c->d_prev_fit) cudaFree(c->d_prev_fit);
+    if (c->d_prev_valid) cudaFree(c->d_prev_valid);
+    if (c->h_prev_fit) cudaFreeHost(c->h_prev_fit);
+    if (c->h_prev_valid) cudaFreeHost(c->h_prev_valid);
+    c->d_prev_fit = nullptr; c->d_prev_valid = nullptr; c->h_prev_fit = nullptr; c->h_prev_valid = nullptr;
+    CU(dalloc(&c->d_prev_fit, (size_t)S * 6));
+    CU(dalloc(&c->d_prev_valid, (size_t)S * 2));
+    CU(cudaMallocHost((void **)&c->h_prev_fit, sizeof(double) * S * 6));
+    CU(cudaMallocHost((void **)&c->h_prev_valid, (size_t)S * 2));
+    c->stream_cap = S;
+    return LANE_OK;
+}
+
+int mark(lane_ctx *c, int i)
+{
+    if (c->profiling) CU(cudaEventRecord(c->ev[i], c->st));
+    return LANE_OK;
+}
+
+// Enqueue every stage for n device-resident frames.
+int enqueue(lane_ctx *c, const uint8_t *frames_dev, int n, const int32_t *stream_id, int S,
+            const double *prev_fit, const uint8_t *prev_valid)
+{
+    const LaneGeom &g = c->g;
+    const int H = g.H, W = g.W;
+    int *L = c->stage_launches;
+    // small host->device state: stream ids + EMA state
+    int rc = ensure_streams(c, S);
+    if (rc) return rc;
+    if (stream_id) CU(cudaMemcpyAsync(c->d_stream_id, stream_id, sizeof(int) * n, cudaMemcpyHostToDevice, c->st));
+    memcpy(c->h_prev_fit, prev_fit, sizeof(double) * S * 6);
+    memcpy(c->h_prev_valid, prev_valid, (size_t)S * 2);
+    CU(cudaMemcpyAsync(c->d_prev_fit, c->h_prev_fit, sizeof(double) * S * 6, cudaMemcpyHostToDevice, c->st));
+    CU(cudaMemcpyAsync(c->d_prev_valid, c->h_prev_valid, (size_t)S * 2, cudaMemcpyHostToDevice, c->st));
+
+    rc = mark(c, LANE_STAGE_BLUR_HIST); if (rc) return rc;
+    launch_blur_hist(frames_dev, c->d_blur, c->d_hist, n, H, W, c->st, &L[LANE_STAGE_BLUR_HIST]);
+
+    rc = mark(c, LANE_STAGE_CANNY); if (rc) return rc;
+    launch_thresholds(c->d_hist, c->d_lut, c->d_lut + 511, c->d_thr, n, H, W, c->st, &L[LANE_STAGE_CANNY]);
+    launch_sobel_nms(c->d_blur, c->d_thr, c->d_cls, c->d_seedsA, c->d_seed_count, c->seed_cap, n, H, W, c->st,
+                     &L[LANE_STAGE_CANNY]);
+    if (c->debug)
+        CU(cudaMemcpyAsync(c->d_cls_dbg, c->d_cls, (size_t)n * H * W, cudaMemcpyDeviceToDevice, c->st));
+    launch_hysteresis(c->d_cls, c->d_seedsA, c->d_seedsB, c->d_seed_count, c->seed_cap, c->d_rounds, n, H, W, c->st,
+                      &L[LANE_STAGE_CANNY]);
+    launch_finalize_edges(c->d_cls, c->d_n_edges, n, H, W, c->st, &L[LANE_STAGE_CANNY]);
+
+    rc = mark(c, LANE_STAGE_COMPACT); if (rc) return rc;
+    launch_compact(c->d_cls, c->d_roi, c->d_pmask, c->d_points, c->d_n_points, g, n, c->st, &L[LANE_STAGE_COMPACT]);
+    if (c->debug)
+        CU(cudaMemcpyAsync(c->d_points_dbg, c->d_points, sizeof(uint32_t) * (size_t)n * g.max_points,
+                           cudaMemcpyDeviceToDevice, c->st));
+
+    rc = mark(c, LANE_STAGE_PPHT); if (rc) return rc;
+    launch_ppht(c->d_points, c->d_n_points, c->d_pmask, c->d_accum, c->d_lines, c->d_n_lines, g, c->hp, n, c->st,
+                &L[LANE_STAGE_PPHT]);
+
+    rc = mark(c, LANE_STAGE_FIT); if (rc) return rc;
+    launch_fit(c->d_lines, c->d_n_lines, c->fit, stream_id ? c->d_stream_id : nullptr, S, c->d_prev_fit,
+               c->d_prev_valid, c->smooth, c->one_minus_smooth, c->d_thr, c->d_n_edges, c->d_n_points, c->d_rounds,
+               c->d_records, g, n, c->st, &L[LANE_STAGE_FIT]);
+
+    rc = mark(c, LANE_STAGE_D2H); if (rc) return rc;
+    CU(cudaMemcpyAsync(c->h_records, c->d_records, sizeof(lane_record) * n, cudaMemcpyDeviceToHost, c->st));
+    CU(cudaMemcpyAsync(c->h_prev_fit, c->d_prev_fit, sizeof(double) * S * 6, cudaMemcpyDeviceToHost, c->st));
+    CU(cudaMemcpyAsync(c->h_prev_valid, c->d_prev_valid, (size_t)S * 2, cudaMemcpyDeviceToHost, c->st));
+    rc = mark(c, LANE_NUM_STAGES); if (rc) return rc;
+    CU(cudaGetLastError());
+    c->last_frames_dev = frames_dev;
+    c->last_n = n;
+    c->last_streams = S;
+    c->in_flight = true;
+    c->timed = c->profiling;
+    return LANE_OK;
+}
+
+int check_call(lane_ctx *c, const void *frames, int n, int S, const void *pf, const void *pv)
+{
+    if (!c) return LANE_ERR_INVALID;
+    if (!frames || n <= 0 || n > c->max_batch) return fail(c, LANE_ERR_INVALID, "bad batch: n=%d (max_batch=%d)", n, c->max_batch);
+    if (S <= 0 || !pf || !pv) return fail(c, LANE_ERR_INVALID, "bad stream state: n_streams=%d", S);
+    if (!c->have_roi || !c->have_lut) return fail(c, LANE_ERR_STATE, "lane_set_roi_mask and lane_set_threshold_lut must be called first");
+    if (c->in_flight) return fail(c, LANE_ERR_STATE, "a batch is already in flight; call lane_detect_collect");
+    return LANE_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int lane_abi_version(void) { return LANE_B200_ABI_VERSION; }
+
+const char *lane_last_error(const lane_ctx *ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+int lane_ctx_create(int device, int height, int width, int max_batch, int max_segments, lane_ctx **out)
+{
+    lane_ctx *c = nullptr;   // errors before allocation go to the global slot
+    if (!out) return fail(c, LANE_ERR_INVALID, "out is null");
+    *out = nullptr;
+    if (height < 1 || width < 1 || max_batch < 1) return fail(c, LANE_ERR_INVALID, "bad shape %dx%d batch %d", height, width, max_batch);
+    if (height > 32767 || width > 32767) return fail(c, LANE_ERR_UNSUPPORTED, "frame %dx%d exceeds 32767 px per side", height, width);
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+        return fail(c, LANE_ERR_NO_DEVICE, "no CUDA device visible: this library has no CPU fallback");
+    if (device < 0 || device >= ndev) return fail(c, LANE_ERR_INVALID, "device %d out of range (%d visible)", device, ndev);
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess || prop.major != 10)
+        return fail(c, LANE_ERR_NO_DEVICE, "device %d is sm_%d%d; this build holds sm_100a code only", device, prop.major, prop.minor);
+    if (cudaSetDevice(device) != cudaSuccess) return fail(c, LANE_ERR_CUDA, "cudaSetDevice(%d) failed", device);
+
+    lane_ctx *ctx = new lane_ctx();
+    ctx->device = device;
+    ctx->max_batch = max_batch;
+    LaneGeom &g = ctx->g;
+    g.H = height; g.W = width;
+    g.numrho = 2 * (width + height) + 1;
+    g.max_segments = max_segments > 0 ? max_segments : 256;
+    g.bx0 = g.by0 = g.bx1 = g.by1 = g.bw = g.bh = 0;
+    g.max_points = 0;
+    const size_t P = (size_t)height * width, B = (size_t)max_batch;
+    ctx->seed_cap = (int)std::min<size_t>(P, (size_t)1 << 17);
+    c = ctx;
+    auto bail = [&](int code) { std::string e = ctx->err; free_all(ctx); delete ctx; g_create_error = e; return code; };
+#define CUB(call)                                                                                       \
+    do {                                                                                                \
+        cudaError_t e_ = (call);                                                                        \
+        if (e_ != cudaSuccess) {                                                                        \
+            fail(c, LANE_ERR_CUDA, "%s failed: %s", #call, cudaGetErrorString(e_));                     \
+            return bail(LANE_ERR_CUDA);                                                                 \
+        }                                                                                               \
+    } while (0)
+    CUB(cudaStreamCreateWithFlags(&ctx->st, cudaStreamNonBlocking));
+    for (auto &e : ctx->ev) CUB(cudaEventCreate(&e));
+    CUB(dalloc(&ctx->d_blur, B * P));
+    CUB(dalloc(&ctx->d_cls, B * P));
+    CUB(dalloc(&ctx->d_roi, P));
+    CUB(dalloc(&ctx->d_hist, B * 256));
+    CUB(dalloc(&ctx->d_lut, 1022));
+    CUB(dalloc(&ctx->d_thr, B));
+    CUB(dalloc(&ctx->d_seedsA, B * ctx->seed_cap));
+    CUB(dalloc(&ctx->d_seedsB, B * ctx->seed_cap));
+    CUB(dalloc(&ctx->d_seed_count, B));
+    CUB(dalloc(&ctx->d_n_edges, B));
+    CUB(dalloc(&ctx->d_n_points, B));
+    CUB(dalloc(&ctx->d_rounds, B));
+    CUB(dalloc(&ctx->d_n_lines, B));
+    CUB(dalloc(&ctx->d_accum, B * LANE_NUM_ANGLES * g.numrho));
+    CUB(dalloc(&ctx->d_lines, B * g.max_segments * 4));
+    CUB(dalloc(&ctx->fit.raw, B * 6));
+    CUB(dalloc(&ctx->fit.side_n, B * 2));
+    CUB(dalloc(&ctx->fit.side_flags, B));
+    CUB(dalloc(&ctx->d_stream_id, B));
+    CUB(dalloc(&ctx->d_records, B));
+    CUB(cudaMallocHost((void **)&ctx->h_records, sizeof(lane_record) * B));
+    CUB(cudaMemset(ctx->d_records, 0, sizeof(lane_record) * B));
+    lane_upload_tables();
+    lane_upload_sample_rows(height);
+    CUB(cudaGetLastError());
+    CUB(cudaDeviceSynchronize());
+#undef CUB
+    *out = ctx;
+    return LANE_OK;
+}
+
+void lane_ctx_destroy(lane_ctx *ctx)
+{
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    if (ctx->st) cudaStreamSynchronize(ctx->st);
+    free_all(ctx);
+    delete ctx;
+}
+
+int lane_set_roi_mask(lane_ctx *c, const uint8_t *mask)
+{
+    if (!c || !mask) return LANE_ERR_INVALID;
+    CU(cudaSetDevice(c->device));
+    LaneGeom &g = c->g;
+    int x0 = g.W, y0 = g.H, x1 = -1, y1 = -1, cnt = 0;
+    for (int y = 0; y < g.H; y++)
+        for (int x = 0; x < g.W; x++)
+            if (mask[(size_t)y * g.W + x]) {
+                x0 = std::min(x0, x); x1 = std::max(x1, x); y0 = std::min(y0, y); y1 = std::max(y1, y);
+                cnt++;
+            }
+    if (cnt == 0) { x0 = y0 = 0; x1 = y1 = -1; }
+    g.bx0 = x0; g.by0 = y0; g.bx1 = x1 + 1; g.by1 = y1 + 1;
+    g.bw = g.bx1 - g.bx0; g.bh = g.by1 - g.by0;
+    g.max_points = cnt;
+    CU(cudaStreamSynchronize(c->st));
+    CU(cudaMemcpy(c->d_roi, mask, (size_t)g.H * g.W, cudaMemcpyHostToDevice));
+    if (c->d_pmask) cudaFree(c->d_pmask);
+    if (c->d_points) cudaFree(c->d_points);
+    if (c->d_points_dbg) cudaFree(c->d_points_dbg);
+    c->d_pmask = nullptr; c->d_points = nullptr; c->d_points_dbg = nullptr;
+    CU(dalloc(&c->d_pmask, (size_t)c->max_batch * g.bw * g.bh));
+    CU(dalloc(&c->d_points, (size_t)c->max_batch * g.max_points));
+    if (c->debug) CU(dalloc(&c->d_points_dbg, (size_t)c->max_batch * g.max_points));
+    c->have_roi = true;
+    return LANE_OK;
+}
+
+int lane_set_threshold_lut(lane_ctx *c, const uint8_t *low511, const uint8_t *high511)
+{
+    if (!c || !low511 || !high511) return LANE_ERR_INVALID;
+    CU(cudaSetDevice(c->device));
+    CU(cudaStreamSynchronize(c->st));
+    CU(cudaMemcpy(c->d_lut, low511, 511, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(c->d_lut + 511, high511, 511, cudaMemcpyHostToDevice));
+    c->have_lut = true;
+    return LANE_OK;
+}
+
+int lane_set_hough_params(lane_ctx *c, int threshold, int min_line_length, int max_line_gap)
+{
+    if (!c || threshold < 1 || min_line_length < 0 || max_line_gap < 0) return LANE_ERR_INVALID;
+    c->hp = LaneHoughParams{threshold, min_line_length, max_line_gap};
+    return LANE_OK;
+}
+
+int lane_set_smoothing(lane_ctx *c, double factor, double one_minus_factor)
+{
+    if (!c) return LANE_ERR_INVALID;
+    c->smooth = factor; c->one_minus_smooth = one_minus_factor;
+    return LANE_OK;
+}
+
+int lane_set_debug(lane_ctx *c, int keep)
+{
+    if (!c) return LANE_ERR_INVALID;
+    CU(cudaSetDevice(c->device));
+    c->debug = keep != 0;
+    if (c->debug) {
+        const size_t P = (size_t)c->g.H * c->g.W;
+        if (!c->d_cls_dbg) CU(dalloc(&c->d_cls_dbg, (size_t)c->max_batch * P));
+        if (!c->d_gray_dbg) CU(dalloc(&c->d_gray_dbg, P));
+        if (!c->d_points_dbg && c->have_roi) CU(dalloc(&c->d_points_dbg, (size_t)c->max_batch * c->g.max_points));
+    }
+    return LANE_OK;
+}
+
+int lane_set_profiling(lane_ctx *c, int enabled)
+{
+    if (!c) return LANE_ERR_INVALID;
+    c->profiling = enabled != 0;
+    return LANE_OK;
+}
+
+void *lane_ctx_stream(lane_ctx *c) { return c ? (void *)c->st : nullptr; }
+
+int lane_ctx_set_stream(lane_ctx *c, void *cuda_stream)
+{
+    if (!c) return LANE_ERR_INVALID;
+    if (c->in_flight) return fail(c, LANE_ERR_STATE, "cannot switch streams with a batch in flight");
+    if (c->own_stream && c->st) { cudaStreamSynchronize(c->st); cudaStreamDestroy(c->st); }
+    c->st = (cudaStream_t)cuda_stream;
+    c->own_stream = false;
+    return LANE_OK;
+}
+
+int lane_detect_enqueue(lane_ctx *c, const uint8_t *frames_dev, int n, const int32_t *stream_id, int n_streams,
+                        const double *prev_fit, const uint8_t *prev_valid)
+{
+    int rc = check_call(c, frames_dev, n, n_streams, prev_fit, prev_valid);
+    if (rc) return rc;
+    CU(cudaSetDevice(c->device));
+    if (stream_id)
+        for (int i = 0; i < n; i++)
+            if (stream_id[i] < 0 || stream_id[i] >= n_streams)
+                return fail(c, LANE_ERR_INVALID, "stream_id[%d]=%d outside [0,%d)", i, stream_id[i], n_streams);
+    memset(c->stage_launches, 0, sizeof(c->stage_launches));
+    if (c->profiling) CU(cudaEventRecord(c->ev[LANE_STAGE_H2D], c->st));
+    return enqueue(c, frames_dev, n, stream_id, n_streams, prev_fit, prev_valid);
+}
+
+int lane_detect_collect(lane_ctx *c, double *prev_fit, uint8_t *prev_valid, lane_record *out)
+{
+    if (!c || !out || !prev_fit || !prev_valid) return LANE_ERR_INVALID;
+    if (!c->in_flight) return fail(c, LANE_ERR_STATE, "no batch in flight");
+    CU(cudaSetDevice(c->device));
+    c->in_flight = false;
+    CU(cudaStreamSynchronize(c->st));
+    memcpy(out, c->h_records, sizeof(lane_record) * c->last_n);
+    memcpy(prev_fit, c->h_prev_fit, sizeof(double) * c->last_streams * 6);
+    memcpy(prev_valid, c->h_prev_valid, (size_t)c->last_streams * 2);
+    if (c->timed)
+        for (int i = 0; i < LANE_NUM_STAGES; i++) CU(cudaEventElapsedTime(&c->stage_ms[i], c->ev[i], c->ev[i + 1]));
+    return LANE_OK;
+}
+
+int lane_detect_batch(lane_ctx *c, const uint8_t *frames, int frames_on_device, int n, const int32_t *stream_id,
+                      int n_streams, double *prev_fit, uint8_t *prev_valid, lane_record *out)
+{
+    int rc = check_call(c, frames, n, n_streams, prev_fit, prev_valid);
+    if (rc) return rc;
+    if (!out) return fail(c, LANE_ERR_INVALID, "out is null");
+    CU(cudaSetDevice(c->device));
+    if (stream_id)
+        for (int i = 0; i < n; i++)
+            if (stream_id[i] < 0 || stream_id[i] >= n_streams)
+                return fail(c, LANE_ERR_INVALID, "stream_id[%d]=%d outside [0,%d)", i, stream_id[i], n_streams);
+    memset(c->stage_launches, 0, sizeof(c->stage_launches));
+    if (c->profiling) CU(cudaEventRecord(c->ev[LANE_STAGE_H2D], c->st));
+    const uint8_t *dev = frames;
+    if (!frames_on_device) {
+        const size_t bytes = (size_t)c->g.H * c->g.W * 3;
+        if (!c->d_frames) CU(dalloc(&c->d_frames, (size_t)c->max_batch * bytes));
+        CU(cudaMemcpyAsync(c->d_frames, frames, bytes * n, cudaMemcpyHostToDevice, c->st));
+        dev = c->d_frames;
+    }
+    rc = enqueue(c, dev, n, stream_id, n_streams, prev_fit, prev_valid);
+    if (rc) return rc;
+    return lane_detect_collect(c, prev_fit, prev_valid, out);
+}
+
+int lane_get_stage_ms(lane_ctx *c, float ms[LANE_NUM_STAGES], int32_t launches[LANE_NUM_STAGES])
+{
+    if (!c) return LANE_ERR_INVALID;
+    if (ms) memcpy(ms, c->stage_ms, sizeof(c->stage_ms));
+    if (launches) memcpy(launches, c->stage_launches, sizeof(c->stage_launches));
+    return LANE_OK;
+}
+
+int lane_debug_tap(lane_ctx *c, int what, int fi, void *host_out, size_t capacity, size_t *bytes_written)
+{
+    if (!c || !host_out) return LANE_ERR_INVALID;
+    if (c->in_flight) return fail(c, LANE_ERR_STATE, "collect the batch before reading taps");
+    if (fi < 0 || fi >= c->last_n) return fail(c, LANE_ERR_INVALID, "frame_index %d outside last batch (%d)", fi, c->last_n);
+    CU(cudaSetDevice(c->device));
+    const LaneGeom &g = c->g;
+    const size_t P = (size_t)g.H * g.W;
+    const void *src = nullptr;
+    size_t bytes = 0;
+    std::vector<int32_t> tmp;
+    switch (what) {
+    case LANE_TAP_BLUR: src = c->d_blur + fi * P; bytes = P; break;
+    case LANE_TAP_HIST: src = c->d_hist + fi * 256; bytes = 256 * sizeof(uint32_t); break;
+    case LANE_TAP_EDGES: src = c->d_cls + fi * P; bytes = P; break;
+    case LANE_TAP_CLASS:
+        if (!c->debug || !c->d_cls_dbg) return fail(c, LANE_ERR_STATE, "LANE_TAP_CLASS needs lane_set_debug(ctx,1) before detect");
+        src = c->d_cls_dbg + fi * P; bytes = P; break;
+    case LANE_TAP_GRAY:
+        if (!c->d_gray_dbg) return fail(c, LANE_ERR_STATE, "LANE_TAP_GRAY needs lane_set_debug(ctx,1)");
+        launch_gray_debug(c->last_frames_dev + fi * P * 3, c->d_gray_dbg, g.H, g.W, c->st);
+        CU(cudaStreamSynchronize(c->st));
+        src = c->d_gray_dbg; bytes = P; break;
+    case LANE_TAP_POINTS: {
+        if (!c->debug || !c->d_points_dbg) return fail(c, LANE_ERR_STATE, "LANE_TAP_POINTS needs lane_set_debug(ctx,1) before detect");
+        int np = c->h_records[fi].n_roi_points;
+        std::vector<uint32_t> packed(np);
+        CU(cudaMemcpy(packed.data(), c->d_points_dbg + (size_t)fi * g.max_points, sizeof(uint32_t) * np, cudaMemcpyDeviceToHost));
+        bytes = sizeof(int32_t) * 2 * np;
+        if (bytes > capacity) return fail(c, LANE_ERR_INVALID, "tap needs %zu bytes, capacity %zu", bytes, capacity);
+        int32_t *o = (int32_t *)host_out;
+        for (int i = 0; i < np; i++) { o[2 * i] = packed[i] & 0xFFFF; o[2 * i + 1] = packed[i] >> 16; }
+        if (bytes_written) *bytes_written = bytes;
+        return LANE_OK;
+    }
+    case LANE_TAP_SEGMENTS:
+        src = c->d_lines + (size_t)fi * g.max_segments * 4;
+        bytes = sizeof(int32_t) * 4 * c->h_records[fi].n_segments; break;
+    default: return fail(c, LANE_ERR_INVALID, "unknown tap %d", what);
+    }
+    if (bytes > capacity) return fail(c, LANE_ERR_INVALID, "tap needs %zu bytes, capacity %zu", bytes, capacity);
+    if (bytes) CU(cudaMemcpy(host_out, src, bytes, cudaMemcpyDeviceToHost));
+    if (bytes_written) *bytes_written = bytes;
+    return LANE_OK;
+}
+
+int lane_hough_accumulator(lane_ctx *c, int fi, int32_t *accum_host, int threshold, int32_t *peaks_host,
+                           int max_peaks, int *n_peaks)
+{
+    if (!c) return LANE_ERR_INVALID;
+    if (c->in_flight) return fail(c, LANE_ERR_STATE, "collect the batch first");
+    if (fi < 0 || fi >= c->last_n) return fail(c, LANE_ERR_INVALID, "frame_index %d outside last batch (%d)", fi, c->last_n);
+    if (!c->debug || !c->d_points_dbg) return fail(c, LANE_ERR_STATE, "lane_hough_accumulator needs lane_set_debug(ctx,1) before detect");
+    CU(cudaSetDevice(c->device));
+    const LaneGeom &g = c->g;
+    const size_t cells = (size_t)(LANE_NUM_ANGLES + 2) * (g.numrho + 2);
+    if (!c->d_std_accum) CU(dalloc(&c->d_std_accum, cells));
+    launch_hough_accum(c->d_points_dbg + (size_t)fi * g.max_points, c->d_n_points + fi, c->d_std_accum, g, c->st);
+    CU(cudaGetLastError());
+    if (accum_host) CU(cudaMemcpyAsync(accum_host, c->d_std_accum, sizeof(int32_t) * cells, cudaMemcpyDeviceToHost, c->st));
+    int found = 0;
+    if (peaks_host && max_peaks > 0) {
+        if (max_peaks > c->peaks_cap) {
+            if (c->d_peaks) cudaFree(c->d_peaks);
+            c->d_peaks = nullptr;
+            CU(dalloc(&c->d_peaks, (size_t)max_peaks));
+            c->peaks_cap = max_peaks;
+        }
+        if (!c->d_n_peaks) CU(dalloc(&c->d_n_peaks, 1));
+        launch_hough_peaks(c->d_std_accum, g.numrho, threshold, c->d_peaks, max_peaks, c->d_n_peaks, c->st);
+        CU(cudaGetLastError());
+        CU(cudaMemcpyAsync(&found, c->d_n_peaks, sizeof(int), cudaMemcpyDeviceToHost, c->st));
+        CU(cudaStreamSynchronize(c->st));
+        int m = std::min(found, max_peaks);
+        std::vector<int2> pk(m);
+        CU(cudaMemcpy(pk.data(), c->d_peaks, sizeof(int2) * m, cudaMemcpyDeviceToHost));
+        // cv2 order: votes descending, flat index ascending
+        std::sort(pk.begin(), pk.end(), [](const int2 &a, const int2 &b) { return a.y != b.y ? a.y > b.y : a.x < b.x; });
+        for (int i = 0; i < m; i++) {
+            int nn = pk[i].x / (g.numrho + 2) - 1;
+            int r = pk[i].x - (nn + 1) * (g.numrho + 2) - 1;
+            peaks_host[3 * i] = r; peaks_host[3 * i + 1] = nn; peaks_host[3 * i + 2] = pk[i].y;
+        }
+    }
+    CU(cudaStreamSynchronize(c->st));
+    if (n_peaks) *n_peaks = found;
+    return LANE_OK;
+}
+
+}  // extern "C"

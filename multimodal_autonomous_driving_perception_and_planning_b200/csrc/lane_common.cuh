@@ -1,0 +1,75 @@
+// Shared declarations for the lane-detection kernels (sm_100a).
+//
+// Stage map (reference lines are under /root/reference/src/perception/lane_detector.py):
+//   K1  k1_blur_hist.cu   gray (:69) + 5x5 binomial blur (:72) + 256-bin histogram (:79)
+//   K2  k2_canny.cu       median/thresholds (:79-81) + Sobel + NMS + hysteresis (:83)
+//       k2_compact.cu     ROI mask (:86-90) + row-major point list (HoughLinesP's nzloc)
+//   K3  k3_hough.cu       standard Hough accumulator + peaks (north-star add-on)
+//   K4  k4_ppht.cu        exact cv2.HoughLinesP (:94-101)
+//   K5  k5_fit.cu         side split (:105-134), polyfit + EMA + points (:136-176), offset (:253-272)
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/lane_b200.h"
+
+#define LANE_NUM_ANGLES 180
+#define LANE_MAX_SIDE_SEGMENTS 256   // per side; more sets LANE_FLAG_POINTS_TRUNCATED
+
+struct LaneGeom {
+    int H, W;
+    int bx0, by0, bx1, by1;   // ROI bounding box [bx0,bx1) x [by0,by1); empty => bx1 <= bx0
+    int bw, bh;               // bbox size
+    int numrho;               // 2*(W+H)+1
+    int max_points;           // non-zero pixels of the ROI mask (upper bound of the point list)
+    int max_segments;
+};
+
+struct LaneHoughParams {
+    int threshold, min_len, max_gap;
+};
+
+// ---- K1 ---------------------------------------------------------------------------------
+void launch_blur_hist(const uint8_t *frames, uint8_t *blur, uint32_t *hist, int n, int H, int W,
+                      cudaStream_t st, int *launches);
+void launch_gray_debug(const uint8_t *frame, uint8_t *gray, int H, int W, cudaStream_t st);
+
+// ---- K2 ---------------------------------------------------------------------------------
+// thr: int4 per frame = (median_x2, low, high, 0)
+void launch_thresholds(const uint32_t *hist, const uint8_t *lut_low, const uint8_t *lut_high, int4 *thr,
+                       int n, int H, int W, cudaStream_t st, int *launches);
+// cls: 0 none / 1 weak / 2 strong;  seeds: per-frame list of strong pixel indices
+void launch_sobel_nms(const uint8_t *blur, const int4 *thr, uint8_t *cls, int *seeds, int *seed_count,
+                      int seed_cap, int n, int H, int W, cudaStream_t st, int *launches);
+// in place: promoted pixels become 3; afterwards cls >= 2 <=> edge.  rounds: per-frame BFS depth.
+void launch_hysteresis(uint8_t *cls, int *seeds, int *seeds2, const int *seed_count, int seed_cap,
+                       int *rounds, int n, int H, int W, cudaStream_t st, int *launches);
+// cls (>=2) -> edges 0/255 in place, n_edges per frame
+void launch_finalize_edges(uint8_t *cls_edges, int *n_edges, int n, int H, int W, cudaStream_t st, int *launches);
+// ROI mask + ordered compaction: points[f][k] = (y<<16)|x in row-major order; pmask = bbox-sized byte mask
+void launch_compact(const uint8_t *edges, const uint8_t *roi, uint8_t *pmask, uint32_t *points, int *n_points,
+                    LaneGeom g, int n, cudaStream_t st, int *launches);
+
+// ---- K3 ---------------------------------------------------------------------------------
+void launch_hough_accum(const uint32_t *points, const int *n_points, int32_t *accum_padded, LaneGeom g,
+                        cudaStream_t st);
+void launch_hough_peaks(const int32_t *accum_padded, int numrho, int threshold, int2 *peaks, int max_peaks,
+                        int *n_peaks, cudaStream_t st);
+void lane_upload_tables();       // trig tables -> __constant__ (both Hough variants)
+void lane_upload_tables_std();
+
+// ---- K4 ---------------------------------------------------------------------------------
+// accum: int32 [n][180][numrho] zeroed by the launcher; lines: int32 [n][max_segments][4]
+void launch_ppht(uint32_t *points, const int *n_points, uint8_t *pmask, int32_t *accum, int32_t *lines,
+                 int *n_lines, LaneGeom g, LaneHoughParams hp, int n, cudaStream_t st, int *launches);
+
+// ---- K5 ---------------------------------------------------------------------------------
+struct LaneFitScratch {
+    double *raw;        // [n][2][3]
+    int *side_n;        // [n][2] segments per side (0 => None)
+    int *side_flags;    // [n]
+};
+void launch_fit(const int32_t *lines, const int *n_lines, LaneFitScratch fs, const int *stream_id, int n_streams,
+                double *prev_fit, uint8_t *prev_valid, double smooth, double one_minus_smooth,
+                const int4 *thr, const int *n_edges, const int *n_points, const int *rounds,
+                lane_record *records, LaneGeom g, int n, cudaStream_t st, int *launches);

@@ -1,0 +1,252 @@
+"""Lane detection behind the reference's ``LaneDetector`` API, computed on a B200.
+
+Mirror of ``/root/reference/src/perception/lane_detector.py``: the same public names, argument
+meaning and return types (``LaneLine``, ``LaneDetector.detect / draw_lanes /
+get_lane_center_offset / reset``, attributes ``roi_vertices``, ``prev_left_fit``,
+``prev_right_fit``, ``smoothing_factor``), plus the new ``detect_batch`` / ``detect_streams``.
+Every pixel stage runs in hand-written CUDA (``csrc/``) through the C ABI in
+``include/lane_b200.h``; there is no OpenCV on the detection path and no CPU fallback.  cv2 is
+used only where the reference's result *is* cv2's rasteriser and does not depend on the frame:
+the ROI polygon mask (``cv2.fillPoly``, built once per frame size) and ``draw_lanes``.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import List, Optional, Sequence, Tuple
+
+import cv2
+import numpy as np
+
+from .. import _native
+
+
+@dataclass
+class LaneLine:
+    """Represents a detected lane line (reference: lane_detector.py:13-19)."""
+    points: np.ndarray  # int32 [50, 2] (x, y)
+    side: str  # "left" or "right"
+    confidence: float
+    polynomial: Optional[np.ndarray] = None  # float64 [3], highest power first
+
+
+LanePair = Tuple[Optional[LaneLine], Optional[LaneLine]]
+_SIDES = ("left", "right")
+
+
+def _is_torch_cuda(x) -> bool:
+    return type(x).__module__.startswith("torch") and hasattr(x, "is_cuda") and bool(x.is_cuda)
+
+
+class LaneDetector:
+    """Edge + Hough lane detector with temporal smoothing (reference: lane_detector.py:22-277).
+
+    ``LaneDetector(roi_vertices=None)`` is the reference signature; the keyword-only extras pick the
+    GPU and the largest batch one native call processes (larger batches are chunked).
+    """
+
+    def __init__(self, roi_vertices: Optional[np.ndarray] = None, *, device: Optional[int] = None,
+                 max_batch: int = 64, max_segments: int = 256, debug: bool = False):
+        self.roi_vertices = roi_vertices
+        self.prev_left_fit = None
+        self.prev_right_fit = None
+        self.smoothing_factor = 0.7
+        self._device = device
+        self._max_batch = int(max_batch)
+        self._max_segments = int(max_segments)
+        self._debug = bool(debug)
+        self._ctx: Optional[_native.LaneContext] = None
+        self._ctx_key = None
+        self._stream_fit = None     # float64 [S,2,3] for detect_streams
+        self._stream_valid = None   # uint8  [S,2]
+        self.last_records = None    # RECORD_DTYPE array of the last call (diagnostics)
+
+    # ------------------------------------------------------------------ static inputs
+    def _get_roi_mask(self, shape: Tuple[int, int]) -> np.ndarray:
+        """ROI mask exactly as the reference rasterises it (lane_detector.py:47-64)."""
+        h, w = shape[:2]
+        if self.roi_vertices is not None:
+            vertices = self.roi_vertices
+        else:
+            vertices = np.array([[(int(w * 0.1), h), (int(w * 0.4), int(h * 0.6)),
+                                  (int(w * 0.6), int(h * 0.6)), (int(w * 0.9), h)]], dtype=np.int32)
+        mask = np.zeros((h, w), dtype=np.uint8)
+        cv2.fillPoly(mask, vertices, 255)
+        return mask
+
+    def _device_index(self) -> int:
+        if self._device is not None:
+            return int(self._device)
+        try:
+            import torch
+            if torch.cuda.is_available():
+                return int(torch.cuda.current_device())
+        except Exception:
+            pass
+        return 0
+
+    def _context(self, h: int, w: int, n: int) -> _native.LaneContext:
+        roi_key = None if self.roi_vertices is None else np.asarray(self.roi_vertices).tobytes()
+        key = (h, w, roi_key, self._device_index())
+        if self._ctx is None or self._ctx_key != key or self._ctx.max_batch < min(n, self._max_batch):
+            if self._ctx is not None:
+                self._ctx.close()
+            cap = max(min(n, self._max_batch), 1)
+            self._ctx = _native.LaneContext(h, w, cap, self._get_roi_mask((h, w)), device=key[3],
+                                            max_segments=self._max_segments, debug=self._debug)
+            self._ctx_key = key
+        return self._ctx
+
+    # ------------------------------------------------------------------ input checking
+    @staticmethod
+    def _check_frames(frames, batched: bool):
+        nd = 4 if batched else 3
+        shape = tuple(frames.shape)
+        if len(shape) != nd or shape[-1] != 3:
+            # the reference fails inside cv2.cvtColor for anything but 3-channel input
+            raise cv2.error(f"LaneDetector: expected uint8 BGR frame(s) of shape "
+                            f"{'[N,H,W,3]' if batched else '[H,W,3]'}, got {shape}")
+        dt = str(frames.dtype).replace("torch.", "")
+        if dt != "uint8":
+            # the reference fails inside cv2.Canny (depth assertion) for non-8-bit input
+            raise cv2.error(f"LaneDetector: frames must be uint8, got {dt}")
+
+    # ------------------------------------------------------------------ record decoding
+    def _lanes_from_records(self, recs: np.ndarray) -> List[LanePair]:
+        out: List[LanePair] = []
+        sides = recs["side"]
+        for i in range(len(recs)):
+            pair = []
+            for s in (0, 1):
+                sd = sides[i, s]
+                if sd["valid"]:
+                    pair.append(LaneLine(points=sd["points"].astype(np.int32, copy=True), side=_SIDES[s],
+                                         confidence=float(sd["confidence"]),
+                                         polynomial=sd["coeffs"].astype(np.float64, copy=True)))
+                else:
+                    pair.append(None)
+            out.append((pair[0], pair[1]))
+        return out
+
+    def _run(self, frames, stream_id, n_streams, prev_fit, prev_valid) -> np.ndarray:
+        """Chunked native calls over frames [N,H,W,3] (numpy or CUDA torch); state arrays updated in place."""
+        n, h, w = int(frames.shape[0]), int(frames.shape[1]), int(frames.shape[2])
+        ctx = self._context(h, w, n)
+        s, oms = self.smoothing_factor, 1 - self.smoothing_factor
+        chunks = []
+        on_device = _is_torch_cuda(frames)
+        if on_device:
+            import torch
+            frames = frames.contiguous()
+            torch.cuda.current_stream(frames.device).synchronize()
+        else:
+            frames = np.ascontiguousarray(frames)
+        for a in range(0, n, ctx.max_batch):
+            b = min(a + ctx.max_batch, n)
+            sid = None if stream_id is None else stream_id[a:b]
+            if on_device:
+                ptr = frames.data_ptr() + a * h * w * 3
+                chunks.append(ctx.detect(ptr, b - a, True, sid, n_streams, prev_fit, prev_valid, s, oms))
+            else:
+                chunks.append(ctx.detect(frames[a:b], b - a, False, sid, n_streams, prev_fit, prev_valid, s, oms))
+        recs = chunks[0] if len(chunks) == 1 else np.concatenate(chunks)
+        self.last_records = recs
+        return recs
+
+    def _state_arrays(self):
+        fit = np.zeros((1, 2, 3), np.float64)
+        valid = np.zeros((1, 2), np.uint8)
+        for s, p in enumerate((self.prev_left_fit, self.prev_right_fit)):
+            if p is not None:
+                fit[0, s] = np.asarray(p, dtype=np.float64)
+                valid[0, s] = 1
+        return fit, valid
+
+    # ------------------------------------------------------------------ public API
+    def detect(self, frame: np.ndarray) -> LanePair:
+        """Detect lane lines in one BGR frame (reference: lane_detector.py:178-218)."""
+        self._check_frames(frame, batched=False)
+        return self.detect_batch(frame[None])[0]
+
+    def detect_batch(self, frames) -> List[LanePair]:
+        """``frames`` uint8 [N,H,W,3] (numpy, or a CUDA torch tensor already on the device).
+
+        Semantics: identical to calling ``detect`` on ``frames[0..N-1]`` in order on this instance --
+        the temporal smoothing is carried through the batch and left in ``prev_*_fit``.
+        """
+        self._check_frames(frames, batched=True)
+        if frames.shape[0] == 0:
+            return []
+        fit, valid = self._state_arrays()
+        recs = self._run(frames, None, 1, fit, valid)
+        lanes = self._lanes_from_records(recs)
+        # like the reference (:210-216), prev_*_fit aliases the last returned polynomial of that side
+        for left, right in lanes:
+            if left is not None:
+                self.prev_left_fit = left.polynomial
+            if right is not None:
+                self.prev_right_fit = right.polynomial
+        return lanes
+
+    def detect_streams(self, frames, stream_ids: Optional[Sequence[int]] = None) -> List[LanePair]:
+        """Multi-camera form: ``frames`` is [S,T,H,W,3] (stream-major) or [N,H,W,3] with ``stream_ids[N]``.
+
+        Every stream keeps its own smoothing state inside this detector (``reset`` clears all of them);
+        frames of one stream must be in temporal order.  Returns one pair per frame, in input order.
+        """
+        if len(frames.shape) == 5:
+            s_, t_ = int(frames.shape[0]), int(frames.shape[1])
+            stream_ids = np.repeat(np.arange(s_, dtype=np.int32), t_)
+            frames = frames.reshape((s_ * t_,) + tuple(frames.shape[2:]))
+        if stream_ids is None:
+            raise ValueError("stream_ids is required for [N,H,W,3] input")
+        self._check_frames(frames, batched=True)
+        stream_ids = np.asarray(stream_ids, dtype=np.int32)
+        if stream_ids.shape != (frames.shape[0],) or (len(stream_ids) and stream_ids.min() < 0):
+            raise ValueError("stream_ids must be non-negative int32[N]")
+        if frames.shape[0] == 0:
+            return []
+        n_streams = int(stream_ids.max()) + 1
+        if self._stream_fit is None or self._stream_fit.shape[0] < n_streams:
+            fit = np.zeros((n_streams, 2, 3), np.float64)
+            valid = np.zeros((n_streams, 2), np.uint8)
+            if self._stream_fit is not None:
+                k = self._stream_fit.shape[0]
+                fit[:k], valid[:k] = self._stream_fit, self._stream_valid
+            self._stream_fit, self._stream_valid = fit, valid
+        recs = self._run(frames, stream_ids, self._stream_fit.shape[0], self._stream_fit, self._stream_valid)
+        return self._lanes_from_records(recs)
+
+    def draw_lanes(self, frame: np.ndarray, left_lane: Optional[LaneLine], right_lane: Optional[LaneLine],
+                   fill_lane: bool = True) -> np.ndarray:
+        """Overlay rendering, kept on the CPU with cv2 as in the reference (lane_detector.py:220-251):
+        translucent fill between the lanes, then the two polylines (blue left, red right)."""
+        if fill_lane and left_lane is not None and right_lane is not None:
+            filled = frame.copy()
+            outline = np.vstack([left_lane.points, right_lane.points[::-1]])
+            cv2.fillPoly(filled, [outline], (0, 255, 100))
+            frame = cv2.addWeighted(frame, 0.7, filled, 0.3, 0)
+        for lane, colour in ((left_lane, (255, 0, 0)), (right_lane, (0, 0, 255))):
+            if lane is not None:
+                cv2.polylines(frame, [lane.points], False, colour, 3)
+        return frame
+
+    def get_lane_center_offset(self, frame_width: int, left_lane: Optional[LaneLine],
+                               right_lane: Optional[LaneLine]) -> Optional[float]:
+        """Vehicle offset from the lane centre in px, None unless both lanes exist
+        (reference: lane_detector.py:253-272; the x positions are the last sample points)."""
+        if left_lane is None or right_lane is None:
+            return None
+        lane_center = (left_lane.points[-1, 0] + right_lane.points[-1, 0]) / 2
+        return frame_width / 2 - lane_center
+
+    def reset(self):
+        """Reset lane tracking state (reference: lane_detector.py:274-277)."""
+        self.prev_left_fit = None
+        self.prev_right_fit = None
+        self._stream_fit = None
+        self._stream_valid = None
+
+    def close(self):
+        if self._ctx is not None:
+            self._ctx.close()
+            self._ctx = None

@@ -1,0 +1,290 @@
+"""Parity of the CUDA path (through the C ABI) against the oracle and the reference goldens.
+
+Run on the B200 box: python -m pytest tests -m gpu.  Nothing here reads /root/reference.
+Bars: integer/byte/index stages bit-exact (blur, histogram, thresholds, NMS classes, Canny map,
+ROI point list, HoughLinesP segments, standard-Hough accumulator and peaks); fp64 tail within
+1e-3 relative on coefficients (atol for the mathematically-zero ones), <= 1e-6 px on the
+evaluated lane x positions, sample points within 1 px of the reference's truncated ints.
+"""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+import cv2  # noqa: E402
+
+from cases import CUSTOM_ROI, build_cases, custom_roi_frames  # noqa: E402
+from multimodal_autonomous_driving_perception_and_planning_b200 import (  # noqa: E402
+    LaneDetector, SyntheticDataGenerator, _native)
+from oracle import stages as S  # noqa: E402
+from oracle.cv2_pipeline import Cv2LaneOracle  # noqa: E402
+from util import gen_frames, golden, h16, lines_of, unpack_edges  # noqa: E402
+
+COEF_RTOL = 1e-3       # north_star: "within 1e-3 relative (or 0.5 px)"
+X_ATOL_PX = 1e-6
+
+
+def _sample_rows(h):
+    return np.linspace(h * 0.6, h, 50)
+
+
+def _check_side(rec_side, want_coeffs, want_points, want_conf, h):
+    got = rec_side["coeffs"]
+    xs_got = np.polyval(got, _sample_rows(h))
+    xs_want = np.polyval(want_coeffs, _sample_rows(h))
+    assert np.abs(xs_got - xs_want).max() <= X_ATOL_PX * max(1.0, np.abs(xs_want).max())
+    scale = np.abs(want_coeffs) + np.array([1e-9, 1e-6, 1e-3])   # zero quadratic terms come back as 1e-15 noise
+    assert (np.abs(got - want_coeffs) / scale).max() <= COEF_RTOL
+    assert np.abs(rec_side["points"].astype(np.int64) - want_points).max() <= 1
+    assert rec_side["confidence"] == want_conf
+
+
+def _run_stage_checks(frames, roi=None, hough=False):
+    """Every tap of every frame against the stage oracle (bit-exact), records against its fits."""
+    h, w = frames[0].shape[:2]
+    det = LaneDetector(roi, max_batch=len(frames), debug=True)
+    lanes = det.detect_batch(np.stack(frames))
+    recs, ctx = det.last_records, det._ctx
+    so = S.StageOracle(roi_vertices=roi)
+    for i, f in enumerate(frames):
+        tr = so.step(f)
+        assert np.array_equal(ctx.tap(_native.TAP_GRAY, i), tr.gray), i
+        assert np.array_equal(ctx.tap(_native.TAP_BLUR, i), tr.blurred), i
+        assert np.array_equal(ctx.tap(_native.TAP_HIST, i), S.hist256(tr.blurred)), i
+        assert (recs[i]["median_x2"], recs[i]["low"], recs[i]["high"]) == (tr.median_x2, tr.low, tr.high), i
+        assert np.array_equal(ctx.tap(_native.TAP_CLASS, i), tr.canny.cls), i
+        edges = ctx.tap(_native.TAP_EDGES, i)
+        assert np.array_equal(edges, tr.canny.edges), i
+        assert recs[i]["n_edges"] == int((tr.canny.edges != 0).sum())
+        ys, xs = np.nonzero(tr.masked)
+        assert recs[i]["n_roi_points"] == len(xs)
+        if len(xs):
+            assert np.array_equal(ctx.tap(_native.TAP_POINTS, i), np.stack([xs, ys], 1).astype(np.int32)), i
+        assert recs[i]["n_segments"] == len(tr.lines), (i, recs[i]["n_segments"], len(tr.lines))
+        assert np.array_equal(ctx.tap(_native.TAP_SEGMENTS, i), tr.lines), i
+        for s, fit in enumerate((tr.left, tr.right)):
+            assert bool(recs[i]["side"][s]["valid"]) == (fit is not None), (i, s)
+            assert (lanes[i][s] is None) == (fit is None)
+            if fit is not None:
+                _check_side(recs[i]["side"][s], fit.coeffs, fit.points, fit.confidence, h)
+                assert recs[i]["side"][s]["n_lines"] == fit.n_lines
+        assert bool(recs[i]["offset_valid"]) == (tr.offset is not None)
+        if tr.offset is not None:
+            assert abs(recs[i]["offset"] - tr.offset) <= 0.5
+        if hough:
+            acc, peaks, found = ctx.hough_accumulator(i, threshold=5, max_peaks=1 << 16)
+            want = S.hough_accum(tr.masked)
+            assert np.array_equal(acc, want), i
+            assert np.array_equal(peaks, S.hough_peaks(want, h, w, 5)), i
+    det.close()
+    return recs
+
+
+def test_stage_taps_generator_640x480():
+    _run_stage_checks(gen_frames(640, 480, 6), hough=True)
+
+
+@pytest.mark.parametrize("shape", [(7, 9), (5, 5), (3, 3), (33, 65), (64, 64), (481, 643), (240, 320)])
+def test_stage_taps_noise(shape):
+    rng = np.random.default_rng(shape[0] * 1000 + shape[1])
+    frames = [rng.integers(0, 256, shape + (3,), dtype=np.uint8) for _ in range(2)]
+    _run_stage_checks(frames, hough=shape[0] >= 33)
+
+
+def test_stage_taps_smooth_black_white_lines():
+    rng = np.random.default_rng(11)
+    smooth = cv2.GaussianBlur(rng.integers(0, 256, (300, 400, 3), dtype=np.uint8), (31, 31), 0)
+    lines = np.zeros((300, 400, 3), np.uint8)
+    for _ in range(30):
+        p = rng.integers(0, 400, 4)
+        cv2.line(lines, (int(p[0]), int(p[1] % 300)), (int(p[2]), int(p[3] % 300)),
+                 tuple(int(v) for v in rng.integers(60, 256, 3)), int(rng.integers(1, 4)))
+    _run_stage_checks([smooth, np.zeros((300, 400, 3), np.uint8), np.full((300, 400, 3), 255, np.uint8), lines],
+                      hough=True)
+
+
+def test_edge_cases_against_oracle_and_golden():
+    for name, frames in build_cases(SyntheticDataGenerator).items():
+        recs = _run_stage_checks(frames)
+        gold = golden("case_" + name)
+        for i in range(len(frames)):
+            assert recs[i]["n_edges"] == gold["n_edges"][i] and recs[i]["n_roi_points"] == gold["n_roi"][i], name
+            assert np.array_equal(recs[i]["side"]["valid"], gold["valid"][i]), name
+
+
+def test_custom_roi():
+    frames = custom_roi_frames(SyntheticDataGenerator)
+    recs = _run_stage_checks(frames, roi=CUSTOM_ROI, hough=True)
+    gold = golden("case_custom_roi")
+    assert [r["n_roi_points"] for r in recs] == list(gold["n_roi"])
+
+
+def _check_against_golden(frames, gold, max_batch):
+    h, w = frames[0].shape[:2]
+    det = LaneDetector(max_batch=max_batch, debug=True)
+    lanes = det.detect_batch(np.stack(frames))
+    recs = det.last_records
+    exact_points = 0
+    total_points = 0
+    for i in range(len(frames)):
+        assert (recs[i]["median_x2"], recs[i]["low"], recs[i]["high"]) == \
+            (gold["median_x2"][i], gold["low"][i], gold["high"][i])
+        assert recs[i]["n_edges"] == gold["n_edges"][i] and recs[i]["n_roi_points"] == gold["n_roi"][i]
+        assert recs[i]["n_segments"] == len(lines_of(gold, i))
+        for s in (0, 1):
+            assert bool(recs[i]["side"][s]["valid"]) == bool(gold["valid"][i, s])
+            if gold["valid"][i, s]:
+                _check_side(recs[i]["side"][s], gold["poly"][i, s], gold["points"][i, s], gold["conf"][i, s], h)
+                exact_points += int((lanes[i][s].points == gold["points"][i, s]).all())
+                total_points += 1
+        off = det.get_lane_center_offset(w, *lanes[i])
+        assert (off is None) == bool(np.isnan(gold["offset"][i]))
+        if off is not None:
+            assert abs(off - gold["offset"][i]) <= 0.5
+    assert exact_points >= 0.99 * total_points
+    return det, recs
+
+
+def test_config1_300_frames_vs_reference_golden():
+    """BASELINE config 1: the demo's 300-frame 640x480 sequence, one stream, EMA carried through."""
+    gold = golden("config1_640x480")
+    frames = gen_frames(640, 480, 300)
+    det, recs = _check_against_golden(frames, gold, max_batch=300)
+    ctx = det._ctx
+    for i in range(0, 300, 7):
+        assert h16(ctx.tap(_native.TAP_BLUR, i)) == str(gold["blur_hash"][i])
+        assert h16(ctx.tap(_native.TAP_EDGES, i)) == str(gold["edge_hash"][i])
+        assert np.array_equal(ctx.tap(_native.TAP_SEGMENTS, i), lines_of(gold, i))
+    det.close()
+
+
+@pytest.mark.parametrize("name,w,h,n,start", [("hd1080_cam0", 1920, 1080, 4, 0), ("hd1080_cam1", 1920, 1080, 2, 1000),
+                                               ("hd720", 1280, 720, 2, 0), ("uhd2160", 3840, 2160, 1, 0)])
+def test_larger_resolutions_vs_reference_golden(name, w, h, n, start):
+    gold = golden(name)
+    frames = gen_frames(w, h, n, start)
+    det, recs = _check_against_golden(frames, gold, max_batch=n)
+    for i in range(n):
+        assert np.array_equal(det._ctx.tap(_native.TAP_EDGES, i), unpack_edges(gold["edges_packed"][i], h, w))
+        assert np.array_equal(det._ctx.tap(_native.TAP_SEGMENTS, i), lines_of(gold, i))
+    acc, peaks, found = det._ctx.hough_accumulator(0, threshold=50, max_peaks=4096)
+    masked = unpack_edges(gold["edges_packed"][0], h, w) & S.roi_mask(h, w)
+    want = S.hough_accum(masked)
+    assert np.array_equal(acc, want)
+    assert np.array_equal(peaks, S.hough_peaks(want, h, w, 50))
+    det.close()
+
+
+def test_detect_equals_detect_batch_and_chunking():
+    frames = gen_frames(640, 480, 24)
+    a = LaneDetector(max_batch=24)
+    b = LaneDetector(max_batch=5)      # forces chunked native calls
+    c = LaneDetector()
+    la = a.detect_batch(np.stack(frames))
+    lb = b.detect_batch(np.stack(frames))
+    lc = [c.detect(f) for f in frames]
+    for x, y, z in zip(la, lb, lc):
+        for s in (0, 1):
+            assert (x[s] is None) == (y[s] is None) == (z[s] is None)
+            if x[s] is not None:
+                assert np.array_equal(x[s].polynomial, y[s].polynomial) and np.array_equal(x[s].polynomial, z[s].polynomial)
+                assert np.array_equal(x[s].points, z[s].points) and x[s].side == ("left", "right")[s]
+    assert np.array_equal(a.prev_left_fit, c.prev_left_fit) and c.prev_left_fit is lc[-1][0].polynomial
+    for d in (a, b, c):
+        d.close()
+
+
+def test_state_semantics_hit_miss_hit_and_reset():
+    """a miss keeps prev_*_fit; the next hit is smoothed against it; reset clears it."""
+    g = SyntheticDataGenerator()
+    f0 = g.generate_frame_with_vehicles()
+    f1 = g.generate_frame_with_vehicles()
+    det = LaneDetector()
+    l0, r0 = det.detect(f0)
+    assert l0 is not None and r0 is not None
+    keep = det.prev_left_fit.copy()
+    assert det.detect(np.zeros_like(f0)) == (None, None)
+    assert np.array_equal(det.prev_left_fit, keep)
+    l1, _ = det.detect(f1)
+    raw = det.last_records[0]["side"][0]["raw"]
+    assert np.array_equal(l1.polynomial, 0.7 * keep + (1 - 0.7) * raw)
+    det.reset()
+    assert det.prev_left_fit is None and det.prev_right_fit is None
+    l2, _ = det.detect(f1)
+    assert np.array_equal(l2.polynomial, det.last_records[0]["side"][0]["raw"])   # first hit is unsmoothed
+    assert det.get_lane_center_offset(640, l2, None) is None
+    # input untouched, non-contiguous view accepted
+    view = np.ascontiguousarray(np.repeat(f0, 2, axis=1))[:, ::2]
+    before = view.copy()
+    det.reset()
+    lv, _ = det.detect(view)
+    assert np.array_equal(view, before) and np.array_equal(lv.polynomial, l0.polynomial)
+    det.close()
+
+
+def test_error_behaviour_matches_reference():
+    det = LaneDetector()
+    with pytest.raises(cv2.error):
+        det.detect(np.zeros((48, 64, 3), np.float32))
+    with pytest.raises(cv2.error):
+        det.detect(np.zeros((48, 64), np.uint8))
+    with pytest.raises(cv2.error):
+        det.detect_batch(np.zeros((2, 48, 64, 1), np.uint8))
+    assert det.detect_batch(np.zeros((0, 48, 64, 3), np.uint8)) == []
+
+
+def test_streams_equal_independent_detectors():
+    """Config 3 semantics at small scale: S cameras interleaved, each with its own EMA."""
+    from multimodal_autonomous_driving_perception_and_planning_b200 import multi_camera_batch
+    batch = multi_camera_batch(3, 5, 640, 480)
+    det = LaneDetector(max_batch=16)
+    got = det.detect_streams(batch)
+    # interleaved order with explicit ids must give the same per-frame answers
+    order = np.array([s * 5 + t for t in range(5) for s in range(3)])
+    det2 = LaneDetector(max_batch=4)
+    got2 = det2.detect_streams(batch.reshape(15, 480, 640, 3)[order], stream_ids=order // 5)
+    for s in range(3):
+        ref = Cv2LaneOracle()
+        for t in range(5):
+            lf, rf = ref.detect(batch[s, t])
+            for side, fit in enumerate((lf, rf)):
+                lane = got[s * 5 + t][side]
+                lane2 = got2[int(np.nonzero(order == s * 5 + t)[0][0])][side]
+                assert (lane is None) == (fit is None) == (lane2 is None)
+                if fit is not None:
+                    assert np.array_equal(lane.polynomial, lane2.polynomial)
+                    assert np.abs(np.polyval(lane.polynomial, _sample_rows(480)) -
+                                  np.polyval(fit.coeffs, _sample_rows(480))).max() < 1e-6
+    det.close(); det2.close()
+
+
+def test_torch_cuda_input_matches_host_input():
+    import torch
+    frames = np.stack(gen_frames(640, 480, 4))
+    a = LaneDetector(max_batch=4).detect_batch(frames)
+    b = LaneDetector(max_batch=4).detect_batch(torch.from_numpy(frames).cuda())
+    for x, y in zip(a, b):
+        for s in (0, 1):
+            assert np.array_equal(x[s].polynomial, y[s].polynomial)
+
+
+def test_config2_full_size_properties():
+    """BASELINE config 2 at full size (256 x 1080p on one GPU): size-independent properties.
+    The batch tiles 8 distinct frames, so per-frame (pre-EMA) results must repeat with period 8,
+    must equal the golden for frames 0..3, and the edge count must equal a popcount of the map."""
+    from multimodal_autonomous_driving_perception_and_planning_b200 import multi_camera_batch
+    batch = multi_camera_batch(1, 256, 1920, 1080, period=8)[0]
+    det = LaneDetector(max_batch=256, debug=False)
+    det.detect_batch(batch)
+    recs = det.last_records
+    gold = golden("hd1080_cam0")
+    for k in ("median_x2", "low", "high", "n_edges", "n_roi_points", "n_segments"):
+        assert np.array_equal(recs[k], np.tile(recs[k][:8], 32)), k
+    assert np.array_equal(recs["side"]["raw"], np.tile(recs["side"]["raw"][:8], (32, 1, 1)))
+    assert np.array_equal(recs["n_edges"][:4], gold["n_edges"]) and np.array_equal(recs["n_roi_points"][:4], gold["n_roi"])
+    for i in (0, 100, 255):
+        e = det._ctx.tap(_native.TAP_EDGES, i)
+        assert int((e != 0).sum()) == recs[i]["n_edges"] and set(np.unique(e)) <= {0, 255}
+        assert np.array_equal(e, unpack_edges(gold["edges_packed"][i % 8], 1080, 1920)) if i % 8 < 4 else True
+    assert recs["side"]["valid"].all()
+    det.close()
