@@ -135,6 +135,8 @@ def main():
     ap.add_argument("--frames", type=int, default=256, help="frames per GPU per step")
     ap.add_argument("--distinct", type=int, default=64, help="distinct generator frames per stream (tiled in time)")
     ap.add_argument("--cpu-frames", type=int, default=256, help="CPU baseline sample: frames per host core")
+    ap.add_argument("--skip-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
+    ap.add_argument("--skip-e2e", action="store_true", help="skip the e2e leg (profiling runs)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -172,7 +174,7 @@ def main():
 
     # ---------------------------------------------------------------- CPU baseline first (before CUDA init)
     cpu_baseline = None
-    if rank == 0 and args.gpus == 1:
+    if rank == 0 and args.gpus == 1 and not args.skip_cpu:
         fps, cores, total, slowest = cpu_reference_fps(args.cpu_frames)
         cpu_baseline = {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port",
                         "sample": f"{total} frames ({args.cpu_frames} per core x {cores} processes, cv2 threads=1 each) "
@@ -259,20 +261,22 @@ def main():
     # ---- e2e: public API with host (pinned) frames, H2D + records D2H inside the timed region
     host_frames = pinned.numpy()
     det.reset()
-    for _ in range(2):
+    off = None
+    e2e_steps = 0 if args.skip_e2e else args.steps
+    for _ in range(2 if e2e_steps else 0):
         det.detect_batch(host_frames)
     barrier()
     t2 = time.perf_counter()
-    for _ in range(args.steps):
+    for _ in range(e2e_steps):
         lanes = det.detect_batch(host_frames)
         off = det.get_lane_center_offset(W, *lanes[-1])
     barrier()
-    e2e_s = time.perf_counter() - t2
+    e2e_s = max(time.perf_counter() - t2, 1e-9)
     if world > 1:
         tm = torch.tensor([e2e_s], device=dev)
         dist.all_reduce(tm, op=dist.ReduceOp.MAX)
         e2e_s = float(tm.item())
-    e2e_val = args.gpus * n * args.steps / e2e_s
+    e2e_val = args.gpus * n * e2e_steps / e2e_s
 
     if rank == 0:
         peaks = {}
