@@ -61,6 +61,191 @@ __global__ void __launch_bounds__(NT) k1_tile(const uint8_t *__restrict__ frames
     if (lh[tid]) atomicAdd(&hist[f * 256 + tid], lh[tid]);
 }
 
+// ---------------------------------------------------------------------------------------------
+// Strip kernel (W % 16 == 0, 16-byte aligned frames): the HBM-roofline path.
+//
+// One warp owns a column strip of 512 pixels (16 px per lane: three 16-byte loads per lane per row)
+// and rolls down a band of rows keeping everything in registers:
+//   gray    : 2 IDP2A per pixel straight off the interleaved BGR words (Q16 coefficients = 2x the Q15
+//             ones, so the rounded result lands byte-aligned), packed as u16x2 pairs
+//   vertical: [1 4 6 4 1] as four chained pair-adds ([1 1]^4) on packed u16x2 (max 4080, carry-free)
+//   horizontal: neighbours' edge pairs by two shuffles, odd alignments by PRMT, u16x2 arithmetic
+//             (max 65408, carry-free), +128 >> 8 folded into the final byte pick (PRMT)
+//   store   : one 16-byte store per lane per row
+//   histogram: per-lane private byte counters in shared memory (no atomics, conflict-free in smooth
+//             regions), flushed every 15 rows into per-lane registers, one RED per bin per task
+// Lanes 0 and 31 only provide the 2-px halo (30 x 16 = 480 output px per warp); image borders are
+// REFLECT_101 on register pairs (columns) and on the row index (rows).  Warps pull (frame, band,
+// strip) tasks from a global counter, so the grid is persistent and there is no tail.
+constexpr int SPX = 16;                 // pixels per lane
+constexpr int STRIP_OUT = 30 * SPX;     // 480 output pixels per warp
+constexpr int SWARPS = 4;               // warps per CTA
+constexpr int FLUSH_ROWS = 15;          // 15 rows x 16 px = 240 < 256 increments per byte counter
+
+__device__ __forceinline__ uint32_t dp2a_lo(uint32_t a, uint32_t b, uint32_t c)
+{
+    uint32_t d;
+    asm("dp2a.lo.u32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+__device__ __forceinline__ uint32_t dp2a_hi(uint32_t a, uint32_t b, uint32_t c)
+{
+    uint32_t d;
+    asm("dp2a.hi.u32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+__device__ __forceinline__ uint4 ldg_stream(const uint4 *p)
+{
+    uint4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+    return r;
+}
+
+// 16 interleaved BGR pixels (12 words) -> 8 packed u16x2 gray pairs
+__device__ __forceinline__ void gray16(const uint32_t (&w)[12], uint32_t (&g)[8])
+{
+    constexpr uint32_t CB = 2 * 3735, CG = 2 * 19235, CR = 2 * 9798, RND = 1u << 15;
+    constexpr uint32_t KBG = CB | (CG << 16), KR0 = CR, K0B = CB << 16, KGR = CG | (CR << 16);
+#pragma unroll
+    for (int q = 0; q < 4; q++) {       // 4 pixels per 3 words
+        const uint32_t w0 = w[3 * q], w1 = w[3 * q + 1], w2 = w[3 * q + 2];
+        uint32_t s0 = dp2a_hi(KR0, w0, dp2a_lo(KBG, w0, RND));   // B0 G0 R0 | .
+        uint32_t s1 = dp2a_lo(KGR, w1, dp2a_hi(K0B, w0, RND));   // . . . B1 | G1 R1
+        uint32_t s2 = dp2a_lo(KR0, w2, dp2a_hi(KBG, w1, RND));   // . . B2 G2 | R2
+        uint32_t s3 = dp2a_hi(KGR, w2, dp2a_lo(K0B, w2, RND));   // . B3 G3 R3
+        g[2 * q] = __byte_perm(s0, s1, 0x7632);                  // gray = bits 16..23 of each sum
+        g[2 * q + 1] = __byte_perm(s2, s3, 0x7632);
+    }
+}
+
+__global__ void __launch_bounds__(SWARPS * 32) k1_strip(const uint8_t *__restrict__ frames, uint8_t *__restrict__ blur,
+                                                        uint32_t *__restrict__ hist, int *__restrict__ task_counter,
+                                                        int n_frames, int H, int W, int band_rows)
+{
+    __shared__ __align__(16) uint8_t s_hist[SWARPS][256 * 32];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    uint8_t *wh = s_hist[wid];
+    {   // zero this warp's private counters
+        uint4 *z = reinterpret_cast<uint4 *>(wh);
+        for (int i = lane; i < 256 * 32 / 16; i += 32) z[i] = make_uint4(0, 0, 0, 0);
+    }
+    __syncwarp();
+    const int n_strips = (W + STRIP_OUT - 1) / STRIP_OUT;
+    const int n_bands = (H + band_rows - 1) / band_rows;
+    const int n_tasks = n_frames * n_bands * n_strips;
+    const size_t frame_px = (size_t)H * W;
+
+    for (;;) {
+        int task = 0;
+        if (lane == 0) task = atomicAdd(task_counter, 1);
+        task = __shfl_sync(0xffffffffu, task, 0);
+        if (task >= n_tasks) break;
+        const int strip = task % n_strips;
+        const int band = (task / n_strips) % n_bands;
+        const int f = task / (n_strips * n_bands);
+        const int r0 = band * band_rows, r1 = min(r0 + band_rows, H);
+        const int xl = strip * STRIP_OUT - SPX + SPX * lane;          // first pixel of this lane
+        const bool in_img = xl >= 0 && xl < W;
+        const bool is_out = in_img && lane >= 1 && lane <= 30;
+        const bool left_edge = xl == 0, right_edge = xl + SPX == W;
+        const uint8_t *src = frames + f * frame_px * 3 + (size_t)max(xl, 0) * 3;
+        uint8_t *dst = blur + f * frame_px + max(xl, 0);
+
+        uint32_t p1[8], p2[8], p3[8], p4[8];
+#pragma unroll
+        for (int j = 0; j < 8; j++) p1[j] = p2[j] = p3[j] = p4[j] = 0;
+        uint32_t tot[8];
+#pragma unroll
+        for (int b = 0; b < 8; b++) tot[b] = 0;
+        int since_flush = 0;
+
+        auto flush = [&]() {
+            __syncwarp();
+#pragma unroll
+            for (int b = 0; b < 8; b++) {
+                uint4 *row = reinterpret_cast<uint4 *>(wh + (b * 32 + lane) * 32);
+                uint4 a = row[0], c = row[1];
+                uint32_t s = 0;
+                s = __dp4a(a.x, 0x01010101u, s); s = __dp4a(a.y, 0x01010101u, s);
+                s = __dp4a(a.z, 0x01010101u, s); s = __dp4a(a.w, 0x01010101u, s);
+                s = __dp4a(c.x, 0x01010101u, s); s = __dp4a(c.y, 0x01010101u, s);
+                s = __dp4a(c.z, 0x01010101u, s); s = __dp4a(c.w, 0x01010101u, s);
+                tot[b] += s;
+                row[0] = make_uint4(0, 0, 0, 0); row[1] = make_uint4(0, 0, 0, 0);
+            }
+            __syncwarp();
+        };
+
+        uint32_t w[12];
+        auto load_row = [&](int y) {
+            const int yy = fold101(y, H);
+            if (in_img) {
+                const uint4 *p = reinterpret_cast<const uint4 *>(src + (size_t)yy * W * 3);
+                uint4 a = ldg_stream(p), b = ldg_stream(p + 1), c = ldg_stream(p + 2);
+                w[0] = a.x; w[1] = a.y; w[2] = a.z; w[3] = a.w; w[4] = b.x; w[5] = b.y; w[6] = b.z; w[7] = b.w;
+                w[8] = c.x; w[9] = c.y; w[10] = c.z; w[11] = c.w;
+            }
+        };
+#pragma unroll
+        for (int j = 0; j < 12; j++) w[j] = 0;
+        load_row(r0 - 2);
+        for (int y = r0 - 2; y < r1 + 2; y++) {
+            uint32_t g[8];
+            gray16(w, g);
+            if (y + 1 < r1 + 2) load_row(y + 1);        // prefetch the next row behind the arithmetic
+            uint32_t V[8];
+#pragma unroll
+            for (int j = 0; j < 8; j++) {               // [1 1]^4 down the column
+                uint32_t t1 = g[j] + p1[j]; p1[j] = g[j];
+                uint32_t t2 = t1 + p2[j];   p2[j] = t1;
+                uint32_t t3 = t2 + p3[j];   p3[j] = t2;
+                V[j] = t3 + p4[j];          p4[j] = t3;
+            }
+            if (y < r0 + 2) continue;                    // pipeline fill: V is the blur column sum of row y-2
+            const int yo = y - 2;
+            uint32_t L7 = __shfl_up_sync(0xffffffffu, V[7], 1);
+            uint32_t R0 = __shfl_down_sync(0xffffffffu, V[0], 1);
+            if (left_edge) L7 = __byte_perm(V[1], V[0], 0x7610);     // (x=-2,-1) := (x=2, 1)
+            if (right_edge) R0 = __byte_perm(V[7], V[6], 0x7610);    // (x=W, W+1) := (x=W-2, W-3)
+            uint32_t O[9];
+            O[0] = __byte_perm(L7, V[0], 0x5432);
+#pragma unroll
+            for (int j = 1; j < 8; j++) O[j] = __byte_perm(V[j - 1], V[j], 0x5432);
+            O[8] = __byte_perm(V[7], R0, 0x5432);
+            uint32_t Hs[8];
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                const uint32_t vm = j == 0 ? L7 : V[j - 1], vp = j == 7 ? R0 : V[j + 1];
+                Hs[j] = vm + vp + 0x00800080u + 4u * (O[j] + O[j + 1]) + 6u * V[j];
+            }
+            uint4 o;
+            o.x = __byte_perm(Hs[0], Hs[1], 0x7531);
+            o.y = __byte_perm(Hs[2], Hs[3], 0x7531);
+            o.z = __byte_perm(Hs[4], Hs[5], 0x7531);
+            o.w = __byte_perm(Hs[6], Hs[7], 0x7531);
+            if (is_out) {
+                *reinterpret_cast<uint4 *>(dst + (size_t)yo * W) = o;
+                uint8_t *hp = wh + lane;
+                const uint32_t ow[4] = {o.x, o.y, o.z, o.w};
+#pragma unroll
+                for (int q = 0; q < 4; q++) {
+#pragma unroll
+                    for (int k = 0; k < 4; k++) {
+                        uint32_t v = (ow[q] >> (8 * k)) & 0xFFu;
+                        hp[v * 32] += 1;
+                    }
+                }
+            }
+            if (++since_flush == FLUSH_ROWS) { flush(); since_flush = 0; }
+        }
+        flush();
+#pragma unroll
+        for (int b = 0; b < 8; b++)
+            if (tot[b]) atomicAdd(&hist[f * 256 + b * 32 + lane], tot[b]);
+    }
+}
+
 __global__ void k_gray(const uint8_t *__restrict__ frame, uint8_t *__restrict__ gray, int n)
 {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -70,11 +255,24 @@ __global__ void k_gray(const uint8_t *__restrict__ frame, uint8_t *__restrict__ 
 }  // namespace
 
 void launch_blur_hist(const uint8_t *frames, uint8_t *blur, uint32_t *hist, int n, int H, int W,
-                      cudaStream_t st, int *launches)
+                      cudaStream_t st, int *launches, int *task_counter, int force_tile)
 {
     cudaMemsetAsync(hist, 0, sizeof(uint32_t) * 256 * n, st);
-    dim3 grid((W + TW - 1) / TW, (H + TH - 1) / TH, n);
-    k1_tile<<<grid, NT, 0, st>>>(frames, blur, hist, H, W);
+    const bool aligned = (W % 16 == 0) && (((uintptr_t)frames | (uintptr_t)blur) % 16 == 0);
+    if (aligned && !force_tile) {
+        static int sms = 0;
+        if (!sms) {
+            int dev = 0;
+            cudaGetDevice(&dev);
+            cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        }
+        const int band_rows = H >= 540 ? 135 : (H >= 120 ? 60 : H);
+        cudaMemsetAsync(task_counter, 0, sizeof(int), st);
+        k1_strip<<<sms * 5, SWARPS * 32, 0, st>>>(frames, blur, hist, task_counter, n, H, W, band_rows);
+    } else {
+        dim3 grid((W + TW - 1) / TW, (H + TH - 1) / TH, n);
+        k1_tile<<<grid, NT, 0, st>>>(frames, blur, hist, H, W);
+    }
     *launches += 1;
 }
 

@@ -46,6 +46,8 @@ struct lane_ctx {
     int32_t *d_std_accum = nullptr;
     int2 *d_peaks = nullptr;
     int *d_n_peaks = nullptr;
+    int *d_task_counter = nullptr;
+    int force_tile = 0;               // LANE_B200_K1=tile forces the generic K1 kernel (A/B checks)
     int peaks_cap = 0;
 
     // last call
@@ -92,7 +94,7 @@ void free_all(lane_ctx *c)
                     c->d_points, c->d_points_dbg, c->d_lut, c->d_thr, c->d_seedsA, c->d_seedsB, c->d_seed_count,
                     c->d_n_edges, c->d_n_points, c->d_rounds, c->d_n_lines, c->d_accum, c->d_lines, c->fit.raw,
                     c->fit.side_n, c->fit.side_flags, c->d_stream_id, c->d_prev_fit, c->d_prev_valid,
-                    c->d_records, c->d_std_accum, c->d_peaks, c->d_n_peaks};
+                    c->d_records, c->d_std_accum, c->d_peaks, c->d_n_peaks, c->d_task_counter};
     for (void *p : ptrs)
         if (p) cudaFree(p);
     if (c->h_records) cudaFreeHost(c->h_records);
@@ -142,7 +144,8 @@ int enqueue(lane_ctx *c, const uint8_t *frames_dev, int n, const int32_t *stream
     CU(cudaMemcpyAsync(c->d_prev_valid, c->h_prev_valid, (size_t)S * 2, cudaMemcpyHostToDevice, c->st));
 
     rc = mark(c, LANE_STAGE_BLUR_HIST); if (rc) return rc;
-    launch_blur_hist(frames_dev, c->d_blur, c->d_hist, n, H, W, c->st, &L[LANE_STAGE_BLUR_HIST]);
+    launch_blur_hist(frames_dev, c->d_blur, c->d_hist, n, H, W, c->st, &L[LANE_STAGE_BLUR_HIST], c->d_task_counter,
+                     c->force_tile);
 
     rc = mark(c, LANE_STAGE_CANNY); if (rc) return rc;
     launch_thresholds(c->d_hist, c->d_lut, c->d_lut + 511, c->d_thr, n, H, W, c->st, &L[LANE_STAGE_CANNY]);
@@ -260,6 +263,11 @@ int lane_ctx_create(int device, int height, int width, int max_batch, int max_se
     CUB(dalloc(&ctx->fit.side_flags, B));
     CUB(dalloc(&ctx->d_stream_id, B));
     CUB(dalloc(&ctx->d_records, B));
+    CUB(dalloc(&ctx->d_task_counter, 4));
+    {
+        const char *e = getenv("LANE_B200_K1");
+        ctx->force_tile = e && !strcmp(e, "tile");
+    }
     CUB(cudaMallocHost((void **)&ctx->h_records, sizeof(lane_record) * B));
     CUB(cudaMemset(ctx->d_records, 0, sizeof(lane_record) * B));
     lane_upload_tables();

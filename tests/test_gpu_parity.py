@@ -91,6 +91,25 @@ def test_stage_taps_noise(shape):
     _run_stage_checks(frames, hough=shape[0] >= 33)
 
 
+@pytest.mark.parametrize("shape", [(16, 16), (48, 64), (135, 480), (271, 976), (137, 1936), (1080, 1920)])
+def test_k1_strip_kernel_noise(shape):
+    """K1 fast path (W % 16 == 0): blur plane, histogram and thresholds on uniform noise, every
+    strip/band/edge-lane layout (1, 2, 3 and 5 strips; partial last strip; odd band heights)."""
+    rng = np.random.default_rng(shape[0] + shape[1])
+    frames = np.stack([rng.integers(0, 256, shape + (3,), dtype=np.uint8) for _ in range(3)])
+    frames[2, :, : shape[1] // 2] = 255          # saturated half: counters and clipping
+    det = LaneDetector(max_batch=3, debug=True)
+    det.detect_batch(frames)
+    for i in range(3):
+        want = S.blur5(S.gray(frames[i]))
+        assert np.array_equal(det._ctx.tap(_native.TAP_BLUR, i), want), (shape, i)
+        assert np.array_equal(det._ctx.tap(_native.TAP_HIST, i), S.hist256(want))
+        low, high, m2 = S.thresholds(want)
+        r = det.last_records[i]
+        assert (r["median_x2"], r["low"], r["high"]) == (m2, low, high)
+    det.close()
+
+
 def test_stage_taps_smooth_black_white_lines():
     rng = np.random.default_rng(11)
     smooth = cv2.GaussianBlur(rng.integers(0, 256, (300, 400, 3), dtype=np.uint8), (31, 31), 0)
