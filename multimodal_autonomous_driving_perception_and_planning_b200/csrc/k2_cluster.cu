@@ -1,0 +1,555 @@
+// K2 (cluster form): thresholds + Sobel + NMS + double threshold + hysteresis + ROI compaction
+// for one frame per thread-block cluster, bit-planes in (distributed) shared memory.
+//
+// Replaces np.median/low/high (lane_detector.py:79-81), cv2.Canny (:83), the ROI mask (:86-90) and the
+// row-major nzloc scan of cv2.HoughLinesP (:94); arithmetic per SURVEY.md A.3/A.4.
+//
+//   cluster = G CTAs, CTA r owns a band of rows.  Per CTA:
+//   phase 1  warps roll down 512-px column strips of the blurred plane (one 16-byte load per lane per
+//            row).  Sobel and |dx|+|dy| run as packed f16x2 on the zero-interleaved bytes: every value
+//            is an integer below 2048 in units of 2^-24, which binary16 (denormals included) holds
+//            exactly and whose bit pattern IS the integer, so the result is bit-exact integer math at
+//            two pixels per instruction.  Only pixels whose magnitude beats `low` (sparse) take the
+//            scalar sector test (TG22 fixed point) and the 3x3 non-maximum test.  Candidate / strong
+//            bits leave the registers as 32-px words into two bit-planes C and S in shared memory.
+//   phase 2  hysteresis = S <- closure of S inside C under 8-connectivity: word-parallel dilation
+//            (32 px per op), in-word flood by carry propagation, column-serial sweeps down and up,
+//            __syncthreads_or convergence per CTA; bands exchange their boundary rows over DSMEM and
+//            a cluster barrier until no band saw a change.
+//   phase 3  edge bit-plane, edge count, ROI-masked bit-plane (the PPHT mask) and the row-major point
+//            list (offsets by per-row popcounts, band bases exchanged over DSMEM).
+#include <cooperative_groups.h>
+
+#include "lane_common.cuh"
+
+namespace cg = cooperative_groups;
+
+namespace {
+
+constexpr int K2T = 256;
+constexpr int SPX = 16;
+constexpr int STRIP_OUT = 30 * SPX;
+
+struct K2Args {
+    const uint8_t *blur;
+    const uint32_t *hist;
+    const uint8_t *lut_low, *lut_high;
+    const uint32_t *roi_bits;      // [H][WW]
+    int4 *thr;
+    int *n_edges, *rounds, *n_points;
+    uint32_t *points;              // [n][max_points]
+    uint32_t *pmask_bits;          // [n][bh][WW]
+    uint32_t *edge_bits;           // [n][H][WW]
+    uint32_t *dbg_c, *dbg_s;       // optional pre-hysteresis planes [n][H][WW]
+    int H, W, WW, R;               // R = rows per band
+    LaneGeom g;
+};
+
+__device__ __forceinline__ uint32_t h2add(uint32_t a, uint32_t b)
+{
+    uint32_t d;
+    asm("add.f16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b));
+    return d;
+}
+__device__ __forceinline__ uint32_t h2sub(uint32_t a, uint32_t b)
+{
+    uint32_t d;
+    asm("sub.f16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b));
+    return d;
+}
+__device__ __forceinline__ uint32_t h2fma2(uint32_t a, uint32_t b)   // 2*a + b
+{
+    uint32_t d;
+    asm("fma.rn.f16x2 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(0x40004000u), "r"(b));
+    return d;
+}
+__device__ __forceinline__ uint32_t h2max(uint32_t a, uint32_t b)
+{
+    uint32_t d;
+    asm("max.f16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b));
+    return d;
+}
+
+template <int P>
+__device__ __forceinline__ int half_of(const uint32_t (&M)[8])
+{
+    return (int)((M[P >> 1] >> ((P & 1) * 16)) & 0xFFFFu);
+}
+template <int P>
+__device__ __forceinline__ int left_of(const uint32_t (&M)[8], uint32_t mL)
+{
+    if constexpr (P == 0) return (int)(mL >> 16);
+    else return half_of<P - 1>(M);
+}
+template <int P>
+__device__ __forceinline__ int right_of(const uint32_t (&M)[8], uint32_t mR)
+{
+    if constexpr (P == 15) return (int)(mR & 0xFFFFu);
+    else return half_of<P + 1>(M);
+}
+
+// sector class of one candidate pixel: 0 horizontal, 1 vertical, 2 diagonal s=+1, 3 diagonal s=-1
+template <int P>
+__device__ __forceinline__ void classify_px(const uint32_t (&M)[8], const uint32_t (&dx)[8], const uint32_t (&dy)[8],
+                                            int low, int high, uint32_t &cand, uint32_t &strong, uint32_t &cls)
+{
+    const int m = half_of<P>(M);
+    if (m > low) {
+        const uint32_t xr = dx[P >> 1] >> ((P & 1) * 16), yr = dy[P >> 1] >> ((P & 1) * 16);
+        const int a = (int)(xr & 0x7FFFu), b = (int)(yr & 0x7FFFu);
+        const int tg22x = a * 13573, ay = b << 15;
+        uint32_t c;
+        if (ay < tg22x) c = 0;
+        else if (ay > tg22x + (a << 16)) c = 1;
+        else c = 2u + (((xr ^ yr) >> 15) & 1u);
+        cand |= 1u << P;
+        cls |= c << (2 * P);
+        if (m > high) strong |= 1u << P;
+    }
+}
+
+template <int P>
+__device__ __forceinline__ void nms_px(const uint32_t (&M0)[8], const uint32_t (&M1)[8], const uint32_t (&M2)[8],
+                                       uint32_t l0, uint32_t r0, uint32_t l1, uint32_t r1, uint32_t l2, uint32_t r2,
+                                       uint32_t cand, uint32_t cls, uint32_t &keep)
+{
+    if (cand & (1u << P)) {
+        const int m = half_of<P>(M1);
+        const uint32_t c = (cls >> (2 * P)) & 3u;
+        int n1, n2;
+        bool ge;          // second comparison is >= for the axis-aligned sectors
+        if (c == 0) { n1 = left_of<P>(M1, l1); n2 = right_of<P>(M1, r1); ge = true; }
+        else if (c == 1) { n1 = half_of<P>(M0); n2 = half_of<P>(M2); ge = true; }
+        else if (c == 2) { n1 = left_of<P>(M0, l0); n2 = right_of<P>(M2, r2); ge = false; }
+        else { n1 = right_of<P>(M0, r0); n2 = left_of<P>(M2, l2); ge = false; }
+        if (m > n1 && (ge ? m >= n2 : m > n2)) keep |= 1u << P;
+    }
+}
+
+template <int P>
+struct ForPx {
+    template <typename F>
+    __device__ __forceinline__ static void run(F &&f)
+    {
+        ForPx<P - 1>::run(f);
+        f.template operator()<P>();
+    }
+};
+template <>
+struct ForPx<-1> {
+    template <typename F>
+    __device__ __forceinline__ static void run(F &&) {}
+};
+
+// median of the blurred plane (x2) from its histogram; warp-collective
+__device__ int median_x2_warp(const uint32_t *h, long long P, int lane)
+{
+    uint32_t c[8], s = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) { c[i] = h[lane * 8 + i]; s += c[i]; }
+    uint32_t inc = s;
+    for (int o = 1; o < 32; o <<= 1) {
+        uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += t;
+    }
+    const long long exc = (long long)inc - s;
+    const long long k0 = (P & 1) ? P / 2 : P / 2 - 1, k1 = P / 2;
+    int v0 = -1, v1 = -1;
+    long long run = exc;
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        run += c[i];
+        if (v0 < 0 && exc <= k0 && run > k0) v0 = lane * 8 + i;
+        if (v1 < 0 && exc <= k1 && run > k1) v1 = lane * 8 + i;
+    }
+    for (int o = 16; o; o >>= 1) {
+        v0 = max(v0, __shfl_xor_sync(0xffffffffu, v0, o));
+        v1 = max(v1, __shfl_xor_sync(0xffffffffu, v1, o));
+    }
+    return v0 + v1;
+}
+
+// phase 1 for one (strip, row range) task; writes C/S words of rows [q0,q1) into the band's planes
+__device__ void canny_rows(const K2Args &A, const uint8_t *blur_f, int strip, int q0, int q1, int b0, uint32_t *C,
+                           uint32_t *S, int lane, int low, int high)
+{
+    const int H = A.H, W = A.W, WW = A.WW;
+    const int xl = strip * STRIP_OUT - SPX + SPX * lane;
+    const bool in_img = xl >= 0 && xl < W;
+    const bool left_edge = xl == 0, right_edge = xl + SPX == W;
+    const uint8_t *src = blur_f + max(xl, 0);
+    const int word = strip * (STRIP_OUT / 32) + ((lane - 1) >> 1);
+    const bool writer = (lane & 1) && lane <= 29 && in_img && word < WW;
+
+    uint32_t B0[8], B1[8], M0[8], M1[8];
+    uint32_t l0 = 0, r0 = 0, l1 = 0, r1 = 0;
+    uint32_t cand1 = 0, strong1 = 0, cls1 = 0;
+#pragma unroll
+    for (int j = 0; j < 8; j++) B0[j] = B1[j] = M0[j] = M1[j] = 0;
+
+    auto load_pairs = [&](int y, uint32_t (&B)[8]) {
+        const int yy = min(max(y, 0), H - 1);          // BORDER_REPLICATE rows
+        uint4 v = make_uint4(0, 0, 0, 0);
+        if (in_img) v = __ldg(reinterpret_cast<const uint4 *>(src + (size_t)yy * W));
+        B[0] = __byte_perm(v.x, 0, 0x4140); B[1] = __byte_perm(v.x, 0, 0x4342);
+        B[2] = __byte_perm(v.y, 0, 0x4140); B[3] = __byte_perm(v.y, 0, 0x4342);
+        B[4] = __byte_perm(v.z, 0, 0x4140); B[5] = __byte_perm(v.z, 0, 0x4342);
+        B[6] = __byte_perm(v.w, 0, 0x4140); B[7] = __byte_perm(v.w, 0, 0x4342);
+    };
+    load_pairs(q0 - 2, B0);
+    load_pairs(q0 - 1, B1);
+
+    for (int c = q0 - 1; c <= q1; c++) {               // c = row whose gradient is formed this step
+        uint32_t B2[8];
+        load_pairs(c + 1, B2);
+        uint32_t M2[8], l2 = 0, r2 = 0, cand2 = 0, strong2 = 0, cls2 = 0;
+        const bool row_ok = c >= 0 && c < H;            // the magnitude plane has a zero border
+        {
+            uint32_t Sc[8], Dc[8];
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                Sc[j] = h2fma2(B1[j], h2add(B0[j], B2[j]));      // column [1 2 1]
+                Dc[j] = h2sub(B2[j], B0[j]);                      // column [-1 0 1]
+            }
+            uint32_t SL = __shfl_up_sync(0xffffffffu, Sc[7], 1), SR = __shfl_down_sync(0xffffffffu, Sc[0], 1);
+            uint32_t DL = __shfl_up_sync(0xffffffffu, Dc[7], 1), DR = __shfl_down_sync(0xffffffffu, Dc[0], 1);
+            if (left_edge) { SL = __byte_perm(Sc[0], 0, 0x1010); DL = __byte_perm(Dc[0], 0, 0x1010); }   // x=-1 := x=0
+            if (right_edge) { SR = __byte_perm(Sc[7], 0, 0x3232); DR = __byte_perm(Dc[7], 0, 0x3232); }  // x=W := x=W-1
+            uint32_t So[9], Do[9];
+            So[0] = __byte_perm(SL, Sc[0], 0x5432); Do[0] = __byte_perm(DL, Dc[0], 0x5432);
+#pragma unroll
+            for (int j = 1; j < 8; j++) {
+                So[j] = __byte_perm(Sc[j - 1], Sc[j], 0x5432);
+                Do[j] = __byte_perm(Dc[j - 1], Dc[j], 0x5432);
+            }
+            So[8] = __byte_perm(Sc[7], SR, 0x5432); Do[8] = __byte_perm(Dc[7], DR, 0x5432);
+            uint32_t dx[8], dy[8], mx = 0;
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                dx[j] = h2sub(So[j + 1], So[j]);
+                dy[j] = h2fma2(Dc[j], h2add(Do[j], Do[j + 1]));
+                M2[j] = h2add(dx[j] & 0x7FFF7FFFu, dy[j] & 0x7FFF7FFFu);
+                if (!(row_ok && in_img)) M2[j] = 0;
+                mx = h2max(mx, M2[j]);
+            }
+            l2 = __shfl_up_sync(0xffffffffu, M2[7], 1);
+            r2 = __shfl_down_sync(0xffffffffu, M2[0], 1);
+            if (left_edge) l2 = 0;
+            if (right_edge) r2 = 0;
+            if ((int)max(mx & 0xFFFFu, mx >> 16) > low) {       // sparse: only lanes with a candidate
+                auto f = [&]<int P>() { classify_px<P>(M2, dx, dy, low, high, cand2, strong2, cls2); };
+                ForPx<15>::run(f);
+            }
+        }
+        if (c >= q0 + 1) {                                       // NMS of row n = c-1 (rows n-1, n, n+1 in M0, M1, M2)
+            const int n = c - 1;
+            uint32_t keep = 0;
+            if (cand1) {
+                auto f = [&]<int P>() { nms_px<P>(M0, M1, M2, l0, r0, l1, r1, l2, r2, cand1, cls1, keep); };
+                ForPx<15>::run(f);
+            }
+            const uint32_t v = keep | ((keep & strong1) << 16);
+            const uint32_t o = __shfl_down_sync(0xffffffffu, v, 1);
+            if (writer) {
+                const int lr = n - b0;
+                C[lr * WW + word] = (v & 0xFFFFu) | (o << 16);
+                S[(lr + 1) * WW + word] = (v >> 16) | (o & 0xFFFF0000u);
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < 8; j++) { B0[j] = B1[j]; B1[j] = B2[j]; M0[j] = M1[j]; M1[j] = M2[j]; }
+        l0 = l1; r0 = r1; l1 = l2; r1 = r2;
+        cand1 = cand2; strong1 = strong2; cls1 = cls2;
+    }
+}
+
+// flood the seed bits of n along the runs of c (n subset of c) inside one 32-bit word
+__device__ __forceinline__ uint32_t flood_word(uint32_t n, uint32_t c)
+{
+    uint32_t up = (((c + n) ^ c) & c) | n;
+    uint32_t cr = __brev(c), ur = __brev(up);
+    uint32_t dn = (((cr + ur) ^ cr) & cr) | ur;
+    return __brev(dn);
+}
+
+__device__ __forceinline__ bool visit(const uint32_t *C, uint32_t *S, int r, int w, int WW)
+{
+    const uint32_t c = C[r * WW + w];
+    uint32_t *sp = S + (r + 1) * WW + w;
+    const uint32_t s = *sp;
+    if ((c & ~s) == 0) return false;
+    const uint32_t v = sp[-WW] | s | sp[WW];
+    uint32_t l = 0, rr = 0;
+    if (w > 0) l = sp[-WW - 1] | sp[-1] | sp[WW - 1];
+    if (w < WW - 1) rr = sp[-WW + 1] | sp[1] | sp[WW + 1];
+    const uint32_t dil = v | (v << 1) | (v >> 1) | (l >> 31) | (rr << 31);
+    uint32_t n = s | (c & dil);
+    if (n == s) return false;
+    *sp = flood_word(n, c);
+    return true;
+}
+
+__global__ void __launch_bounds__(K2T) k2_canny_cluster(K2Args A)
+{
+    extern __shared__ uint32_t smem[];
+    cg::cluster_group cluster = cg::this_cluster();
+    const int G = (int)cluster.num_blocks(), rank = (int)cluster.block_rank();
+    const int f = blockIdx.x / G;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int H = A.H, W = A.W, WW = A.WW, R = A.R;
+    const int b0 = rank * R, b1 = min(b0 + R, H), Rv = max(b1 - b0, 0);
+    uint32_t *C = smem;                         // [R][WW]
+    uint32_t *S = smem + (size_t)R * WW;        // [R+2][WW], row 0 / Rv+1 = neighbour bands
+    int *rowoff = reinterpret_cast<int *>(S + (size_t)(R + 2) * WW);   // [R+1]
+    __shared__ int s_thr[3];
+    __shared__ int s_flag, s_total, s_base, s_red[K2T / 32];
+
+    for (int i = tid; i < R * WW; i += K2T) C[i] = 0;
+    for (int i = tid; i < (R + 2) * WW; i += K2T) S[i] = 0;
+    if (wid == 0) {
+        int m2 = median_x2_warp(A.hist + f * 256, (long long)H * W, lane);
+        if (lane == 0) {
+            int lo = A.lut_low[m2], hi = A.lut_high[m2];
+            if (lo > hi) { int t = lo; lo = hi; hi = t; }
+            s_thr[0] = m2; s_thr[1] = lo; s_thr[2] = hi;
+            if (rank == 0) A.thr[f] = make_int4(m2, lo, hi, 0);
+        }
+    }
+    __syncthreads();
+    const int low = s_thr[1], high = s_thr[2];
+
+    // ---- phase 1: warps split the band into (strip, sub-band) tasks
+    {
+        const int n_strips = (W + STRIP_OUT - 1) / STRIP_OUT;
+        const int n_sub = max(1, (K2T / 32) / n_strips);
+        const int sub_rows = (Rv + n_sub - 1) / n_sub;
+        const uint8_t *blur_f = A.blur + (size_t)f * H * W;
+        for (int t = wid; t < n_strips * n_sub; t += K2T / 32) {
+            const int strip = t % n_strips, sub = t / n_strips;
+            const int q0 = b0 + sub * sub_rows, q1 = min(q0 + sub_rows, b1);
+            if (q0 < q1) canny_rows(A, blur_f, strip, q0, q1, b0, C, S, lane, low, high);
+        }
+    }
+    __syncthreads();
+    if (A.dbg_c) {
+        for (int i = tid; i < Rv * WW; i += K2T) {
+            A.dbg_c[((size_t)f * H + b0) * WW + i] = C[i];
+            A.dbg_s[((size_t)f * H + b0) * WW + i] = S[WW + i];
+        }
+    }
+
+    // ---- phase 2: hysteresis
+    int rounds = 0;
+    {
+        const int nseg = max(1, K2T / WW);
+        const int seg_rows = (Rv + nseg - 1) / nseg;
+        uint32_t *S_up = rank > 0 ? cluster.map_shared_rank(S, rank - 1) : nullptr;
+        uint32_t *S_dn = rank < G - 1 ? cluster.map_shared_rank(S, rank + 1) : nullptr;
+        for (;;) {
+            for (;;) {                                   // sweeps until this band is stable
+                bool ch = false;
+                for (int item = tid; item < WW * nseg; item += K2T) {
+                    const int w = item % WW, seg = item / WW;
+                    const int ra = seg * seg_rows, rb = min(ra + seg_rows, Rv);
+                    for (int r = ra; r < rb; r++) ch |= visit(C, S, r, w, WW);
+                    for (int r = rb - 2; r >= ra; r--) ch |= visit(C, S, r, w, WW);
+                }
+                if (!__syncthreads_or(ch)) break;
+            }
+            rounds++;
+            if (G == 1) break;
+            cluster.sync();                              // every band locally stable
+            bool hc = false;
+            for (int w = tid; w < WW; w += K2T) {
+                if (S_up) { uint32_t v = S_up[(size_t)R * WW + w]; if (v != S[w]) { S[w] = v; hc = true; } }
+                if (S_dn && Rv > 0) {
+                    uint32_t v = S_dn[WW + w];
+                    if (v != S[(size_t)(Rv + 1) * WW + w]) { S[(size_t)(Rv + 1) * WW + w] = v; hc = true; }
+                }
+            }
+            const int flag = __syncthreads_or(hc);
+            if (tid == 0) s_flag = flag;
+            cluster.sync();
+            int any = 0;
+            if (tid < G) any = *cluster.map_shared_rank(&s_flag, tid);
+            any = __syncthreads_or(any);
+            if (!any) break;
+        }
+    }
+
+    // ---- phase 3: outputs
+    int cnt = 0;
+    for (int i = tid; i < Rv * WW; i += K2T) {
+        const uint32_t s = S[WW + i];
+        A.edge_bits[((size_t)f * H + b0) * WW + i] = s;
+        cnt += __popc(s);
+    }
+    for (int o = 16; o; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+    if (lane == 0) s_red[wid] = cnt;
+    __syncthreads();
+    if (tid == 0) {
+        int t = 0;
+        for (int i = 0; i < K2T / 32; i++) t += s_red[i];
+        if (t) atomicAdd(&A.n_edges[f], t);
+        if (rank == 0) A.rounds[f] = rounds;
+    }
+    // ROI rows of this band
+    const LaneGeom &g = A.g;
+    const int y0 = max(b0, g.by0), y1 = min(b1, g.by1);
+    const uint32_t *roi = A.roi_bits;
+    for (int y = y0 + wid; y < y1; y += K2T / 32) {
+        int c = 0;
+        for (int w = lane; w < WW; w += 32) {
+            const uint32_t m = S[(size_t)(y - b0 + 1) * WW + w] & roi[(size_t)y * WW + w];
+            A.pmask_bits[((size_t)f * g.bh + (y - g.by0)) * WW + w] = m;
+            c += __popc(m);
+        }
+        for (int o = 16; o; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+        if (lane == 0) rowoff[y - b0] = c;
+    }
+    __syncthreads();
+    if (wid == 0) {                                       // exclusive scan of the row counts
+        int run = 0;
+        for (int base = y0; base < y1; base += 32) {
+            const int y = base + lane;
+            const int v = y < y1 ? rowoff[y - b0] : 0;
+            int inc = v;
+            for (int o = 1; o < 32; o <<= 1) {
+                int t = __shfl_up_sync(0xffffffffu, inc, o);
+                if (lane >= o) inc += t;
+            }
+            if (y < y1) rowoff[y - b0] = run + inc - v;
+            run += __shfl_sync(0xffffffffu, inc, 31);
+        }
+        if (lane == 0) s_total = run;
+    }
+    __syncthreads();
+    if (G > 1) cluster.sync();
+    if (tid == 0) {
+        int base = 0;
+        for (int r = 0; r < rank; r++) base += *cluster.map_shared_rank(&s_total, r);
+        s_base = base;
+        if (s_total) atomicAdd(&A.n_points[f], s_total);
+    }
+    __syncthreads();
+    uint32_t *out = A.points + (size_t)f * g.max_points + s_base;
+    for (int y = y0 + wid; y < y1; y += K2T / 32) {
+        int pos = rowoff[y - b0];
+        for (int wb = 0; wb < WW; wb += 32) {
+            const int w = wb + lane;
+            uint32_t m = 0;
+            if (w < WW) m = S[(size_t)(y - b0 + 1) * WW + w] & roi[(size_t)y * WW + w];
+            const int c = __popc(m);
+            int inc = c;
+            for (int o = 1; o < 32; o <<= 1) {
+                int t = __shfl_up_sync(0xffffffffu, inc, o);
+                if (lane >= o) inc += t;
+            }
+            int p = pos + inc - c;
+            while (m) {
+                const int b = __ffs(m) - 1;
+                out[p++] = ((uint32_t)y << 16) | (uint32_t)(w * 32 + b);
+                m &= m - 1;
+            }
+            pos += __shfl_sync(0xffffffffu, inc, 31);
+        }
+    }
+    if (G > 1) cluster.sync();                            // keep s_total alive until every band has read it
+}
+
+// byte map -> bit-plane (generic-width fallback path)
+__global__ void k_bytes_to_bits(const uint8_t *__restrict__ bytes, uint32_t *__restrict__ bits, int rows, int W,
+                                int row_stride, int WW)
+{
+    const int y = blockIdx.y, f = blockIdx.z;
+    const uint8_t *src = bytes + ((size_t)f * rows + y) * row_stride;
+    uint32_t *dst = bits + ((size_t)f * rows + y) * WW;
+    for (int w = blockIdx.x * blockDim.x + threadIdx.x; w < WW; w += gridDim.x * blockDim.x) {
+        uint32_t m = 0;
+        for (int b = 0; b < 32; b++) {
+            const int x = w * 32 + b;
+            if (x < W && src[x]) m |= 1u << b;
+        }
+        dst[w] = m;
+    }
+}
+
+// pmask[f][y-by0][w] = edge_bits[f][y][w] & roi_bits[y][w]  (generic-width fallback path)
+__global__ void k_mask_rows(const uint32_t *__restrict__ edge_bits, const uint32_t *__restrict__ roi_bits,
+                            uint32_t *__restrict__ pmask_bits, int H, int WW, int by0, int bh)
+{
+    const int f = blockIdx.y;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < bh * WW; i += gridDim.x * blockDim.x) {
+        const int y = by0 + i / WW, w = i % WW;
+        pmask_bits[(size_t)f * bh * WW + i] = edge_bits[((size_t)f * H + y) * WW + w] & roi_bits[(size_t)y * WW + w];
+    }
+}
+
+}  // namespace
+
+// Returns false when this frame geometry cannot take the cluster path (caller falls back to the
+// generic byte-map kernels).
+bool launch_canny_cluster(const uint8_t *blur, const uint32_t *hist, const uint8_t *lut_low, const uint8_t *lut_high,
+                          const uint32_t *roi_bits, int4 *thr, int *n_edges, int *rounds, uint32_t *points,
+                          int *n_points, uint32_t *pmask_bits, uint32_t *edge_bits, uint32_t *dbg_c, uint32_t *dbg_s,
+                          LaneGeom g, int n, cudaStream_t st, int *launches)
+{
+    const int H = g.H, W = g.W, WW = (W + 31) / 32;
+    if (W % 16 != 0 || ((uintptr_t)blur % 16) != 0) return false;
+    int G = 1;
+    while (G < 16 && H > 160 * G) G *= 2;
+    size_t smem = 0;
+    int R = 0;
+    for (;; G *= 2) {
+        R = (H + G - 1) / G;
+        smem = sizeof(uint32_t) * ((size_t)R * WW + (size_t)(R + 2) * WW) + sizeof(int) * (R + 1);
+        if (smem <= 200 * 1024 || G >= 16) break;
+    }
+    if (smem > 220 * 1024) return false;
+    static bool configured = false;
+    if (!configured) {
+        cudaFuncSetAttribute(k2_canny_cluster, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+        cudaFuncSetAttribute(k2_canny_cluster, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+        configured = true;
+    }
+    K2Args A;
+    A.blur = blur; A.hist = hist; A.lut_low = lut_low; A.lut_high = lut_high; A.roi_bits = roi_bits;
+    A.thr = thr; A.n_edges = n_edges; A.rounds = rounds; A.n_points = n_points; A.points = points;
+    A.pmask_bits = pmask_bits; A.edge_bits = edge_bits; A.dbg_c = dbg_c; A.dbg_s = dbg_s;
+    A.H = H; A.W = W; A.WW = WW; A.R = R; A.g = g;
+    cudaMemsetAsync(n_edges, 0, sizeof(int) * n, st);
+    cudaMemsetAsync(n_points, 0, sizeof(int) * n, st);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(n * G);
+    cfg.blockDim = dim3(K2T);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = G; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, k2_canny_cluster, A);
+    if (e != cudaSuccess) { cudaGetLastError(); return false; }
+    *launches += 1;
+    return true;
+}
+
+void launch_bytes_to_bits(const uint8_t *bytes, uint32_t *bits, int n, int rows, int W, int row_stride,
+                          cudaStream_t st, int *launches)
+{
+    const int WW = (W + 31) / 32;
+    dim3 grid((WW + 63) / 64, rows, n);
+    k_bytes_to_bits<<<grid, 64, 0, st>>>(bytes, bits, rows, W, row_stride, WW);
+    if (launches) *launches += 1;
+}
+
+void launch_mask_rows(const uint32_t *edge_bits, const uint32_t *roi_bits, uint32_t *pmask_bits, LaneGeom g, int n,
+                      cudaStream_t st, int *launches)
+{
+    const int WW = (g.W + 31) / 32;
+    if (g.bh <= 0) return;
+    dim3 grid((g.bh * WW + 255) / 256, n);
+    k_mask_rows<<<grid, 256, 0, st>>>(edge_bits, roi_bits, pmask_bits, g.H, WW, g.by0, g.bh);
+    if (launches) *launches += 1;
+}

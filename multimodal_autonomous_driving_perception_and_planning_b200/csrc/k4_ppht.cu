@@ -55,7 +55,7 @@ __device__ __forceinline__ void step_pixel(const WalkSetup &w, int k, int s, int
 }
 
 __global__ void __launch_bounds__(NT) k4_ppht(uint32_t *__restrict__ points_all, const int *__restrict__ n_points,
-                                              uint8_t *__restrict__ pmask_all, int32_t *__restrict__ accum_all,
+                                              uint32_t *__restrict__ pmask_all, int32_t *__restrict__ accum_all,
                                               int32_t *__restrict__ lines_all, int *__restrict__ n_lines,
                                               LaneGeom g, LaneHoughParams hp)
 {
@@ -72,8 +72,8 @@ __global__ void __launch_bounds__(NT) k4_ppht(uint32_t *__restrict__ points_all,
 
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, f = blockIdx.x;
     const bool active = tid < LANE_NUM_ANGLES;
-    const int bw = g.bw, bh = g.bh;
-    uint8_t *pm = pmask_all + (size_t)f * bw * bh;
+    const int WW = (g.W + 31) / 32;
+    uint32_t *pm = pmask_all + (size_t)f * g.bh * WW;     // mask word of (x, y): pm[(y-by0)*WW + (x>>5)], bit x&31
     int32_t *lines = lines_all + (size_t)f * g.max_segments * 4;
     const int rho_off = (g.numrho - 1) / 2;
     int32_t *acc = accum_all + ((size_t)f * LANE_NUM_ANGLES + (active ? tid : 0)) * g.numrho + rho_off;
@@ -112,7 +112,7 @@ __global__ void __launch_bounds__(NT) k4_ppht(uint32_t *__restrict__ points_all,
                 uint32_t pt = s_batch[tid];
                 if (pt != SKIP) {
                     int x = pt & 0xFFFF, y = pt >> 16;
-                    if (!pm[(y - g.by0) * bw + (x - g.bx0)]) s_batch[tid] = SKIP;
+                    if (!((__ldcg(&pm[(y - g.by0) * WW + (x >> 5)]) >> (x & 31)) & 1u)) s_batch[tid] = SKIP;
                 }
             }
             __syncthreads();
@@ -182,7 +182,7 @@ __global__ void __launch_bounds__(NT) k4_ppht(uint32_t *__restrict__ points_all,
                     bool ib = j1 >= 0 && j1 < g.W && i1 >= 0 && i1 < g.H;
                     bool hit = false;
                     if (ib && j1 >= g.bx0 && j1 < g.bx1 && i1 >= g.by0 && i1 < g.by1)
-                        hit = pm[(i1 - g.by0) * bw + (j1 - g.bx0)] != 0;
+                        hit = ((__ldcg(&pm[(i1 - g.by0) * WW + (j1 >> 5)]) >> (j1 & 31)) & 1u) != 0;
                     unsigned IB = __ballot_sync(0xffffffffu, ib), Hh = __ballot_sync(0xffffffffu, hit);
                     int limit = (~IB) ? __ffs(~IB) - 1 : 32;       // valid steps of this chunk: [0, limit)
                     if (limit < 32) Hh &= (1u << limit) - 1u;
@@ -227,11 +227,9 @@ __global__ void __launch_bounds__(NT) k4_ppht(uint32_t *__restrict__ points_all,
                         int j1, i1;
                         step_pixel(w, k, s, j1, i1);
                         if (j1 >= g.bx0 && j1 < g.bx1 && i1 >= g.by0 && i1 < g.by1) {
-                            uint8_t *m = pm + (i1 - g.by0) * bw + (j1 - g.bx0);
-                            if (*m) {
-                                *m = 0;
+                            const uint32_t bit = 1u << (j1 & 31);
+                            if (atomicAnd(&pm[(i1 - g.by0) * WW + (j1 >> 5)], ~bit) & bit)
                                 s_hits[atomicAdd(&s_nhits, 1)] = ((uint32_t)i1 << 16) | (uint32_t)j1;
-                            }
                         }
                     }
                     __syncthreads();
@@ -253,7 +251,7 @@ __global__ void __launch_bounds__(NT) k4_ppht(uint32_t *__restrict__ points_all,
 
 }  // namespace
 
-void launch_ppht(uint32_t *points, const int *n_points, uint8_t *pmask, int32_t *accum, int32_t *lines,
+void launch_ppht(uint32_t *points, const int *n_points, uint32_t *pmask, int32_t *accum, int32_t *lines,
                  int *n_lines, LaneGeom g, LaneHoughParams hp, int n, cudaStream_t st, int *launches)
 {
     cudaMemsetAsync(accum, 0, sizeof(int32_t) * (size_t)n * LANE_NUM_ANGLES * g.numrho, st);

@@ -26,7 +26,16 @@ struct lane_ctx {
 
     // device buffers
     uint8_t *d_frames = nullptr;      // staging for host frames (lazy)
-    uint8_t *d_blur = nullptr, *d_cls = nullptr, *d_cls_dbg = nullptr, *d_roi = nullptr, *d_pmask = nullptr;
+    uint8_t *d_blur = nullptr;
+    uint32_t *d_roi_bits = nullptr;   // [H][WW] bit-plane of the ROI mask
+    uint32_t *d_pmask_bits = nullptr; // [B][bh][WW] ROI-masked edges (the HoughLinesP mask)
+    uint32_t *d_edge_bits = nullptr;  // [B][H][WW] Canny map
+    uint32_t *d_dbg_c = nullptr, *d_dbg_s = nullptr;   // debug: pre-hysteresis candidate / strong planes
+    // generic-width fallback (byte maps), allocated on first use
+    uint8_t *d_cls = nullptr, *d_cls_dbg = nullptr, *d_roi = nullptr, *d_pmask = nullptr;
+    uint8_t *h_roi = nullptr;
+    bool fallback_ready = false, last_cluster = false;
+    int force_generic_k2 = 0;         // LANE_B200_K2=generic forces the byte-map kernels (A/B checks)
     uint8_t *d_gray_dbg = nullptr;
     uint32_t *d_hist = nullptr, *d_points = nullptr, *d_points_dbg = nullptr;
     uint8_t *d_lut = nullptr;         // low[511] | high[511]
@@ -91,12 +100,14 @@ void free_all(lane_ctx *c)
 {
     cudaSetDevice(c->device);
     void *ptrs[] = {c->d_frames, c->d_blur, c->d_cls, c->d_cls_dbg, c->d_roi, c->d_pmask, c->d_gray_dbg, c->d_hist,
+                    c->d_roi_bits, c->d_pmask_bits, c->d_edge_bits, c->d_dbg_c, c->d_dbg_s,
                     c->d_points, c->d_points_dbg, c->d_lut, c->d_thr, c->d_seedsA, c->d_seedsB, c->d_seed_count,
                     c->d_n_edges, c->d_n_points, c->d_rounds, c->d_n_lines, c->d_accum, c->d_lines, c->fit.raw,
                     c->fit.side_n, c->fit.side_flags, c->d_stream_id, c->d_prev_fit, c->d_prev_valid,
                     c->d_records, c->d_std_accum, c->d_peaks, c->d_n_peaks, c->d_task_counter};
     for (void *p : ptrs)
         if (p) cudaFree(p);
+    free(c->h_roi);
     if (c->h_records) cudaFreeHost(c->h_records);
     if (c->h_prev_fit) cudaFreeHost(c->h_prev_fit);
     if (c->h_prev_valid) cudaFreeHost(c->h_prev_valid);
@@ -118,6 +129,23 @@ int ensure_streams(lane_ctx *c, int S)
     CU(cudaMallocHost((void **)&c->h_prev_fit, sizeof(double) * S * 6));
     CU(cudaMallocHost((void **)&c->h_prev_valid, (size_t)S * 2));
     c->stream_cap = S;
+    return LANE_OK;
+}
+
+// Byte-map buffers of the generic-width path, allocated the first time that path runs.
+int ensure_fallback(lane_ctx *c)
+{
+    if (c->fallback_ready) return LANE_OK;
+    const size_t P = (size_t)c->g.H * c->g.W, B = (size_t)c->max_batch;
+    CU(dalloc(&c->d_cls, B * P));
+    if (c->debug) CU(dalloc(&c->d_cls_dbg, B * P));
+    CU(dalloc(&c->d_roi, P));
+    CU(dalloc(&c->d_pmask, B * std::max(c->g.bw * c->g.bh, 1)));
+    CU(dalloc(&c->d_seedsA, B * c->seed_cap));
+    CU(dalloc(&c->d_seedsB, B * c->seed_cap));
+    CU(dalloc(&c->d_seed_count, B));
+    CU(cudaMemcpyAsync(c->d_roi, c->h_roi, P, cudaMemcpyHostToDevice, c->st));
+    c->fallback_ready = true;
     return LANE_OK;
 }
 
@@ -148,23 +176,35 @@ int enqueue(lane_ctx *c, const uint8_t *frames_dev, int n, const int32_t *stream
                      c->force_tile);
 
     rc = mark(c, LANE_STAGE_CANNY); if (rc) return rc;
-    launch_thresholds(c->d_hist, c->d_lut, c->d_lut + 511, c->d_thr, n, H, W, c->st, &L[LANE_STAGE_CANNY]);
-    launch_sobel_nms(c->d_blur, c->d_thr, c->d_cls, c->d_seedsA, c->d_seed_count, c->seed_cap, n, H, W, c->st,
-                     &L[LANE_STAGE_CANNY]);
-    if (c->debug)
-        CU(cudaMemcpyAsync(c->d_cls_dbg, c->d_cls, (size_t)n * H * W, cudaMemcpyDeviceToDevice, c->st));
-    launch_hysteresis(c->d_cls, c->d_seedsA, c->d_seedsB, c->d_seed_count, c->seed_cap, c->d_rounds, n, H, W, c->st,
-                      &L[LANE_STAGE_CANNY]);
-    launch_finalize_edges(c->d_cls, c->d_n_edges, n, H, W, c->st, &L[LANE_STAGE_CANNY]);
-
-    rc = mark(c, LANE_STAGE_COMPACT); if (rc) return rc;
-    launch_compact(c->d_cls, c->d_roi, c->d_pmask, c->d_points, c->d_n_points, g, n, c->st, &L[LANE_STAGE_COMPACT]);
+    c->last_cluster = !c->force_generic_k2 &&
+        launch_canny_cluster(c->d_blur, c->d_hist, c->d_lut, c->d_lut + 511, c->d_roi_bits, c->d_thr, c->d_n_edges,
+                             c->d_rounds, c->d_points, c->d_n_points, c->d_pmask_bits, c->d_edge_bits,
+                             c->debug ? c->d_dbg_c : nullptr, c->debug ? c->d_dbg_s : nullptr, g, n, c->st,
+                             &L[LANE_STAGE_CANNY]);
+    if (c->last_cluster) {
+        rc = mark(c, LANE_STAGE_COMPACT); if (rc) return rc;
+    } else {
+        // generic widths / unaligned planes: byte-map kernels, then the same bit-plane outputs
+        rc = ensure_fallback(c); if (rc) return rc;
+        launch_thresholds(c->d_hist, c->d_lut, c->d_lut + 511, c->d_thr, n, H, W, c->st, &L[LANE_STAGE_CANNY]);
+        launch_sobel_nms(c->d_blur, c->d_thr, c->d_cls, c->d_seedsA, c->d_seed_count, c->seed_cap, n, H, W, c->st,
+                         &L[LANE_STAGE_CANNY]);
+        if (c->debug)
+            CU(cudaMemcpyAsync(c->d_cls_dbg, c->d_cls, (size_t)n * H * W, cudaMemcpyDeviceToDevice, c->st));
+        launch_hysteresis(c->d_cls, c->d_seedsA, c->d_seedsB, c->d_seed_count, c->seed_cap, c->d_rounds, n, H, W,
+                          c->st, &L[LANE_STAGE_CANNY]);
+        launch_finalize_edges(c->d_cls, c->d_n_edges, n, H, W, c->st, &L[LANE_STAGE_CANNY]);
+        rc = mark(c, LANE_STAGE_COMPACT); if (rc) return rc;
+        launch_compact(c->d_cls, c->d_roi, c->d_pmask, c->d_points, c->d_n_points, g, n, c->st, &L[LANE_STAGE_COMPACT]);
+        launch_bytes_to_bits(c->d_cls, c->d_edge_bits, n, H, W, W, c->st, &L[LANE_STAGE_COMPACT]);
+        launch_mask_rows(c->d_edge_bits, c->d_roi_bits, c->d_pmask_bits, g, n, c->st, &L[LANE_STAGE_COMPACT]);
+    }
     if (c->debug)
         CU(cudaMemcpyAsync(c->d_points_dbg, c->d_points, sizeof(uint32_t) * (size_t)n * g.max_points,
                            cudaMemcpyDeviceToDevice, c->st));
 
     rc = mark(c, LANE_STAGE_PPHT); if (rc) return rc;
-    launch_ppht(c->d_points, c->d_n_points, c->d_pmask, c->d_accum, c->d_lines, c->d_n_lines, g, c->hp, n, c->st,
+    launch_ppht(c->d_points, c->d_n_points, c->d_pmask_bits, c->d_accum, c->d_lines, c->d_n_lines, g, c->hp, n, c->st,
                 &L[LANE_STAGE_PPHT]);
 
     rc = mark(c, LANE_STAGE_FIT); if (rc) return rc;
@@ -244,14 +284,12 @@ int lane_ctx_create(int device, int height, int width, int max_batch, int max_se
     CUB(cudaStreamCreateWithFlags(&ctx->st, cudaStreamNonBlocking));
     for (auto &e : ctx->ev) CUB(cudaEventCreate(&e));
     CUB(dalloc(&ctx->d_blur, B * P));
-    CUB(dalloc(&ctx->d_cls, B * P));
-    CUB(dalloc(&ctx->d_roi, P));
+    const size_t WW = (width + 31) / 32;
+    CUB(dalloc(&ctx->d_roi_bits, (size_t)height * WW));
+    CUB(dalloc(&ctx->d_edge_bits, B * height * WW));
     CUB(dalloc(&ctx->d_hist, B * 256));
     CUB(dalloc(&ctx->d_lut, 1022));
     CUB(dalloc(&ctx->d_thr, B));
-    CUB(dalloc(&ctx->d_seedsA, B * ctx->seed_cap));
-    CUB(dalloc(&ctx->d_seedsB, B * ctx->seed_cap));
-    CUB(dalloc(&ctx->d_seed_count, B));
     CUB(dalloc(&ctx->d_n_edges, B));
     CUB(dalloc(&ctx->d_n_points, B));
     CUB(dalloc(&ctx->d_rounds, B));
@@ -267,6 +305,8 @@ int lane_ctx_create(int device, int height, int width, int max_batch, int max_se
     {
         const char *e = getenv("LANE_B200_K1");
         ctx->force_tile = e && !strcmp(e, "tile");
+        e = getenv("LANE_B200_K2");
+        ctx->force_generic_k2 = e && !strcmp(e, "generic");
     }
     CUB(cudaMallocHost((void **)&ctx->h_records, sizeof(lane_record) * B));
     CUB(cudaMemset(ctx->d_records, 0, sizeof(lane_record) * B));
@@ -305,12 +345,24 @@ int lane_set_roi_mask(lane_ctx *c, const uint8_t *mask)
     g.bw = g.bx1 - g.bx0; g.bh = g.by1 - g.by0;
     g.max_points = cnt;
     CU(cudaStreamSynchronize(c->st));
-    CU(cudaMemcpy(c->d_roi, mask, (size_t)g.H * g.W, cudaMemcpyHostToDevice));
-    if (c->d_pmask) cudaFree(c->d_pmask);
-    if (c->d_points) cudaFree(c->d_points);
-    if (c->d_points_dbg) cudaFree(c->d_points_dbg);
-    c->d_pmask = nullptr; c->d_points = nullptr; c->d_points_dbg = nullptr;
-    CU(dalloc(&c->d_pmask, (size_t)c->max_batch * g.bw * g.bh));
+    const size_t P = (size_t)g.H * g.W, WW = (g.W + 31) / 32;
+    free(c->h_roi);
+    c->h_roi = (uint8_t *)malloc(P);
+    memcpy(c->h_roi, mask, P);
+    std::vector<uint32_t> bits((size_t)g.H * WW, 0u);
+    for (int y = 0; y < g.H; y++)
+        for (int x = 0; x < g.W; x++)
+            if (mask[(size_t)y * g.W + x]) bits[(size_t)y * WW + (x >> 5)] |= 1u << (x & 31);
+    CU(cudaMemcpy(c->d_roi_bits, bits.data(), sizeof(uint32_t) * bits.size(), cudaMemcpyHostToDevice));
+    // geometry changed: the lazily-built fallback buffers are rebuilt on next use
+    for (void **p : {(void **)&c->d_pmask, (void **)&c->d_roi, (void **)&c->d_cls, (void **)&c->d_cls_dbg,
+                     (void **)&c->d_seedsA, (void **)&c->d_seedsB, (void **)&c->d_seed_count,
+                     (void **)&c->d_pmask_bits, (void **)&c->d_points, (void **)&c->d_points_dbg}) {
+        if (*p) cudaFree(*p);
+        *p = nullptr;
+    }
+    c->fallback_ready = false;
+    CU(dalloc(&c->d_pmask_bits, (size_t)c->max_batch * std::max(g.bh, 1) * WW));
     CU(dalloc(&c->d_points, (size_t)c->max_batch * g.max_points));
     if (c->debug) CU(dalloc(&c->d_points_dbg, (size_t)c->max_batch * g.max_points));
     c->have_roi = true;
@@ -349,7 +401,10 @@ int lane_set_debug(lane_ctx *c, int keep)
     c->debug = keep != 0;
     if (c->debug) {
         const size_t P = (size_t)c->g.H * c->g.W;
-        if (!c->d_cls_dbg) CU(dalloc(&c->d_cls_dbg, (size_t)c->max_batch * P));
+        const size_t WW = (c->g.W + 31) / 32;
+        if (!c->d_dbg_c) CU(dalloc(&c->d_dbg_c, (size_t)c->max_batch * c->g.H * WW));
+        if (!c->d_dbg_s) CU(dalloc(&c->d_dbg_s, (size_t)c->max_batch * c->g.H * WW));
+        if (c->fallback_ready && !c->d_cls_dbg) CU(dalloc(&c->d_cls_dbg, (size_t)c->max_batch * P));
         if (!c->d_gray_dbg) CU(dalloc(&c->d_gray_dbg, P));
         if (!c->d_points_dbg && c->have_roi) CU(dalloc(&c->d_points_dbg, (size_t)c->max_batch * c->g.max_points));
     }
@@ -452,10 +507,34 @@ int lane_debug_tap(lane_ctx *c, int what, int fi, void *host_out, size_t capacit
     switch (what) {
     case LANE_TAP_BLUR: src = c->d_blur + fi * P; bytes = P; break;
     case LANE_TAP_HIST: src = c->d_hist + fi * 256; bytes = 256 * sizeof(uint32_t); break;
-    case LANE_TAP_EDGES: src = c->d_cls + fi * P; bytes = P; break;
-    case LANE_TAP_CLASS:
-        if (!c->debug || !c->d_cls_dbg) return fail(c, LANE_ERR_STATE, "LANE_TAP_CLASS needs lane_set_debug(ctx,1) before detect");
-        src = c->d_cls_dbg + fi * P; bytes = P; break;
+    case LANE_TAP_EDGES:
+    case LANE_TAP_CLASS: {
+        const size_t WW = (g.W + 31) / 32, words = (size_t)g.H * WW;
+        if (P > capacity) return fail(c, LANE_ERR_INVALID, "tap needs %zu bytes, capacity %zu", P, capacity);
+        uint8_t *o = (uint8_t *)host_out;
+        if (what == LANE_TAP_EDGES) {
+            std::vector<uint32_t> e(words);
+            CU(cudaMemcpy(e.data(), c->d_edge_bits + fi * words, sizeof(uint32_t) * words, cudaMemcpyDeviceToHost));
+            for (int y = 0; y < g.H; y++)
+                for (int x = 0; x < g.W; x++)
+                    o[(size_t)y * g.W + x] = ((e[y * WW + (x >> 5)] >> (x & 31)) & 1u) ? 255 : 0;
+        } else if (!c->debug) {
+            return fail(c, LANE_ERR_STATE, "LANE_TAP_CLASS needs lane_set_debug(ctx,1) before detect");
+        } else if (c->last_cluster) {
+            std::vector<uint32_t> cc(words), ss(words);
+            CU(cudaMemcpy(cc.data(), c->d_dbg_c + fi * words, sizeof(uint32_t) * words, cudaMemcpyDeviceToHost));
+            CU(cudaMemcpy(ss.data(), c->d_dbg_s + fi * words, sizeof(uint32_t) * words, cudaMemcpyDeviceToHost));
+            for (int y = 0; y < g.H; y++)
+                for (int x = 0; x < g.W; x++) {
+                    const uint32_t cb = (cc[y * WW + (x >> 5)] >> (x & 31)) & 1u, sb = (ss[y * WW + (x >> 5)] >> (x & 31)) & 1u;
+                    o[(size_t)y * g.W + x] = (uint8_t)(sb ? 2 : cb);
+                }
+        } else {
+            CU(cudaMemcpy(o, c->d_cls_dbg + fi * P, P, cudaMemcpyDeviceToHost));
+        }
+        if (bytes_written) *bytes_written = P;
+        return LANE_OK;
+    }
     case LANE_TAP_GRAY:
         if (!c->d_gray_dbg) return fail(c, LANE_ERR_STATE, "LANE_TAP_GRAY needs lane_set_debug(ctx,1)");
         launch_gray_debug(c->last_frames_dev + fi * P * 3, c->d_gray_dbg, g.H, g.W, c->st);

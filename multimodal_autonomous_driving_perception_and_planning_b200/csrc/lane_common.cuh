@@ -50,6 +50,16 @@ void launch_finalize_edges(uint8_t *cls_edges, int *n_edges, int n, int H, int W
 void launch_compact(const uint8_t *edges, const uint8_t *roi, uint8_t *pmask, uint32_t *points, int *n_points,
                     LaneGeom g, int n, cudaStream_t st, int *launches);
 
+// cluster form of K2 (bit-planes in distributed shared memory); false => geometry not supported, use the kernels above
+bool launch_canny_cluster(const uint8_t *blur, const uint32_t *hist, const uint8_t *lut_low, const uint8_t *lut_high,
+                          const uint32_t *roi_bits, int4 *thr, int *n_edges, int *rounds, uint32_t *points,
+                          int *n_points, uint32_t *pmask_bits, uint32_t *edge_bits, uint32_t *dbg_c, uint32_t *dbg_s,
+                          LaneGeom g, int n, cudaStream_t st, int *launches);
+void launch_bytes_to_bits(const uint8_t *bytes, uint32_t *bits, int n, int rows, int W, int row_stride,
+                          cudaStream_t st, int *launches);
+void launch_mask_rows(const uint32_t *edge_bits, const uint32_t *roi_bits, uint32_t *pmask_bits, LaneGeom g, int n,
+                      cudaStream_t st, int *launches);
+
 // ---- K3 ---------------------------------------------------------------------------------
 void launch_hough_accum(const uint32_t *points, const int *n_points, int32_t *accum_padded, LaneGeom g,
                         cudaStream_t st);
@@ -60,7 +70,8 @@ void lane_upload_tables_std();
 
 // ---- K4 ---------------------------------------------------------------------------------
 // accum: int32 [n][180][numrho] zeroed by the launcher; lines: int32 [n][max_segments][4]
-void launch_ppht(uint32_t *points, const int *n_points, uint8_t *pmask, int32_t *accum, int32_t *lines,
+// pmask_bits: [n][bh][WW] bit-plane of the ROI-masked edges (bit x&31 of word x>>5), cleared as lines are found
+void launch_ppht(uint32_t *points, const int *n_points, uint32_t *pmask_bits, int32_t *accum, int32_t *lines,
                  int *n_lines, LaneGeom g, LaneHoughParams hp, int n, cudaStream_t st, int *launches);
 
 // ---- K5 ---------------------------------------------------------------------------------
