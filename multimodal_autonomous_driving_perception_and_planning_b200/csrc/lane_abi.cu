@@ -43,7 +43,11 @@ struct lane_ctx {
     int *d_seedsA = nullptr, *d_seedsB = nullptr, *d_seed_count = nullptr;
     int seed_cap = 0;
     int *d_n_edges = nullptr, *d_n_points = nullptr, *d_rounds = nullptr, *d_n_lines = nullptr;
-    int32_t *d_accum = nullptr, *d_lines = nullptr;
+    int32_t *d_accum = nullptr, *d_lines = nullptr;   // d_accum: v1 PPHT only (LANE_B200_K4=v1), lazy
+    uint32_t *d_accum16 = nullptr;    // [B][cells_per_frame] biased 16-bit cells, two per word
+    int2 *d_win = nullptr;            // [180] (rmin, first cell) per angle
+    int cells_per_frame = 0;
+    int ppht_v1 = 0;
     LaneFitScratch fit{};
     int *d_stream_id = nullptr;
     double *d_prev_fit = nullptr;
@@ -100,7 +104,7 @@ void free_all(lane_ctx *c)
 {
     cudaSetDevice(c->device);
     void *ptrs[] = {c->d_frames, c->d_blur, c->d_cls, c->d_cls_dbg, c->d_roi, c->d_pmask, c->d_gray_dbg, c->d_hist,
-                    c->d_roi_bits, c->d_pmask_bits, c->d_edge_bits, c->d_dbg_c, c->d_dbg_s,
+                    c->d_roi_bits, c->d_pmask_bits, c->d_edge_bits, c->d_dbg_c, c->d_dbg_s, c->d_accum16, c->d_win,
                     c->d_points, c->d_points_dbg, c->d_lut, c->d_thr, c->d_seedsA, c->d_seedsB, c->d_seed_count,
                     c->d_n_edges, c->d_n_points, c->d_rounds, c->d_n_lines, c->d_accum, c->d_lines, c->fit.raw,
                     c->fit.side_n, c->fit.side_flags, c->d_stream_id, c->d_prev_fit, c->d_prev_valid,
@@ -204,8 +208,14 @@ int enqueue(lane_ctx *c, const uint8_t *frames_dev, int n, const int32_t *stream
                            cudaMemcpyDeviceToDevice, c->st));
 
     rc = mark(c, LANE_STAGE_PPHT); if (rc) return rc;
-    launch_ppht(c->d_points, c->d_n_points, c->d_pmask_bits, c->d_accum, c->d_lines, c->d_n_lines, g, c->hp, n, c->st,
-                &L[LANE_STAGE_PPHT]);
+    if (c->ppht_v1) {
+        if (!c->d_accum) CU(dalloc(&c->d_accum, (size_t)c->max_batch * LANE_NUM_ANGLES * g.numrho));
+        launch_ppht(c->d_points, c->d_n_points, c->d_pmask_bits, c->d_accum, c->d_lines, c->d_n_lines, g, c->hp, n,
+                    c->st, &L[LANE_STAGE_PPHT]);
+    } else {
+        launch_ppht_v2(c->d_points, c->d_n_points, c->d_pmask_bits, c->d_accum16, c->d_win, c->cells_per_frame,
+                       c->d_lines, c->d_n_lines, g, c->hp, n, c->st, &L[LANE_STAGE_PPHT]);
+    }
 
     rc = mark(c, LANE_STAGE_FIT); if (rc) return rc;
     launch_fit(c->d_lines, c->d_n_lines, c->fit, stream_id ? c->d_stream_id : nullptr, S, c->d_prev_fit,
@@ -294,7 +304,7 @@ int lane_ctx_create(int device, int height, int width, int max_batch, int max_se
     CUB(dalloc(&ctx->d_n_points, B));
     CUB(dalloc(&ctx->d_rounds, B));
     CUB(dalloc(&ctx->d_n_lines, B));
-    CUB(dalloc(&ctx->d_accum, B * LANE_NUM_ANGLES * g.numrho));
+    CUB(dalloc(&ctx->d_win, LANE_NUM_ANGLES));
     CUB(dalloc(&ctx->d_lines, B * g.max_segments * 4));
     CUB(dalloc(&ctx->fit.raw, B * 6));
     CUB(dalloc(&ctx->fit.side_n, B * 2));
@@ -305,6 +315,8 @@ int lane_ctx_create(int device, int height, int width, int max_batch, int max_se
     {
         const char *e = getenv("LANE_B200_K1");
         ctx->force_tile = e && !strcmp(e, "tile");
+        e = getenv("LANE_B200_K4");
+        ctx->ppht_v1 = e && !strcmp(e, "v1");
         e = getenv("LANE_B200_K2");
         ctx->force_generic_k2 = e && !strcmp(e, "generic");
     }
@@ -362,6 +374,14 @@ int lane_set_roi_mask(lane_ctx *c, const uint8_t *mask)
         *p = nullptr;
     }
     c->fallback_ready = false;
+    {
+        int2 win[LANE_NUM_ANGLES];
+        c->cells_per_frame = lane_ppht_windows(mask, g.H, g.W, win);
+        CU(cudaMemcpy(c->d_win, win, sizeof(win), cudaMemcpyHostToDevice));
+        if (c->d_accum16) cudaFree(c->d_accum16);
+        c->d_accum16 = nullptr;
+        CU(dalloc(&c->d_accum16, (size_t)c->max_batch * (c->cells_per_frame / 2)));
+    }
     CU(dalloc(&c->d_pmask_bits, (size_t)c->max_batch * std::max(g.bh, 1) * WW));
     CU(dalloc(&c->d_points, (size_t)c->max_batch * g.max_points));
     if (c->debug) CU(dalloc(&c->d_points_dbg, (size_t)c->max_batch * g.max_points));

@@ -74,6 +74,12 @@ void lane_upload_tables_std();
 void launch_ppht(uint32_t *points, const int *n_points, uint32_t *pmask_bits, int32_t *accum, int32_t *lines,
                  int *n_lines, LaneGeom g, LaneHoughParams hp, int n, cudaStream_t st, int *launches);
 
+// v2: 16-bit biased cells inside per-angle rho windows (win[n] = (rmin, first cell)), producer warp, deep votes
+void launch_ppht_v2(uint32_t *points, const int *n_points, uint32_t *pmask_bits, uint32_t *accum16, const int2 *win,
+                    int cells_per_frame, int32_t *lines, int *n_lines, LaneGeom g, LaneHoughParams hp, int n,
+                    cudaStream_t st, int *launches);
+int lane_ppht_windows(const uint8_t *mask, int H, int W, int2 *win);   // returns cells per frame
+
 // ---- K5 ---------------------------------------------------------------------------------
 struct LaneFitScratch {
     double *raw;        // [n][2][3]
