@@ -280,10 +280,16 @@ __global__ void __launch_bounds__(NT2) k4_ppht_v2(uint32_t *__restrict__ points_
                                                   uint32_t *__restrict__ pmask_all, uint32_t *__restrict__ accum_all,
                                                   const int2 *__restrict__ win, int cells_per_frame,
                                                   int32_t *__restrict__ lines_all, int *__restrict__ n_lines,
-                                                  LaneGeom g, LaneHoughParams hp)
+                                                  LaneGeom g, LaneHoughParams hp, int only_flagged)
 {
     __shared__ uint32_t s_list[LIST_CAP];
     __shared__ uint32_t s_buf[2][BATCH2];
+    if (only_flagged) {                             // clean-up pass behind v3: frames it could not take (n_lines == -1)
+        if (n_lines[blockIdx.x] != -1) return;
+        uint32_t *a = accum_all + (size_t)blockIdx.x * (cells_per_frame / 2);
+        for (int i = threadIdx.x; i < cells_per_frame / 2; i += NT2) a[i] = BIAS | (BIAS << 16);
+        __threadfence_block();
+    }
     __shared__ int s_trig;
     __shared__ int s_redv[NV / 32], s_redn[NV / 32];
     __shared__ int s_end[2][2];
@@ -482,15 +488,466 @@ __global__ void __launch_bounds__(NT2) k4_ppht_v2(uint32_t *__restrict__ points_
     if (tid == 0) n_lines[f] = nl;
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// v3: accumulator in (distributed) shared memory.  Global atomics bound v2 (85 M votes per 256
+// frames against the L2 atomic rate), so here a cluster of G CTAs owns one frame and CTA r keeps
+// the 16-bit cells of the angles n = r (mod G) in its own shared memory; each angle is still voted
+// by exactly one thread, in point order, with plain shared-memory read-modify-writes (exact
+// sequential counts, no atomics).  Every CTA draws the same point sequence (producer warp) and
+// walks the same lines on its private copy of the mask, so the only traffic between CTAs is one
+// 64-bit word per CTA per batch (first triggering point) and one per trigger (arg-max), exchanged
+// through DSMEM slots with a sequence number -- no cluster barrier on the hot path.
+constexpr int BATCH3 = 64;
+constexpr int LIST_CAP3 = 4096;
+
+struct XchgSlots {
+    unsigned long long v[2][16];   // [seq parity][source rank] = seq << 32 | payload
+};
+
+__device__ __forceinline__ uint32_t dsmem_addr(const void *local_smem_ptr, unsigned rank)
+{
+    uint32_t a = (uint32_t)__cvta_generic_to_shared(local_smem_ptr), r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(rank));
+    return r;
+}
+// payload and sequence number travel in one 64-bit word, so relaxed accesses suffice (no fence, no L1 flush)
+__device__ __forceinline__ void dsmem_store_release(uint32_t addr, unsigned long long v)
+{
+    asm volatile("st.relaxed.cluster.shared::cluster.b64 [%0], %1;" ::"r"(addr), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long smem_load_acquire(const unsigned long long *p)
+{
+    unsigned long long v;
+    uint32_t a = (uint32_t)__cvta_generic_to_shared(p);
+    asm volatile("ld.relaxed.cluster.shared::cta.b64 %0, [%1];" : "=l"(v) : "r"(a) : "memory");
+    return v;
+}
+
+// all-gather of one 32-bit payload per CTA; called by one thread per CTA.  op: 0 = min, 1 = max.
+__device__ __forceinline__ uint32_t cluster_reduce(XchgSlots *slots, unsigned &seq, int G, int rank, uint32_t payload,
+                                                   int op)
+{
+    seq++;
+    const unsigned par = seq & 1;
+    const unsigned long long word = ((unsigned long long)seq << 32) | payload;
+    for (int p = 0; p < G; p++) dsmem_store_release(dsmem_addr(&slots->v[par][rank], p), word);
+    uint32_t res = payload;
+    for (int p = 0; p < G; p++) {
+        unsigned long long w;
+        do { w = smem_load_acquire(&slots->v[par][p]); } while ((unsigned)(w >> 32) != seq);
+        const uint32_t q = (uint32_t)w;
+        res = op ? max(res, q) : min(res, q);
+    }
+    return res;
+}
+
+constexpr int FLAG_CAP = 48;
+constexpr unsigned CBIAS = 0x4000u;
+constexpr int HITS_CAP = 768;
+
+__device__ __forceinline__ int scell_add(uint32_t *cells32, int cell, int delta)   // value BEFORE the add
+{
+    const unsigned sh = (cell & 1) * 16;
+    const unsigned old = atomicAdd(&cells32[cell >> 1], (unsigned)delta << sh);
+    return (int)((old >> sh) & 0xFFFFu) - (int)CBIAS;
+}
+__device__ __forceinline__ int scell_get(const uint32_t *cells32, int cell)
+{
+    return (int)((cells32[cell >> 1] >> ((cell & 1) * 16)) & 0xFFFFu) - (int)CBIAS;
+}
+
+// tpa = voter threads per angle.  Votes of a batch are applied by all voter threads at once with
+// shared-memory atomics (order-free); a vote that sees its bin at or above the threshold flags the
+// bin, and the exact first triggering point is then recovered per flagged bin by replaying only that
+// bin over the batch (counts inside a batch are monotone, so no other bin can trigger earlier).
+__global__ void k4_ppht_v3(const uint32_t *__restrict__ points_all, const int *__restrict__ n_points,
+                           const uint32_t *__restrict__ pmask_all, uint32_t *__restrict__ pmask_work,
+                           const int2 *__restrict__ win, int cells_max, int G, int nvw, int tpa,
+                           int32_t *__restrict__ lines_all, int *__restrict__ n_lines, LaneGeom g, LaneHoughParams hp)
+{
+    extern __shared__ __align__(16) unsigned char dyn[];
+    uint32_t *cells32 = reinterpret_cast<uint32_t *>(dyn);
+    uint32_t *s_list = reinterpret_cast<uint32_t *>(dyn + (((size_t)cells_max * 2 + 15) & ~(size_t)15));
+    __shared__ uint32_t s_buf[2][BATCH3];
+    __shared__ uint32_t s_rnd[BATCH3];
+    __shared__ XchgSlots s_slots;
+    __shared__ int s_trig, s_nflag;
+    __shared__ int s_flag_cell[FLAG_CAP], s_flag_slot[FLAG_CAP];
+    __shared__ int s_redkey[32];
+    __shared__ int s_end[2][2];
+    __shared__ int s_nsteps[2];
+    __shared__ int s_good;
+    __shared__ uint32_t s_hits[HITS_CAP];
+    __shared__ int s_nhits;
+    __shared__ WalkSetup s_walk;
+
+    unsigned rank;
+    asm("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
+    const int NVT = nvw * 32;                      // voter threads
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, f = blockIdx.x / G;
+    const bool producer = wid == nvw;
+    const int slot = tid / tpa, sub = tid - slot * tpa;
+    const int angle = slot * G + (int)rank;
+    const bool active = !producer && angle < LANE_NUM_ANGLES;
+    const int WW = (g.W + 31) / 32;
+    const int mask_words = g.bh * WW;
+    uint32_t *pm = pmask_work + ((size_t)f * G + rank) * mask_words;
+    const float cs = active ? c_ppht_cos[angle] : 0.f, sn = active ? c_ppht_sin[angle] : 0.f;
+    const int2 wn = active ? win[angle] : make_int2(0, 0);
+    const int cell0 = wn.y - wn.x;                 // cell of rho r = cell0 + r
+
+    for (int i = tid; i < cells_max / 2; i += blockDim.x) cells32[i] = CBIAS | (CBIAS << 16);
+    {   // private copy of the frame's mask (walks clear bits in it)
+        const uint4 *src = reinterpret_cast<const uint4 *>(pmask_all + (size_t)f * mask_words);
+        uint4 *dst = reinterpret_cast<uint4 *>(pm);
+        const int n4 = mask_words / 4;             // rows are padded so mask_words % 4 == 0 (launcher checks)
+        int i = tid;
+        for (; i + 3 * (int)blockDim.x < n4; i += 4 * blockDim.x) {
+            uint4 a = src[i], b = src[i + blockDim.x], c = src[i + 2 * blockDim.x], d = src[i + 3 * blockDim.x];
+            dst[i] = a; dst[i + blockDim.x] = b; dst[i + 2 * blockDim.x] = c; dst[i + 3 * blockDim.x] = d;
+        }
+        for (; i < n4; i += blockDim.x) dst[i] = src[i];
+    }
+    if (tid < 32) { s_slots.v[0][tid & 15] = 0; s_slots.v[1][tid & 15] = 0; }
+    const int count0 = n_points[f];
+    const uint32_t *glist = points_all + (size_t)f * g.max_points;
+    uint32_t *list = s_list;
+    const bool dense = count0 > LIST_CAP3;          // point list does not fit: the frame is left to v2
+    if (!dense)
+        for (int i = tid; i < count0; i += blockDim.x) s_list[i] = glist[i];
+    const int n_batches = (count0 + BATCH3 - 1) / BATCH3;
+    uint64_t rng = 0xFFFFFFFFFFFFFFFFull;
+    int remaining = count0, nl = 0;
+    unsigned seq = 0;
+    __syncthreads();
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+    if (dense) {
+        if (tid == 0 && rank == 0) n_lines[f] = -1;
+        asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+        return;
+    }
+
+    auto bar_v = [&]() { asm volatile("bar.sync 1, %0;" ::"r"(NVT) : "memory"); };
+    // Producer warp: draw the next min(BATCH3, remaining) points.  The generator is a serial chain (lane 0),
+    // the 64 remainders are independent (all lanes), and the swap-remove on the list runs four steps at a time
+    // with the values a later step would have read forwarded in registers.
+    auto draw = [&](uint32_t *buf) {
+        const int P = remaining < BATCH3 ? remaining : BATCH3;
+        if (lane == 0) {
+            for (int k = 0; k < P; k++) {
+                rng = (uint64_t)(uint32_t)rng * 4164903690ull + (uint32_t)(rng >> 32);
+                s_rnd[k] = (uint32_t)rng;
+            }
+        }
+        __syncwarp();
+        for (int k = lane; k < P; k += 32) s_rnd[k] = s_rnd[k] % (uint32_t)(remaining - k);
+        __syncwarp();
+        if (lane == 0) {
+            int k = 0;
+            for (; k + 4 <= P; k += 4) {
+                const int i0 = s_rnd[k], i1 = s_rnd[k + 1], i2 = s_rnd[k + 2], i3 = s_rnd[k + 3];
+                const int l0 = remaining - k - 1, l1 = l0 - 1, l2 = l0 - 2, l3 = l0 - 3;
+                uint32_t a0 = list[i0], a1 = list[i1], a2 = list[i2], a3 = list[i3];
+                uint32_t b0 = list[l0], b1 = list[l1], b2 = list[l2], b3 = list[l3];
+                // step 0 writes list[i0] = b0; later reads of slot i0 must see it, and so on down the chain
+                if (i1 == i0) a1 = b0;
+                if (l1 == i0) b1 = b0;
+                if (i2 == i1) a2 = b1; else if (i2 == i0) a2 = b0;
+                if (l2 == i1) b2 = b1; else if (l2 == i0) b2 = b0;
+                if (i3 == i2) a3 = b2; else if (i3 == i1) a3 = b1; else if (i3 == i0) a3 = b0;
+                if (l3 == i2) b3 = b2; else if (l3 == i1) b3 = b1; else if (l3 == i0) b3 = b0;
+                buf[k] = a0; buf[k + 1] = a1; buf[k + 2] = a2; buf[k + 3] = a3;
+                list[i0] = b0; list[i1] = b1; list[i2] = b2; list[i3] = b3;   // in order: later steps win
+            }
+            for (; k < P; k++) {
+                const int i = s_rnd[k], l = remaining - k - 1;
+                buf[k] = list[i];
+                list[i] = list[l];
+            }
+        }
+        remaining -= P;
+        __syncwarp();
+    };
+    if (producer && n_batches > 0) draw(s_buf[0]);
+    __syncthreads();
+
+    for (int bi = 0; bi < n_batches; bi++) {
+        uint32_t *batch = s_buf[bi & 1];
+        const int P = min(BATCH3, count0 - bi * BATCH3);
+        if (producer) {
+            if (bi + 1 < n_batches) draw(s_buf[(bi + 1) & 1]);
+        } else {
+            int k0 = 0;
+            while (k0 < P) {
+                for (int k = k0 + tid; k < P; k += NVT) {            // drop points an earlier walk removed
+                    const uint32_t pt = batch[k];
+                    if (pt != SKIP) {
+                        const int x = pt & 0xFFFF, y = pt >> 16;
+                        if (!((__ldcg(&pm[(y - g.by0) * WW + (x >> 5)]) >> (x & 31)) & 1u)) batch[k] = SKIP;
+                    }
+                }
+                if (tid == 0) { s_trig = BATCH3; s_nflag = 0; }
+                bar_v();
+                if (active) {                                         // order-free votes, all voter threads
+                    for (int k = k0 + sub; k < P; k += tpa) {
+                        const uint32_t pt = batch[k];
+                        if (pt == SKIP) continue;
+                        const int c = cell0 + rho_of(pt & 0xFFFF, pt >> 16, cs, sn);
+                        if (scell_add(cells32, c, 1) + 1 >= hp.threshold) {
+                            const int i = atomicAdd(&s_nflag, 1);
+                            if (i < FLAG_CAP) { s_flag_cell[i] = c; s_flag_slot[i] = slot; }
+                        }
+                    }
+                }
+                bar_v();
+                const int nflag = s_nflag;
+                if (nflag > FLAG_CAP) {
+                    // too many flagged bins to replay one by one: redo this batch in point order, one thread per angle
+                    if (active)
+                        for (int k = k0 + sub; k < P; k += tpa) {
+                            const uint32_t pt = batch[k];
+                            if (pt != SKIP) scell_add(cells32, cell0 + rho_of(pt & 0xFFFF, pt >> 16, cs, sn), -1);
+                        }
+                    bar_v();
+                    if (active && sub == 0) {
+                        int first = BATCH3;
+                        for (int k = k0; k < P; k++) {
+                            const uint32_t pt = batch[k];
+                            if (pt == SKIP) continue;
+                            if (scell_add(cells32, cell0 + rho_of(pt & 0xFFFF, pt >> 16, cs, sn), 1) + 1 >= hp.threshold)
+                                first = min(first, k);
+                        }
+                        if (first < BATCH3) atomicMin(&s_trig, first);
+                    }
+                    bar_v();
+                } else if (nflag > 0) {
+                    for (int e = tid; e < nflag; e += NVT) {          // replay one flagged bin over the batch
+                        const int c = s_flag_cell[e], an = s_flag_slot[e] * G + (int)rank;
+                        const float ecs = c_ppht_cos[an], esn = c_ppht_sin[an];
+                        const int2 ew = win[an];
+                        const int ec0 = ew.y - ew.x;
+                        int cnt = 0;
+                        for (int k = k0; k < P; k++) {
+                            const uint32_t pt = batch[k];
+                            if (pt != SKIP && ec0 + rho_of(pt & 0xFFFF, pt >> 16, ecs, esn) == c) cnt++;
+                        }
+                        int running = scell_get(cells32, c) - cnt, first = BATCH3;
+                        for (int k = k0; k < P; k++) {
+                            const uint32_t pt = batch[k];
+                            if (pt != SKIP && ec0 + rho_of(pt & 0xFFFF, pt >> 16, ecs, esn) == c && ++running >= hp.threshold) {
+                                first = k;
+                                break;
+                            }
+                        }
+                        if (first < BATCH3) atomicMin(&s_trig, first);
+                    }
+                    bar_v();
+                }
+                if (G > 1) {
+                    if (tid == 0) s_trig = (int)cluster_reduce(&s_slots, seq, G, rank, (uint32_t)s_trig, 0);
+                    bar_v();
+                }
+                const int t = s_trig;
+                if (t == BATCH3) break;
+                int key = 0;                                          // (value, -angle) packed for a max-reduce
+                if (active) {
+                    for (int k = t + 1 + sub; k < P; k += tpa) {      // roll back the votes behind the trigger
+                        const uint32_t pt = batch[k];
+                        if (pt != SKIP) scell_add(cells32, cell0 + rho_of(pt & 0xFFFF, pt >> 16, cs, sn), -1);
+                    }
+                }
+                bar_v();
+                if (active && sub == 0) {
+                    const uint32_t tp = batch[t];
+                    const int v = scell_get(cells32, cell0 + rho_of(tp & 0xFFFF, tp >> 16, cs, sn));
+                    key = ((v + 0x8000) << 8) | (255 - angle);
+                }
+                for (int o = 16; o; o >>= 1) key = max(key, __shfl_xor_sync(0xffffffffu, key, o));
+                if (lane == 0) s_redkey[wid] = key;
+                bar_v();
+                if (tid == 0) {
+                    int best = s_redkey[0];
+                    for (int w = 1; w < nvw; w++) best = max(best, s_redkey[w]);
+                    if (G > 1) best = (int)cluster_reduce(&s_slots, seq, G, rank, (uint32_t)best, 1);
+                    const int mn = 255 - (best & 0xFF);
+                    const uint32_t tp = batch[t];
+                    const int px = tp & 0xFFFF, py = tp >> 16;
+                    float a = -c_ppht_sin[mn], b = c_ppht_cos[mn];
+                    WalkSetup w;
+                    w.x0 = px; w.y0 = py;
+                    if (fabsf(a) > fabsf(b)) {
+                        w.xflag = 1;
+                        w.dx0 = a > 0 ? 1 : -1;
+                        w.dy0 = __float2int_rn(__fdiv_rn(__fmul_rn(b, 65536.0f), fabsf(a)));
+                        w.y0 = (py << 16) + 32768;
+                    } else {
+                        w.xflag = 0;
+                        w.dy0 = b > 0 ? 1 : -1;
+                        w.dx0 = __float2int_rn(__fdiv_rn(__fmul_rn(a, 65536.0f), fabsf(b)));
+                        w.x0 = (px << 16) + 32768;
+                    }
+                    s_walk = w;
+                }
+                bar_v();
+                const WalkSetup w = s_walk;
+                for (int k = wid; k < 2; k += nvw) {                  // pass 1: a warp per direction, 128 steps per round
+                    int last = 0;
+                    bool done = false;
+                    for (int base = 0; !done; base += 128) {
+                        unsigned IBs[4], Hs[4];
+#pragma unroll
+                        for (int j = 0; j < 4; j++) {
+                            int j1, i1;
+                            step_pixel(w, k, base + 32 * j + lane, j1, i1);
+                            const bool ib = j1 >= 0 && j1 < g.W && i1 >= 0 && i1 < g.H;
+                            bool hit = false;
+                            if (ib && i1 >= g.by0 && i1 < g.by1)
+                                hit = ((__ldcg(&pm[(i1 - g.by0) * WW + (j1 >> 5)]) >> (j1 & 31)) & 1u) != 0;
+                            IBs[j] = __ballot_sync(0xffffffffu, ib);
+                            Hs[j] = __ballot_sync(0xffffffffu, hit);
+                        }
+#pragma unroll
+                        for (int j = 0; j < 4; j++) {
+                            if (done) break;
+                            const int b32 = base + 32 * j;
+                            unsigned Hh = Hs[j];
+                            const int limit = (~IBs[j]) ? __ffs(~IBs[j]) - 1 : 32;
+                            if (limit < 32) Hh &= (1u << limit) - 1u;
+                            while (Hh) {
+                                const int p = b32 + __ffs(Hh) - 1;
+                                if (p - last > hp.max_gap + 1) { done = true; break; }
+                                last = p;
+                                Hh &= Hh - 1;
+                            }
+                            if (!done) {
+                                if (limit < 32) done = true;
+                                else if (b32 + 31 - last > hp.max_gap) done = true;
+                            }
+                        }
+                    }
+                    if (lane == 0) {
+                        int j1, i1;
+                        step_pixel(w, k, last, j1, i1);
+                        s_end[k][0] = j1; s_end[k][1] = i1;
+                        s_nsteps[k] = last + 1;
+                    }
+                }
+                bar_v();
+                if (tid == 0) {
+                    int good = abs(s_end[1][0] - s_end[0][0]) >= hp.min_len || abs(s_end[1][1] - s_end[0][1]) >= hp.min_len;
+                    s_good = good;
+                    if (good) {
+                        if (rank == 0 && nl < g.max_segments) {
+                            int32_t *lines = lines_all + (size_t)f * g.max_segments * 4;
+                            lines[4 * nl + 0] = s_end[0][0]; lines[4 * nl + 1] = s_end[0][1];
+                            lines[4 * nl + 2] = s_end[1][0]; lines[4 * nl + 3] = s_end[1][1];
+                        }
+                        nl++;
+                    }
+                }
+                for (int k = 0; k < 2; k++) {                         // pass 2: clear, and un-vote if good
+                    const int ns = s_nsteps[k];
+                    const int per_round = min(4 * NVT, HITS_CAP);
+                    for (int base = 0; base < ns; base += per_round) {
+                        if (tid == 0) s_nhits = 0;
+                        bar_v();
+                        for (int s = base + tid; s < min(ns, base + per_round); s += NVT) {
+                            int j1, i1;
+                            step_pixel(w, k, s, j1, i1);
+                            if (i1 >= g.by0 && i1 < g.by1 && j1 >= 0 && j1 < g.W) {
+                                const uint32_t bit = 1u << (j1 & 31);
+                                if (atomicAnd(&pm[(i1 - g.by0) * WW + (j1 >> 5)], ~bit) & bit)
+                                    s_hits[atomicAdd(&s_nhits, 1)] = ((uint32_t)i1 << 16) | (uint32_t)j1;
+                            }
+                        }
+                        bar_v();
+                        if (s_good && active) {
+                            const int nh = s_nhits;
+                            for (int h = sub; h < nh; h += tpa) {
+                                const uint32_t pt = s_hits[h];
+                                scell_add(cells32, cell0 + rho_of(pt & 0xFFFF, pt >> 16, cs, sn), -1);
+                            }
+                        }
+                        bar_v();
+                    }
+                }
+                k0 = t + 1;
+            }
+        }
+        __syncthreads();
+    }
+    if (tid == 0 && rank == 0) n_lines[f] = nl;
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
 }  // namespace
 
 void launch_ppht_v2(uint32_t *points, const int *n_points, uint32_t *pmask, uint32_t *accum16, const int2 *win,
                     int cells_per_frame, int32_t *lines, int *n_lines, LaneGeom g, LaneHoughParams hp, int n,
-                    cudaStream_t st, int *launches)
+                    cudaStream_t st, int *launches, int only_flagged)
 {
-    cudaMemsetAsync(accum16, 0x40, sizeof(uint16_t) * (size_t)n * cells_per_frame, st);
-    k4_ppht_v2<<<n, NT2, 0, st>>>(points, n_points, pmask, accum16, win, cells_per_frame, lines, n_lines, g, hp);
+    if (!only_flagged) cudaMemsetAsync(accum16, 0x40, sizeof(uint16_t) * (size_t)n * cells_per_frame, st);
+    k4_ppht_v2<<<n, NT2, 0, st>>>(points, n_points, pmask, accum16, win, cells_per_frame, lines, n_lines, g, hp,
+                                  only_flagged);
     *launches += 1;
+}
+
+// v3 launch: false if the geometry does not fit (caller uses v2)
+bool launch_ppht_v3(const uint32_t *points, const int *n_points, const uint32_t *pmask, uint32_t *pmask_work,
+                    const int2 *win3, int cells_max, int G, int32_t *lines, int *n_lines, LaneGeom g,
+                    LaneHoughParams hp, int n, cudaStream_t st, int *launches)
+{
+    if (G < 1 || (g.bh * ((g.W + 31) / 32)) % 4 != 0 || ((uintptr_t)pmask % 16) != 0) return false;
+    const int angles = (LANE_NUM_ANGLES + G - 1) / G;
+    int tpa = 384 / angles;                      // aim at ~12 voter warps per CTA
+    tpa = tpa < 1 ? 1 : (tpa > 8 ? 8 : tpa);
+    const int nvw = (angles * tpa + 31) / 32;
+    const size_t smem = (((size_t)cells_max * 2 + 15) & ~(size_t)15) + sizeof(uint32_t) * LIST_CAP3;
+    static bool configured = false;
+    if (!configured) {
+        cudaFuncSetAttribute(k4_ppht_v3, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+        cudaFuncSetAttribute(k4_ppht_v3, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+        configured = true;
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(n * G);
+    cfg.blockDim = dim3((nvw + 1) * 32);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = G; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, k4_ppht_v3, points, n_points, pmask, pmask_work, win3, cells_max, G, nvw, tpa,
+                                       lines, n_lines, g, hp);
+    if (e != cudaSuccess) { cudaGetLastError(); return false; }
+    *launches += 1;
+    return true;
+}
+
+int lane_ppht_list_cap_v3() { return LIST_CAP3; }
+
+// Plan the v3 layout: smallest cluster size whose per-CTA cell count fits shared memory.  win3[n] = (rmin_n,
+// first cell inside CTA n % G).  Returns G (0 if nothing fits) and *cells_max.
+int lane_ppht_plan_v3(const int2 *win, int cells_total, int2 *win3, int *cells_max)
+{
+    int width[LANE_NUM_ANGLES];
+    for (int n = 0; n < LANE_NUM_ANGLES; n++)
+        width[n] = (n + 1 < LANE_NUM_ANGLES ? win[n + 1].y : cells_total) - win[n].y;
+    for (int G = 1; G <= 16; G *= 2) {
+        int off[16] = {0};
+        for (int n = 0; n < LANE_NUM_ANGLES; n++) {
+            win3[n] = make_int2(win[n].x, off[n % G]);
+            off[n % G] += width[n];
+        }
+        int mx = 0;
+        for (int r = 0; r < G; r++) mx = off[r] > mx ? off[r] : mx;
+        mx = (mx + 7) & ~7;
+        if ((size_t)mx * 2 + sizeof(uint32_t) * LIST_CAP3 + 8192 <= 227 * 1024) { *cells_max = mx; return G; }
+    }
+    return 0;
 }
 
 // Per-angle rho windows reachable from the ROI mask: extremes of the (monotone) rounded rho over every

@@ -47,7 +47,10 @@ struct lane_ctx {
     uint32_t *d_accum16 = nullptr;    // [B][cells_per_frame] biased 16-bit cells, two per word
     int2 *d_win = nullptr;            // [180] (rmin, first cell) per angle
     int cells_per_frame = 0;
-    int ppht_v1 = 0;
+    int ppht_v1 = 0, ppht_v2 = 0;     // LANE_B200_K4=v1|v2 pins an older PPHT kernel (A/B checks)
+    int2 *d_win3 = nullptr;           // v3 layout: (rmin, first cell inside the owning CTA)
+    uint32_t *d_pmask_work = nullptr; // [B][G3][bh][WW] private mask copies of the v3 cluster CTAs
+    int G3 = 0, cells_max3 = 0;
     LaneFitScratch fit{};
     int *d_stream_id = nullptr;
     double *d_prev_fit = nullptr;
@@ -104,7 +107,7 @@ void free_all(lane_ctx *c)
 {
     cudaSetDevice(c->device);
     void *ptrs[] = {c->d_frames, c->d_blur, c->d_cls, c->d_cls_dbg, c->d_roi, c->d_pmask, c->d_gray_dbg, c->d_hist,
-                    c->d_roi_bits, c->d_pmask_bits, c->d_edge_bits, c->d_dbg_c, c->d_dbg_s, c->d_accum16, c->d_win,
+                    c->d_roi_bits, c->d_pmask_bits, c->d_edge_bits, c->d_dbg_c, c->d_dbg_s, c->d_accum16, c->d_win, c->d_win3, c->d_pmask_work,
                     c->d_points, c->d_points_dbg, c->d_lut, c->d_thr, c->d_seedsA, c->d_seedsB, c->d_seed_count,
                     c->d_n_edges, c->d_n_points, c->d_rounds, c->d_n_lines, c->d_accum, c->d_lines, c->fit.raw,
                     c->fit.side_n, c->fit.side_flags, c->d_stream_id, c->d_prev_fit, c->d_prev_valid,
@@ -213,8 +216,13 @@ int enqueue(lane_ctx *c, const uint8_t *frames_dev, int n, const int32_t *stream
         launch_ppht(c->d_points, c->d_n_points, c->d_pmask_bits, c->d_accum, c->d_lines, c->d_n_lines, g, c->hp, n,
                     c->st, &L[LANE_STAGE_PPHT]);
     } else {
+        // v3 (cells in distributed shared memory) takes every frame it can; v2 (global 16-bit cells) then sweeps
+        // up the frames v3 flagged (point list larger than its shared-memory list), or runs alone if v3 cannot launch.
+        bool v3 = !c->ppht_v2 && c->G3 > 0 &&
+                  launch_ppht_v3(c->d_points, c->d_n_points, c->d_pmask_bits, c->d_pmask_work, c->d_win3, c->cells_max3,
+                                 c->G3, c->d_lines, c->d_n_lines, g, c->hp, n, c->st, &L[LANE_STAGE_PPHT]);
         launch_ppht_v2(c->d_points, c->d_n_points, c->d_pmask_bits, c->d_accum16, c->d_win, c->cells_per_frame,
-                       c->d_lines, c->d_n_lines, g, c->hp, n, c->st, &L[LANE_STAGE_PPHT]);
+                       c->d_lines, c->d_n_lines, g, c->hp, n, c->st, &L[LANE_STAGE_PPHT], v3 ? 1 : 0);
     }
 
     rc = mark(c, LANE_STAGE_FIT); if (rc) return rc;
@@ -305,6 +313,7 @@ int lane_ctx_create(int device, int height, int width, int max_batch, int max_se
     CUB(dalloc(&ctx->d_rounds, B));
     CUB(dalloc(&ctx->d_n_lines, B));
     CUB(dalloc(&ctx->d_win, LANE_NUM_ANGLES));
+    CUB(dalloc(&ctx->d_win3, LANE_NUM_ANGLES));
     CUB(dalloc(&ctx->d_lines, B * g.max_segments * 4));
     CUB(dalloc(&ctx->fit.raw, B * 6));
     CUB(dalloc(&ctx->fit.side_n, B * 2));
@@ -317,6 +326,7 @@ int lane_ctx_create(int device, int height, int width, int max_batch, int max_se
         ctx->force_tile = e && !strcmp(e, "tile");
         e = getenv("LANE_B200_K4");
         ctx->ppht_v1 = e && !strcmp(e, "v1");
+        ctx->ppht_v2 = e && !strcmp(e, "v2");
         e = getenv("LANE_B200_K2");
         ctx->force_generic_k2 = e && !strcmp(e, "generic");
     }
@@ -381,6 +391,13 @@ int lane_set_roi_mask(lane_ctx *c, const uint8_t *mask)
         if (c->d_accum16) cudaFree(c->d_accum16);
         c->d_accum16 = nullptr;
         CU(dalloc(&c->d_accum16, (size_t)c->max_batch * (c->cells_per_frame / 2)));
+        int2 win3[LANE_NUM_ANGLES];
+        c->G3 = lane_ppht_plan_v3(win, c->cells_per_frame, win3, &c->cells_max3);
+        CU(cudaMemcpy(c->d_win3, win3, sizeof(win3), cudaMemcpyHostToDevice));
+        if (c->d_pmask_work) cudaFree(c->d_pmask_work);
+        c->d_pmask_work = nullptr;
+        if (c->G3 > 0)
+            CU(dalloc(&c->d_pmask_work, (size_t)c->max_batch * c->G3 * std::max(g.bh, 1) * WW));
     }
     CU(dalloc(&c->d_pmask_bits, (size_t)c->max_batch * std::max(g.bh, 1) * WW));
     CU(dalloc(&c->d_points, (size_t)c->max_batch * g.max_points));
