@@ -43,6 +43,11 @@ __device__ __forceinline__ int rho_of(int x, int y, float cs, float sn)
     return __float2int_rn(__fadd_rn(__fmul_rn((float)x, cs), __fmul_rn((float)y, sn)));
 }
 
+__device__ __forceinline__ int rho_f(float x, float y, float cs, float sn)
+{
+    return __float2int_rn(__fadd_rn(__fmul_rn(x, cs), __fmul_rn(y, sn)));
+}
+
 struct WalkSetup {
     int x0, y0, dx0, dy0, xflag;
 };
@@ -499,7 +504,7 @@ __global__ void __launch_bounds__(NT2) k4_ppht_v2(uint32_t *__restrict__ points_
 // 64-bit word per CTA per batch (first triggering point) and one per trigger (arg-max), exchanged
 // through DSMEM slots with a sequence number -- no cluster barrier on the hot path.
 constexpr int BATCH3 = 64;
-constexpr int LIST_CAP3 = 4096;
+constexpr int LIST_CAP3 = 3072;
 
 struct XchgSlots {
     unsigned long long v[2][16];   // [seq parity][source rank] = seq << 32 | payload
@@ -544,7 +549,7 @@ __device__ __forceinline__ uint32_t cluster_reduce(XchgSlots *slots, unsigned &s
 
 constexpr int FLAG_CAP = 48;
 constexpr unsigned CBIAS = 0x4000u;
-constexpr int HITS_CAP = 768;
+constexpr int HITS_CAP = 512;
 
 __device__ __forceinline__ int scell_add(uint32_t *cells32, int cell, int delta)   // value BEFORE the add
 {
@@ -571,6 +576,8 @@ __global__ void k4_ppht_v3(const uint32_t *__restrict__ points_all, const int *_
     uint32_t *s_list = reinterpret_cast<uint32_t *>(dyn + (((size_t)cells_max * 2 + 15) & ~(size_t)15));
     __shared__ uint32_t s_buf[2][BATCH3];
     __shared__ uint32_t s_rnd[BATCH3];
+    __shared__ float s_fx[BATCH3], s_fy[BATCH3];     // batch points as float32, converted once
+    __shared__ float s_hx[HITS_CAP], s_hy[HITS_CAP];
     __shared__ XchgSlots s_slots;
     __shared__ int s_trig, s_nflag;
     __shared__ int s_flag_cell[FLAG_CAP], s_flag_slot[FLAG_CAP];
@@ -578,7 +585,6 @@ __global__ void k4_ppht_v3(const uint32_t *__restrict__ points_all, const int *_
     __shared__ int s_end[2][2];
     __shared__ int s_nsteps[2];
     __shared__ int s_good;
-    __shared__ uint32_t s_hits[HITS_CAP];
     __shared__ int s_nhits;
     __shared__ WalkSetup s_walk;
 
@@ -684,6 +690,7 @@ __global__ void k4_ppht_v3(const uint32_t *__restrict__ points_all, const int *_
                     const uint32_t pt = batch[k];
                     if (pt != SKIP) {
                         const int x = pt & 0xFFFF, y = pt >> 16;
+                        s_fx[k] = (float)x; s_fy[k] = (float)y;
                         if (!((__ldcg(&pm[(y - g.by0) * WW + (x >> 5)]) >> (x & 31)) & 1u)) batch[k] = SKIP;
                     }
                 }
@@ -691,9 +698,8 @@ __global__ void k4_ppht_v3(const uint32_t *__restrict__ points_all, const int *_
                 bar_v();
                 if (active) {                                         // order-free votes, all voter threads
                     for (int k = k0 + sub; k < P; k += tpa) {
-                        const uint32_t pt = batch[k];
-                        if (pt == SKIP) continue;
-                        const int c = cell0 + rho_of(pt & 0xFFFF, pt >> 16, cs, sn);
+                        if (batch[k] == SKIP) continue;
+                        const int c = cell0 + rho_f(s_fx[k], s_fy[k], cs, sn);
                         if (scell_add(cells32, c, 1) + 1 >= hp.threshold) {
                             const int i = atomicAdd(&s_nflag, 1);
                             if (i < FLAG_CAP) { s_flag_cell[i] = c; s_flag_slot[i] = slot; }
@@ -752,10 +758,8 @@ __global__ void k4_ppht_v3(const uint32_t *__restrict__ points_all, const int *_
                 if (t == BATCH3) break;
                 int key = 0;                                          // (value, -angle) packed for a max-reduce
                 if (active) {
-                    for (int k = t + 1 + sub; k < P; k += tpa) {      // roll back the votes behind the trigger
-                        const uint32_t pt = batch[k];
-                        if (pt != SKIP) scell_add(cells32, cell0 + rho_of(pt & 0xFFFF, pt >> 16, cs, sn), -1);
-                    }
+                    for (int k = t + 1 + sub; k < P; k += tpa)        // roll back the votes behind the trigger
+                        if (batch[k] != SKIP) scell_add(cells32, cell0 + rho_f(s_fx[k], s_fy[k], cs, sn), -1);
                 }
                 bar_v();
                 if (active && sub == 0) {
@@ -857,17 +861,17 @@ __global__ void k4_ppht_v3(const uint32_t *__restrict__ points_all, const int *_
                             step_pixel(w, k, s, j1, i1);
                             if (i1 >= g.by0 && i1 < g.by1 && j1 >= 0 && j1 < g.W) {
                                 const uint32_t bit = 1u << (j1 & 31);
-                                if (atomicAnd(&pm[(i1 - g.by0) * WW + (j1 >> 5)], ~bit) & bit)
-                                    s_hits[atomicAdd(&s_nhits, 1)] = ((uint32_t)i1 << 16) | (uint32_t)j1;
+                                if (atomicAnd(&pm[(i1 - g.by0) * WW + (j1 >> 5)], ~bit) & bit) {
+                                    const int h = atomicAdd(&s_nhits, 1);
+                                    s_hx[h] = (float)j1; s_hy[h] = (float)i1;
+                                }
                             }
                         }
                         bar_v();
                         if (s_good && active) {
                             const int nh = s_nhits;
-                            for (int h = sub; h < nh; h += tpa) {
-                                const uint32_t pt = s_hits[h];
-                                scell_add(cells32, cell0 + rho_of(pt & 0xFFFF, pt >> 16, cs, sn), -1);
-                            }
+                            for (int h = sub; h < nh; h += tpa)
+                                scell_add(cells32, cell0 + rho_f(s_hx[h], s_hy[h], cs, sn), -1);
                         }
                         bar_v();
                     }
@@ -936,7 +940,9 @@ int lane_ppht_plan_v3(const int2 *win, int cells_total, int2 *win3, int *cells_m
     int width[LANE_NUM_ANGLES];
     for (int n = 0; n < LANE_NUM_ANGLES; n++)
         width[n] = (n + 1 < LANE_NUM_ANGLES ? win[n + 1].y : cells_total) - win[n].y;
+    for (int pass = 0; pass < 2; pass++)
     for (int G = 1; G <= 16; G *= 2) {
+        const size_t budget = pass == 0 ? 112 * 1024 : 226 * 1024;   // first try to fit two CTAs per SM
         int off[16] = {0};
         for (int n = 0; n < LANE_NUM_ANGLES; n++) {
             win3[n] = make_int2(win[n].x, off[n % G]);
@@ -945,7 +951,7 @@ int lane_ppht_plan_v3(const int2 *win, int cells_total, int2 *win3, int *cells_m
         int mx = 0;
         for (int r = 0; r < G; r++) mx = off[r] > mx ? off[r] : mx;
         mx = (mx + 7) & ~7;
-        if ((size_t)mx * 2 + sizeof(uint32_t) * LIST_CAP3 + 8192 <= 227 * 1024) { *cells_max = mx; return G; }
+        if ((size_t)mx * 2 + sizeof(uint32_t) * LIST_CAP3 + 4608 <= budget) { *cells_max = mx; return G; }
     }
     return 0;
 }
