@@ -31,16 +31,12 @@ constexpr int SPX = 16;
 constexpr int STRIP_OUT = 30 * SPX;
 
 struct K2Args {
-    const uint8_t *blur;
-    const uint32_t *hist;
-    const uint8_t *lut_low, *lut_high;
+    const uint32_t *c_bits, *s_bits;   // [n][H][WW] candidate / strong planes from k2a_sobel_nms
     const uint32_t *roi_bits;      // [H][WW]
-    int4 *thr;
     int *n_edges, *rounds, *n_points;
     uint32_t *points;              // [n][max_points]
     uint32_t *pmask_bits;          // [n][bh][WW]
     uint32_t *edge_bits;           // [n][H][WW]
-    uint32_t *dbg_c, *dbg_s;       // optional pre-hysteresis planes [n][H][WW]
     int H, W, WW, R;               // R = rows per band
     LaneGeom g;
 };
@@ -170,10 +166,9 @@ __device__ int median_x2_warp(const uint32_t *h, long long P, int lane)
 }
 
 // phase 1 for one (strip, row range) task; writes C/S words of rows [q0,q1) into the band's planes
-__device__ void canny_rows(const K2Args &A, const uint8_t *blur_f, int strip, int q0, int q1, int b0, uint32_t *C,
-                           uint32_t *S, int lane, int low, int high)
+__device__ void canny_rows(int H, int W, int WW, const uint8_t *blur_f, int strip, int q0, int q1, int row0,
+                           uint32_t *Cw, uint32_t *Sw, int lane, int low, int high)
 {
-    const int H = A.H, W = A.W, WW = A.WW;
     const int xl = strip * STRIP_OUT - SPX + SPX * lane;
     const bool in_img = xl >= 0 && xl < W;
     const bool left_edge = xl == 0, right_edge = xl + SPX == W;
@@ -251,15 +246,49 @@ __device__ void canny_rows(const K2Args &A, const uint8_t *blur_f, int strip, in
             const uint32_t v = keep | ((keep & strong1) << 16);
             const uint32_t o = __shfl_down_sync(0xffffffffu, v, 1);
             if (writer) {
-                const int lr = n - b0;
-                C[lr * WW + word] = (v & 0xFFFFu) | (o << 16);
-                S[(lr + 1) * WW + word] = (v >> 16) | (o & 0xFFFF0000u);
+                const int lr = n - row0;
+                Cw[(size_t)lr * WW + word] = (v & 0xFFFFu) | (o << 16);
+                Sw[(size_t)lr * WW + word] = (v >> 16) | (o & 0xFFFF0000u);
             }
         }
 #pragma unroll
         for (int j = 0; j < 8; j++) { B0[j] = B1[j]; B1[j] = B2[j]; M0[j] = M1[j]; M1[j] = M2[j]; }
         l0 = l1; r0 = r1; l1 = l2; r1 = r2;
         cand1 = cand2; strong1 = strong2; cls1 = cls2;
+    }
+}
+
+
+// ---- K2a: Sobel + NMS + double threshold as a persistent warp-task kernel ---------------------------
+// Warps pull (frame, band, strip) tasks from a global counter and write the candidate plane C and the
+// strong plane S (32 px per word) to global memory; perfectly load-balanced, no barriers at all.
+constexpr int K2A_WARPS = 4;
+constexpr int K2A_BAND = 64;
+
+__global__ void __launch_bounds__(K2A_WARPS * 32) k2a_sobel_nms(const uint8_t *__restrict__ blur, const uint32_t *__restrict__ hist,
+                                                               const uint8_t *__restrict__ lut_low,
+                                                               const uint8_t *__restrict__ lut_high, int4 *__restrict__ thr,
+                                                               uint32_t *__restrict__ c_bits, uint32_t *__restrict__ s_bits,
+                                                               int *__restrict__ task_counter, int n_frames, int H, int W)
+{
+    const int lane = threadIdx.x & 31;
+    const int WW = (W + 31) / 32;
+    const int n_strips = (W + STRIP_OUT - 1) / STRIP_OUT;
+    const int n_bands = (H + K2A_BAND - 1) / K2A_BAND;
+    const int n_tasks = n_frames * n_bands * n_strips;
+    for (;;) {
+        int task = 0;
+        if (lane == 0) task = atomicAdd(task_counter, 1);
+        task = __shfl_sync(0xffffffffu, task, 0);
+        if (task >= n_tasks) break;
+        const int strip = task % n_strips, band = (task / n_strips) % n_bands, f = task / (n_strips * n_bands);
+        const int m2 = median_x2_warp(hist + f * 256, (long long)H * W, lane);
+        int low = lut_low[m2], high = lut_high[m2];
+        if (low > high) { int t = low; low = high; high = t; }
+        if (band == 0 && strip == 0 && lane == 0) thr[f] = make_int4(m2, low, high, 0);
+        const int q0 = band * K2A_BAND, q1 = min(q0 + K2A_BAND, H);
+        canny_rows(H, W, WW, blur + (size_t)f * H * W, strip, q0, q1, 0, c_bits + (size_t)f * H * WW,
+                   s_bits + (size_t)f * H * WW, lane, low, high);
     }
 }
 
@@ -296,47 +325,20 @@ __global__ void __launch_bounds__(K2T) k2_canny_cluster(K2Args A)
     const int G = (int)cluster.num_blocks(), rank = (int)cluster.block_rank();
     const int f = blockIdx.x / G;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    const int H = A.H, W = A.W, WW = A.WW, R = A.R;
+    const int H = A.H, WW = A.WW, R = A.R;
     const int b0 = rank * R, b1 = min(b0 + R, H), Rv = max(b1 - b0, 0);
     uint32_t *C = smem;                         // [R][WW]
     uint32_t *S = smem + (size_t)R * WW;        // [R+2][WW], row 0 / Rv+1 = neighbour bands
     int *rowoff = reinterpret_cast<int *>(S + (size_t)(R + 2) * WW);   // [R+1]
-    __shared__ int s_thr[3];
     __shared__ int s_flag, s_total, s_base, s_red[K2T / 32];
 
-    for (int i = tid; i < R * WW; i += K2T) C[i] = 0;
-    for (int i = tid; i < (R + 2) * WW; i += K2T) S[i] = 0;
-    if (wid == 0) {
-        int m2 = median_x2_warp(A.hist + f * 256, (long long)H * W, lane);
-        if (lane == 0) {
-            int lo = A.lut_low[m2], hi = A.lut_high[m2];
-            if (lo > hi) { int t = lo; lo = hi; hi = t; }
-            s_thr[0] = m2; s_thr[1] = lo; s_thr[2] = hi;
-            if (rank == 0) A.thr[f] = make_int4(m2, lo, hi, 0);
-        }
-    }
-    __syncthreads();
-    const int low = s_thr[1], high = s_thr[2];
-
-    // ---- phase 1: warps split the band into (strip, sub-band) tasks
+    // ---- phase 1 ran in k2a_sobel_nms: load this band's candidate / strong planes
     {
-        const int n_strips = (W + STRIP_OUT - 1) / STRIP_OUT;
-        const int n_sub = max(1, (K2T / 32) / n_strips);
-        const int sub_rows = (Rv + n_sub - 1) / n_sub;
-        const uint8_t *blur_f = A.blur + (size_t)f * H * W;
-        for (int t = wid; t < n_strips * n_sub; t += K2T / 32) {
-            const int strip = t % n_strips, sub = t / n_strips;
-            const int q0 = b0 + sub * sub_rows, q1 = min(q0 + sub_rows, b1);
-            if (q0 < q1) canny_rows(A, blur_f, strip, q0, q1, b0, C, S, lane, low, high);
-        }
+        const uint32_t *cg = A.c_bits + ((size_t)f * H + b0) * WW, *sg = A.s_bits + ((size_t)f * H + b0) * WW;
+        for (int i = tid; i < Rv * WW; i += K2T) { C[i] = cg[i]; S[WW + i] = sg[i]; }
+        for (int i = tid; i < WW; i += K2T) { S[i] = 0; S[(size_t)(Rv + 1) * WW + i] = 0; }
     }
     __syncthreads();
-    if (A.dbg_c) {
-        for (int i = tid; i < Rv * WW; i += K2T) {
-            A.dbg_c[((size_t)f * H + b0) * WW + i] = C[i];
-            A.dbg_s[((size_t)f * H + b0) * WW + i] = S[WW + i];
-        }
-    }
 
     // ---- phase 2: hysteresis
     int rounds = 0;
@@ -491,8 +493,8 @@ __global__ void k_mask_rows(const uint32_t *__restrict__ edge_bits, const uint32
 // generic byte-map kernels).
 bool launch_canny_cluster(const uint8_t *blur, const uint32_t *hist, const uint8_t *lut_low, const uint8_t *lut_high,
                           const uint32_t *roi_bits, int4 *thr, int *n_edges, int *rounds, uint32_t *points,
-                          int *n_points, uint32_t *pmask_bits, uint32_t *edge_bits, uint32_t *dbg_c, uint32_t *dbg_s,
-                          LaneGeom g, int n, cudaStream_t st, int *launches)
+                          int *n_points, uint32_t *pmask_bits, uint32_t *edge_bits, uint32_t *c_bits, uint32_t *s_bits,
+                          int *task_counter, LaneGeom g, int n, cudaStream_t st, int *launches)
 {
     const int H = g.H, W = g.W, WW = (W + 31) / 32;
     if (W % 16 != 0 || ((uintptr_t)blur % 16) != 0) return false;
@@ -507,15 +509,21 @@ bool launch_canny_cluster(const uint8_t *blur, const uint32_t *hist, const uint8
     }
     if (smem > 220 * 1024) return false;
     static bool configured = false;
+    static int sms = 0;
     if (!configured) {
         cudaFuncSetAttribute(k2_canny_cluster, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
         cudaFuncSetAttribute(k2_canny_cluster, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
         configured = true;
     }
+    cudaMemsetAsync(task_counter, 0, sizeof(int), st);
+    k2a_sobel_nms<<<sms * 5, K2A_WARPS * 32, 0, st>>>(blur, hist, lut_low, lut_high, thr, c_bits, s_bits, task_counter, n, H, W);
     K2Args A;
-    A.blur = blur; A.hist = hist; A.lut_low = lut_low; A.lut_high = lut_high; A.roi_bits = roi_bits;
-    A.thr = thr; A.n_edges = n_edges; A.rounds = rounds; A.n_points = n_points; A.points = points;
-    A.pmask_bits = pmask_bits; A.edge_bits = edge_bits; A.dbg_c = dbg_c; A.dbg_s = dbg_s;
+    A.c_bits = c_bits; A.s_bits = s_bits; A.roi_bits = roi_bits;
+    A.n_edges = n_edges; A.rounds = rounds; A.n_points = n_points; A.points = points;
+    A.pmask_bits = pmask_bits; A.edge_bits = edge_bits;
     A.H = H; A.W = W; A.WW = WW; A.R = R; A.g = g;
     cudaMemsetAsync(n_edges, 0, sizeof(int) * n, st);
     cudaMemsetAsync(n_points, 0, sizeof(int) * n, st);
@@ -531,7 +539,7 @@ bool launch_canny_cluster(const uint8_t *blur, const uint32_t *hist, const uint8
     cfg.numAttrs = 1;
     cudaError_t e = cudaLaunchKernelEx(&cfg, k2_canny_cluster, A);
     if (e != cudaSuccess) { cudaGetLastError(); return false; }
-    *launches += 1;
+    *launches += 2;
     return true;
 }
 

@@ -30,7 +30,7 @@ struct lane_ctx {
     uint32_t *d_roi_bits = nullptr;   // [H][WW] bit-plane of the ROI mask
     uint32_t *d_pmask_bits = nullptr; // [B][bh][WW] ROI-masked edges (the HoughLinesP mask)
     uint32_t *d_edge_bits = nullptr;  // [B][H][WW] Canny map
-    uint32_t *d_dbg_c = nullptr, *d_dbg_s = nullptr;   // debug: pre-hysteresis candidate / strong planes
+    uint32_t *d_dbg_c = nullptr, *d_dbg_s = nullptr;   // [B][H][WW] candidate / strong planes before hysteresis
     // generic-width fallback (byte maps), allocated on first use
     uint8_t *d_cls = nullptr, *d_cls_dbg = nullptr, *d_roi = nullptr, *d_pmask = nullptr;
     uint8_t *h_roi = nullptr;
@@ -185,9 +185,8 @@ int enqueue(lane_ctx *c, const uint8_t *frames_dev, int n, const int32_t *stream
     rc = mark(c, LANE_STAGE_CANNY); if (rc) return rc;
     c->last_cluster = !c->force_generic_k2 &&
         launch_canny_cluster(c->d_blur, c->d_hist, c->d_lut, c->d_lut + 511, c->d_roi_bits, c->d_thr, c->d_n_edges,
-                             c->d_rounds, c->d_points, c->d_n_points, c->d_pmask_bits, c->d_edge_bits,
-                             c->debug ? c->d_dbg_c : nullptr, c->debug ? c->d_dbg_s : nullptr, g, n, c->st,
-                             &L[LANE_STAGE_CANNY]);
+                             c->d_rounds, c->d_points, c->d_n_points, c->d_pmask_bits, c->d_edge_bits, c->d_dbg_c,
+                             c->d_dbg_s, c->d_task_counter, g, n, c->st, &L[LANE_STAGE_CANNY]);
     if (c->last_cluster) {
         rc = mark(c, LANE_STAGE_COMPACT); if (rc) return rc;
     } else {
@@ -305,6 +304,8 @@ int lane_ctx_create(int device, int height, int width, int max_batch, int max_se
     const size_t WW = (width + 31) / 32;
     CUB(dalloc(&ctx->d_roi_bits, (size_t)height * WW));
     CUB(dalloc(&ctx->d_edge_bits, B * height * WW));
+    CUB(dalloc(&ctx->d_dbg_c, B * height * WW));
+    CUB(dalloc(&ctx->d_dbg_s, B * height * WW));
     CUB(dalloc(&ctx->d_hist, B * 256));
     CUB(dalloc(&ctx->d_lut, 1022));
     CUB(dalloc(&ctx->d_thr, B));

@@ -53,8 +53,8 @@ void launch_compact(const uint8_t *edges, const uint8_t *roi, uint8_t *pmask, ui
 // cluster form of K2 (bit-planes in distributed shared memory); false => geometry not supported, use the kernels above
 bool launch_canny_cluster(const uint8_t *blur, const uint32_t *hist, const uint8_t *lut_low, const uint8_t *lut_high,
                           const uint32_t *roi_bits, int4 *thr, int *n_edges, int *rounds, uint32_t *points,
-                          int *n_points, uint32_t *pmask_bits, uint32_t *edge_bits, uint32_t *dbg_c, uint32_t *dbg_s,
-                          LaneGeom g, int n, cudaStream_t st, int *launches);
+                          int *n_points, uint32_t *pmask_bits, uint32_t *edge_bits, uint32_t *c_bits, uint32_t *s_bits,
+                          int *task_counter, LaneGeom g, int n, cudaStream_t st, int *launches);
 void launch_bytes_to_bits(const uint8_t *bytes, uint32_t *bits, int n, int rows, int W, int row_stride,
                           cudaStream_t st, int *launches);
 void launch_mask_rows(const uint32_t *edge_bits, const uint32_t *roi_bits, uint32_t *pmask_bits, LaneGeom g, int n,
