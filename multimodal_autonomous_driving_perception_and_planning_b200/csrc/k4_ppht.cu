@@ -12,6 +12,8 @@
 #include "lane_common.cuh"
 
 #include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
 
 __constant__ float c_ppht_cos[LANE_NUM_ANGLES], c_ppht_sin[LANE_NUM_ANGLES];
 
@@ -549,7 +551,8 @@ __device__ __forceinline__ uint32_t cluster_reduce(XchgSlots *slots, unsigned &s
 
 constexpr int FLAG_CAP = 48;
 constexpr unsigned CBIAS = 0x4000u;
-constexpr int HITS_CAP = 512;
+constexpr int HITS_CAP = 256;
+constexpr int WPT = 4;             // pass-1 walk steps per thread per round
 
 __device__ __forceinline__ int scell_add(uint32_t *cells32, int cell, int delta)   // value BEFORE the add
 {
@@ -566,10 +569,10 @@ __device__ __forceinline__ int scell_get(const uint32_t *cells32, int cell)
 // shared-memory atomics (order-free); a vote that sees its bin at or above the threshold flags the
 // bin, and the exact first triggering point is then recovered per flagged bin by replaying only that
 // bin over the batch (counts inside a batch are monotone, so no other bin can trigger earlier).
-__global__ void k4_ppht_v3(const uint32_t *__restrict__ points_all, const int *__restrict__ n_points,
+__global__ void __launch_bounds__(416, 2) k4_ppht_v3(const uint32_t *__restrict__ points_all, const int *__restrict__ n_points,
                            const uint32_t *__restrict__ pmask_all, uint32_t *__restrict__ pmask_work,
                            const int2 *__restrict__ win, int cells_max, int G, int nvw, int tpa,
-                           int32_t *__restrict__ lines_all, int *__restrict__ n_lines, LaneGeom g, LaneHoughParams hp)
+                           int32_t *__restrict__ lines_all, int *__restrict__ n_lines, LaneGeom g, LaneHoughParams hp, int prof)
 {
     extern __shared__ __align__(16) unsigned char dyn[];
     uint32_t *cells32 = reinterpret_cast<uint32_t *>(dyn);
@@ -586,6 +589,8 @@ __global__ void k4_ppht_v3(const uint32_t *__restrict__ points_all, const int *_
     __shared__ int s_nsteps[2];
     __shared__ int s_good;
     __shared__ int s_nhits;
+    __shared__ unsigned s_whit[2][24], s_wib[2][24];   // pass-1 ballots of one round, per direction
+    __shared__ int s_wlast[2], s_wdone[2];
     __shared__ WalkSetup s_walk;
 
     unsigned rank;
@@ -626,6 +631,15 @@ __global__ void k4_ppht_v3(const uint32_t *__restrict__ points_all, const int *_
     uint64_t rng = 0xFFFFFFFFFFFFFFFFull;
     int remaining = count0, nl = 0;
     unsigned seq = 0;
+#ifdef LANE_PPHT_PROF   // cycle accounting of thread 0 (build with -DLANE_PPHT_PROF, run with LANE_B200_PPHT_PROF=1)
+    long long tA = 0, tB = 0, tC = 0, tD = 0, tE = 0, tG = 0, tH = 0, tI = 0, t0 = 0, tStart = clock64();
+    int nTrig = 0, nIter = 0;
+#define TICK(acc) do { if (prof && tid == 0) { long long now_ = clock64(); acc += now_ - t0; t0 = now_; } } while (0)
+#define PROF(x) x
+#else
+#define TICK(acc) do { } while (0)
+#define PROF(x)
+#endif
     __syncthreads();
     asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
     if (dense) {
@@ -685,7 +699,9 @@ __global__ void k4_ppht_v3(const uint32_t *__restrict__ points_all, const int *_
             if (bi + 1 < n_batches) draw(s_buf[(bi + 1) & 1]);
         } else {
             int k0 = 0;
+            PROF(if (prof && tid == 0) t0 = clock64();)
             while (k0 < P) {
+                PROF(nIter++;)
                 for (int k = k0 + tid; k < P; k += NVT) {            // drop points an earlier walk removed
                     const uint32_t pt = batch[k];
                     if (pt != SKIP) {
@@ -696,17 +712,29 @@ __global__ void k4_ppht_v3(const uint32_t *__restrict__ points_all, const int *_
                 }
                 if (tid == 0) { s_trig = BATCH3; s_nflag = 0; }
                 bar_v();
+                TICK(tA);
                 if (active) {                                         // order-free votes, all voter threads
-                    for (int k = k0 + sub; k < P; k += tpa) {
-                        if (batch[k] == SKIP) continue;
-                        const int c = cell0 + rho_f(s_fx[k], s_fy[k], cs, sn);
-                        if (scell_add(cells32, c, 1) + 1 >= hp.threshold) {
-                            const int i = atomicAdd(&s_nflag, 1);
-                            if (i < FLAG_CAP) { s_flag_cell[i] = c; s_flag_slot[i] = slot; }
+                    for (int kk = k0 + sub; kk < P; kk += 8 * tpa) {   // eight atomics in flight per thread
+                        int c[8], v[8];
+#pragma unroll
+                        for (int u = 0; u < 8; u++) {
+                            const int k = kk + u * tpa;
+                            v[u] = -0x40000000;
+                            if (k < P && batch[k] != SKIP) {
+                                c[u] = cell0 + rho_f(s_fx[k], s_fy[k], cs, sn);
+                                v[u] = scell_add(cells32, c[u], 1);
+                            }
                         }
+#pragma unroll
+                        for (int u = 0; u < 8; u++)
+                            if (v[u] + 1 >= hp.threshold) {
+                                const int i = atomicAdd(&s_nflag, 1);
+                                if (i < FLAG_CAP) { s_flag_cell[i] = c[u]; s_flag_slot[i] = slot; }
+                            }
                     }
                 }
                 bar_v();
+                TICK(tB);
                 const int nflag = s_nflag;
                 if (nflag > FLAG_CAP) {
                     // too many flagged bins to replay one by one: redo this batch in point order, one thread per angle
@@ -728,34 +756,44 @@ __global__ void k4_ppht_v3(const uint32_t *__restrict__ points_all, const int *_
                     }
                     bar_v();
                 } else if (nflag > 0) {
-                    for (int e = tid; e < nflag; e += NVT) {          // replay one flagged bin over the batch
+                    for (int e = wid; e < nflag; e += nvw) {          // one warp replays one flagged bin over the batch
                         const int c = s_flag_cell[e], an = s_flag_slot[e] * G + (int)rank;
                         const float ecs = c_ppht_cos[an], esn = c_ppht_sin[an];
                         const int2 ew = win[an];
                         const int ec0 = ew.y - ew.x;
-                        int cnt = 0;
-                        for (int k = k0; k < P; k++) {
-                            const uint32_t pt = batch[k];
-                            if (pt != SKIP && ec0 + rho_of(pt & 0xFFFF, pt >> 16, ecs, esn) == c) cnt++;
+                        unsigned bal[BATCH3 / 32];
+                        int total = 0;
+#pragma unroll
+                        for (int gq = 0; gq < BATCH3 / 32; gq++) {
+                            const int k = gq * 32 + lane;
+                            const bool m = k >= k0 && k < P && batch[k] != SKIP && ec0 + rho_f(s_fx[k], s_fy[k], ecs, esn) == c;
+                            bal[gq] = __ballot_sync(0xffffffffu, m);
+                            total += __popc(bal[gq]);
                         }
-                        int running = scell_get(cells32, c) - cnt, first = BATCH3;
-                        for (int k = k0; k < P; k++) {
-                            const uint32_t pt = batch[k];
-                            if (pt != SKIP && ec0 + rho_of(pt & 0xFFFF, pt >> 16, ecs, esn) == c && ++running >= hp.threshold) {
-                                first = k;
-                                break;
+                        int need = hp.threshold - (scell_get(cells32, c) - total);   // votes until the bin reaches the threshold
+                        if (need < 1) need = 1;                       // already there: its first vote triggers
+                        int first = BATCH3;
+#pragma unroll
+                        for (int gq = 0; gq < BATCH3 / 32; gq++) {
+                            const int pc = __popc(bal[gq]);
+                            if (first == BATCH3) {
+                                if (need <= pc) first = gq * 32 + (int)__fns(bal[gq], 0, need);
+                                else need -= pc;
                             }
                         }
-                        if (first < BATCH3) atomicMin(&s_trig, first);
+                        if (lane == 0 && first < BATCH3) atomicMin(&s_trig, first);
                     }
                     bar_v();
                 }
+                TICK(tC);
                 if (G > 1) {
                     if (tid == 0) s_trig = (int)cluster_reduce(&s_slots, seq, G, rank, (uint32_t)s_trig, 0);
                     bar_v();
                 }
+                TICK(tD);
                 const int t = s_trig;
                 if (t == BATCH3) break;
+                PROF(nTrig++;)
                 int key = 0;                                          // (value, -angle) packed for a max-reduce
                 if (active) {
                     for (int k = t + 1 + sub; k < P; k += tpa)        // roll back the votes behind the trigger
@@ -794,50 +832,76 @@ __global__ void k4_ppht_v3(const uint32_t *__restrict__ points_all, const int *_
                     s_walk = w;
                 }
                 bar_v();
+                TICK(tE);
                 const WalkSetup w = s_walk;
-                for (int k = wid; k < 2; k += nvw) {                  // pass 1: a warp per direction, 128 steps per round
-                    int last = 0;
-                    bool done = false;
-                    for (int base = 0; !done; base += 128) {
-                        unsigned IBs[4], Hs[4];
+                // ---- pass 1: half of the voter warps per direction; WSTEPS steps of the line are fetched in one
+                // round (every thread issues its loads back to back), ballots go to shared memory, and one lane then
+                // runs cv2's gap logic over the bit string.  Lines longer than a round simply take another round.
+                {
+                    const int half = nvw >= 2 ? nvw / 2 : 1;          // warps per direction
+                    const int kdir = nvw >= 2 ? (wid < half ? 0 : (wid < 2 * half ? 1 : 2)) : 0;
+                    const int ndir_pass = nvw >= 2 ? 1 : 2;           // a single voter warp does the directions one after the other
+                    for (int dp = 0; dp < ndir_pass; dp++) {
+                        const int k = nvw >= 2 ? kdir : dp;
+                        const int wl = nvw >= 2 ? (wid - k * half) : 0;   // warp index inside the direction group
+                        const int gsteps = half * 32 * WPT;
+                        if (tid < 2) { s_wlast[tid] = 0; s_wdone[tid] = 0; }
+                        bar_v();
+                        for (int base = 0;; base += gsteps) {
+                            if (k < 2 && !s_wdone[k]) {
+                                unsigned hb[WPT], ibb[WPT];
 #pragma unroll
-                        for (int j = 0; j < 4; j++) {
-                            int j1, i1;
-                            step_pixel(w, k, base + 32 * j + lane, j1, i1);
-                            const bool ib = j1 >= 0 && j1 < g.W && i1 >= 0 && i1 < g.H;
-                            bool hit = false;
-                            if (ib && i1 >= g.by0 && i1 < g.by1)
-                                hit = ((__ldcg(&pm[(i1 - g.by0) * WW + (j1 >> 5)]) >> (j1 & 31)) & 1u) != 0;
-                            IBs[j] = __ballot_sync(0xffffffffu, ib);
-                            Hs[j] = __ballot_sync(0xffffffffu, hit);
-                        }
+                                for (int j = 0; j < WPT; j++) {
+                                    int j1, i1;
+                                    step_pixel(w, k, base + (wl * WPT + j) * 32 + lane, j1, i1);
+                                    const bool ib = j1 >= 0 && j1 < g.W && i1 >= 0 && i1 < g.H;
+                                    bool hit = false;
+                                    if (ib && i1 >= g.by0 && i1 < g.by1)
+                                        hit = ((__ldcg(&pm[(i1 - g.by0) * WW + (j1 >> 5)]) >> (j1 & 31)) & 1u) != 0;
+                                    ibb[j] = __ballot_sync(0xffffffffu, ib);
+                                    hb[j] = __ballot_sync(0xffffffffu, hit);
+                                }
+                                if (lane == 0)
 #pragma unroll
-                        for (int j = 0; j < 4; j++) {
-                            if (done) break;
-                            const int b32 = base + 32 * j;
-                            unsigned Hh = Hs[j];
-                            const int limit = (~IBs[j]) ? __ffs(~IBs[j]) - 1 : 32;
-                            if (limit < 32) Hh &= (1u << limit) - 1u;
-                            while (Hh) {
-                                const int p = b32 + __ffs(Hh) - 1;
-                                if (p - last > hp.max_gap + 1) { done = true; break; }
-                                last = p;
-                                Hh &= Hh - 1;
+                                    for (int j = 0; j < WPT; j++) { s_whit[k][wl * WPT + j] = hb[j]; s_wib[k][wl * WPT + j] = ibb[j]; }
                             }
-                            if (!done) {
-                                if (limit < 32) done = true;
-                                else if (b32 + 31 - last > hp.max_gap) done = true;
+                            bar_v();
+                            if (tid < 2 && !s_wdone[tid] && (nvw >= 2 || tid == k)) {   // gap logic over this round's bit string
+                                const int kk = tid;
+                                int last = s_wlast[kk];
+                                bool done = false;
+                                for (int q = 0; q < half * WPT && !done; q++) {
+                                    const int b32 = base + 32 * q;
+                                    unsigned Hh = s_whit[kk][q];
+                                    const unsigned IB = s_wib[kk][q];
+                                    const int limit = (~IB) ? __ffs(~IB) - 1 : 32;
+                                    if (limit < 32) Hh &= (1u << limit) - 1u;
+                                    while (Hh) {
+                                        const int p = b32 + __ffs(Hh) - 1;
+                                        if (p - last > hp.max_gap + 1) { done = true; break; }
+                                        last = p;
+                                        Hh &= Hh - 1;
+                                    }
+                                    if (!done) {
+                                        if (limit < 32) done = true;
+                                        else if (b32 + 31 - last > hp.max_gap) done = true;
+                                    }
+                                }
+                                s_wlast[kk] = last;
+                                if (done) {
+                                    s_wdone[kk] = 1;
+                                    int j1, i1;
+                                    step_pixel(w, kk, last, j1, i1);
+                                    s_end[kk][0] = j1; s_end[kk][1] = i1;
+                                    s_nsteps[kk] = last + 1;
+                                }
                             }
+                            bar_v();
+                            if (nvw >= 2 ? (s_wdone[0] && s_wdone[1]) : s_wdone[k]) break;
                         }
-                    }
-                    if (lane == 0) {
-                        int j1, i1;
-                        step_pixel(w, k, last, j1, i1);
-                        s_end[k][0] = j1; s_end[k][1] = i1;
-                        s_nsteps[k] = last + 1;
                     }
                 }
-                bar_v();
+                TICK(tG);
                 if (tid == 0) {
                     int good = abs(s_end[1][0] - s_end[0][0]) >= hp.min_len || abs(s_end[1][1] - s_end[0][1]) >= hp.min_len;
                     s_good = good;
@@ -876,11 +940,19 @@ __global__ void k4_ppht_v3(const uint32_t *__restrict__ points_all, const int *_
                         bar_v();
                     }
                 }
+                TICK(tH);
                 k0 = t + 1;
             }
         }
+        PROF(if (prof && tid == 0) t0 = clock64();)
         __syncthreads();
+        TICK(tI);
     }
+#ifdef LANE_PPHT_PROF
+    if (prof && tid == 0 && rank == 0 && f < 2)
+        printf("ppht f=%d pts=%d iters=%d trig=%d total=%lld | maskchk=%lld vote=%lld replay=%lld xchg=%lld rollback+argmax+xchg2=%lld pass1=%lld pass2=%lld syncwait=%lld\n",
+               f, count0, nIter, nTrig, clock64() - tStart, tA, tB, tC, tD, tE, tG, tH, tI);
+#endif
     if (tid == 0 && rank == 0) n_lines[f] = nl;
     asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
@@ -925,7 +997,7 @@ bool launch_ppht_v3(const uint32_t *points, const int *n_points, const uint32_t 
     cfg.attrs = attr;
     cfg.numAttrs = 1;
     cudaError_t e = cudaLaunchKernelEx(&cfg, k4_ppht_v3, points, n_points, pmask, pmask_work, win3, cells_max, G, nvw, tpa,
-                                       lines, n_lines, g, hp);
+                                       lines, n_lines, g, hp, getenv("LANE_B200_PPHT_PROF") ? 1 : 0);
     if (e != cudaSuccess) { cudaGetLastError(); return false; }
     *launches += 1;
     return true;
@@ -951,7 +1023,7 @@ int lane_ppht_plan_v3(const int2 *win, int cells_total, int2 *win3, int *cells_m
         int mx = 0;
         for (int r = 0; r < G; r++) mx = off[r] > mx ? off[r] : mx;
         mx = (mx + 7) & ~7;
-        if ((size_t)mx * 2 + sizeof(uint32_t) * LIST_CAP3 + 4608 <= budget) { *cells_max = mx; return G; }
+        if ((size_t)mx * 2 + sizeof(uint32_t) * LIST_CAP3 + 4700 <= budget) { *cells_max = mx; return G; }
     }
     return 0;
 }
