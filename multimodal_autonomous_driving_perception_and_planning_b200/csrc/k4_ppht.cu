@@ -876,11 +876,18 @@ __global__ void __launch_bounds__(416, 2) k4_ppht_v3(const uint32_t *__restrict_
                                     const unsigned IB = s_wib[kk][q];
                                     const int limit = (~IB) ? __ffs(~IB) - 1 : 32;
                                     if (limit < 32) Hh &= (1u << limit) - 1u;
-                                    while (Hh) {
-                                        const int p = b32 + __ffs(Hh) - 1;
-                                        if (p - last > hp.max_gap + 1) { done = true; break; }
-                                        last = p;
-                                        Hh &= Hh - 1;
+                                    if (hp.max_gap >= 31) {           // a gap inside one word can never end the walk
+                                        if (Hh) {
+                                            if (b32 + __ffs(Hh) - 1 - last > hp.max_gap + 1) done = true;
+                                            else last = b32 + 31 - __clz(Hh);
+                                        }
+                                    } else {
+                                        while (Hh) {
+                                            const int p = b32 + __ffs(Hh) - 1;
+                                            if (p - last > hp.max_gap + 1) { done = true; break; }
+                                            last = p;
+                                            Hh &= Hh - 1;
+                                        }
                                     }
                                     if (!done) {
                                         if (limit < 32) done = true;
