@@ -1,0 +1,65 @@
+"""Multi-GPU plumbing for the lane-detection path: one process per GPU, streams sharded, results gathered.
+
+The path shards with no exchange: every stage before the temporal smoothing is
+per frame, and the smoothing state is per camera stream, so whole streams are assigned to ranks and
+nothing crosses GPUs while frames are processed.  The only collective is one gather of the packed
+per-frame ``lane_record`` array to rank 0 (NCCL over NVLink on the GPU box; any torch.distributed
+backend works, the CPU tests use gloo).
+"""
+from __future__ import annotations
+
+from typing import List, Optional, Sequence
+
+import numpy as np
+
+from ._native import RECORD_DTYPE
+
+
+def streams_of_rank(n_streams: int, world_size: int, rank: int) -> List[int]:
+    """Camera streams owned by ``rank``: stream s -> rank s % world_size (BASELINE config 3:
+    8 cameras over 1/2/4/8 GPUs gives 8/4/2/1 whole streams per GPU)."""
+    if world_size < 1 or not (0 <= rank < world_size):
+        raise ValueError(f"bad rank {rank} of {world_size}")
+    return [s for s in range(n_streams) if s % world_size == rank]
+
+
+def gather_records(local: np.ndarray, dst: int = 0, device=None, group=None) -> Optional[List[np.ndarray]]:
+    """Gather every rank's ``RECORD_DTYPE`` array on ``dst`` (ragged lengths allowed).
+
+    Returns the list indexed by rank on ``dst`` and ``None`` elsewhere.  Two collectives: the
+    lengths (all_gather of one int64) and the padded byte payload (gather)."""
+    import torch
+    import torch.distributed as dist
+    if local.dtype != RECORD_DTYPE:
+        raise TypeError("gather_records expects a RECORD_DTYPE array")
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    dev = device if device is not None else torch.device("cpu")
+    n_local = torch.tensor([local.shape[0]], dtype=torch.int64, device=dev)
+    counts = [torch.zeros(1, dtype=torch.int64, device=dev) for _ in range(world)]
+    dist.all_gather(counts, n_local, group=group)
+    counts = [int(c.item()) for c in counts]
+    item = RECORD_DTYPE.itemsize
+    cap = max(max(counts), 1) * item
+    payload = torch.zeros(cap, dtype=torch.uint8, device=dev)
+    if local.shape[0]:
+        raw = torch.from_numpy(np.ascontiguousarray(local).view(np.uint8).reshape(-1))
+        payload[: raw.numel()] = raw.to(dev)
+    bufs = [torch.empty(cap, dtype=torch.uint8, device=dev) for _ in range(world)] if rank == dst else None
+    dist.gather(payload, bufs, dst=dst, group=group)
+    if rank != dst:
+        return None
+    return [b[: counts[r] * item].cpu().numpy().view(RECORD_DTYPE).copy() for r, b in enumerate(bufs)]
+
+
+def merge_stream_major(per_rank: Sequence[np.ndarray], n_streams: int, frames_per_stream: int,
+                       world_size: int) -> np.ndarray:
+    """Reassemble rank-gathered records into [n_streams, frames_per_stream] order, given that each rank
+    processed its streams (``streams_of_rank``) back to back, every stream in temporal order."""
+    out = np.zeros((n_streams, frames_per_stream), RECORD_DTYPE)
+    for rank, recs in enumerate(per_rank):
+        mine = streams_of_rank(n_streams, world_size, rank)
+        if recs.shape[0] != len(mine) * frames_per_stream:
+            raise ValueError(f"rank {rank} returned {recs.shape[0]} records for {len(mine)} streams")
+        for i, s in enumerate(mine):
+            out[s] = recs[i * frames_per_stream:(i + 1) * frames_per_stream]
+    return out
