@@ -211,15 +211,13 @@ def main():
     prev_fit = np.zeros((1, 2, 3), np.float64)
     prev_valid = np.zeros((1, 2), np.uint8)
     rec_bytes = _native.RECORD_DTYPE.itemsize * n
-    gather_buf = None
-    if world > 1:
-        gather_buf = [torch.empty(rec_bytes, dtype=torch.uint8, device=dev) for _ in range(world)] if rank == 0 else None
+    from multimodal_autonomous_driving_perception_and_planning_b200.distributed import RecordGatherer
+    gatherer = RecordGatherer(n, dev) if world > 1 else None
 
     def step():
         recs = ctx.detect(frames_dev.data_ptr(), n, True, None, 1, prev_fit, prev_valid, 0.7, 1 - 0.7)
         if world > 1:
-            t = torch.from_numpy(recs.view(np.uint8)).to(dev)
-            dist.gather(t, gather_buf, dst=0)
+            gatherer.gather(recs, to_host=False)          # the path's only collective (NCCL over NVLink)
         return recs
 
     def barrier():

@@ -63,3 +63,33 @@ def merge_stream_major(per_rank: Sequence[np.ndarray], n_streams: int, frames_pe
         for i, s in enumerate(mine):
             out[s] = recs[i * frames_per_stream:(i + 1) * frames_per_stream]
     return out
+
+
+class RecordGatherer:
+    """Fixed-size gather for steady-state serving: every rank contributes exactly ``n`` records per
+    call, buffers are allocated once (pinned staging + device payload), one collective per call."""
+
+    def __init__(self, n: int, device, dst: int = 0, group=None):
+        import torch
+        import torch.distributed as dist
+        self.n, self.dst, self.group, self.device = n, dst, group, device
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        nbytes = n * RECORD_DTYPE.itemsize
+        self.stage = torch.empty(nbytes, dtype=torch.uint8).pin_memory() if device.type == "cuda" \
+            else torch.empty(nbytes, dtype=torch.uint8)
+        self.payload = torch.empty(nbytes, dtype=torch.uint8, device=device)
+        self.bufs = [torch.empty(nbytes, dtype=torch.uint8, device=device) for _ in range(self.world)] \
+            if self.rank == dst else None
+
+    def gather(self, local: np.ndarray, to_host: bool = True):
+        import torch.distributed as dist
+        if local.shape[0] != self.n or local.dtype != RECORD_DTYPE:
+            raise ValueError("RecordGatherer.gather expects exactly n RECORD_DTYPE records")
+        self.stage.numpy()[:] = np.ascontiguousarray(local).view(np.uint8).reshape(-1)
+        self.payload.copy_(self.stage, non_blocking=True)
+        dist.gather(self.payload, self.bufs, dst=self.dst, group=self.group)
+        if self.rank != self.dst:
+            return None
+        if not to_host:
+            return self.bufs
+        return [b.cpu().numpy().view(RECORD_DTYPE).copy() for b in self.bufs]

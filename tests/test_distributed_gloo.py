@@ -11,7 +11,7 @@ import torch.multiprocessing as mp
 
 from multimodal_autonomous_driving_perception_and_planning_b200 import _native
 from multimodal_autonomous_driving_perception_and_planning_b200.distributed import (
-    gather_records, merge_stream_major, streams_of_rank)
+    RecordGatherer, gather_records, merge_stream_major, streams_of_rank)
 
 
 def test_stream_sharding_is_a_partition():
@@ -43,6 +43,10 @@ def _worker(rank, world, port, n_streams, t, q):
         q.put((merged["n_segments"].tolist(), merged["offset"].tolist(), [len(g) for g in got]))
     else:
         assert got is None
+    if n_streams % world == 0:                      # fixed-size steady-state gather gives the same bytes
+        fixed = RecordGatherer(len(local), torch.device("cpu")).gather(local)
+        if rank == 0:
+            assert all(np.array_equal(a, b) for a, b in zip(fixed, got))
     dist.barrier()
     dist.destroy_process_group()
 
