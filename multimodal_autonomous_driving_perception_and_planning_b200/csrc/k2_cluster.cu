@@ -182,21 +182,26 @@ __device__ void canny_rows(int H, int W, int WW, const uint8_t *blur_f, int stri
 #pragma unroll
     for (int j = 0; j < 8; j++) B0[j] = B1[j] = M0[j] = M1[j] = 0;
 
-    auto load_pairs = [&](int y, uint32_t (&B)[8]) {
+    auto load_raw = [&](int y) {
         const int yy = min(max(y, 0), H - 1);          // BORDER_REPLICATE rows
         uint4 v = make_uint4(0, 0, 0, 0);
         if (in_img) v = __ldg(reinterpret_cast<const uint4 *>(src + (size_t)yy * W));
+        return v;
+    };
+    auto unpack = [&](const uint4 &v, uint32_t (&B)[8]) {   // bytes -> zero-interleaved pairs (= f16x2 denormals)
         B[0] = __byte_perm(v.x, 0, 0x4140); B[1] = __byte_perm(v.x, 0, 0x4342);
         B[2] = __byte_perm(v.y, 0, 0x4140); B[3] = __byte_perm(v.y, 0, 0x4342);
         B[4] = __byte_perm(v.z, 0, 0x4140); B[5] = __byte_perm(v.z, 0, 0x4342);
         B[6] = __byte_perm(v.w, 0, 0x4140); B[7] = __byte_perm(v.w, 0, 0x4342);
     };
-    load_pairs(q0 - 2, B0);
-    load_pairs(q0 - 1, B1);
+    unpack(load_raw(q0 - 2), B0);
+    unpack(load_raw(q0 - 1), B1);
+    uint4 vnext = load_raw(q0);                         // row c+1 of the first step
 
     for (int c = q0 - 1; c <= q1; c++) {               // c = row whose gradient is formed this step
         uint32_t B2[8];
-        load_pairs(c + 1, B2);
+        unpack(vnext, B2);
+        if (c < q1) vnext = load_raw(c + 2);             // prefetch the next step's row behind the arithmetic
         uint32_t M2[8], l2 = 0, r2 = 0, cand2 = 0, strong2 = 0, cls2 = 0;
         const bool row_ok = c >= 0 && c < H;            // the magnitude plane has a zero border
         {
@@ -265,7 +270,7 @@ __device__ void canny_rows(int H, int W, int WW, const uint8_t *blur_f, int stri
 constexpr int K2A_WARPS = 4;
 constexpr int K2A_BAND = 64;
 
-__global__ void __launch_bounds__(K2A_WARPS * 32) k2a_sobel_nms(const uint8_t *__restrict__ blur, const uint32_t *__restrict__ hist,
+__global__ void __launch_bounds__(K2A_WARPS * 32, 5) k2a_sobel_nms(const uint8_t *__restrict__ blur, const uint32_t *__restrict__ hist,
                                                                const uint8_t *__restrict__ lut_low,
                                                                const uint8_t *__restrict__ lut_high, int4 *__restrict__ thr,
                                                                uint32_t *__restrict__ c_bits, uint32_t *__restrict__ s_bits,

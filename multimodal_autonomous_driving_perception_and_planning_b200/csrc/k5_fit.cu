@@ -175,38 +175,67 @@ __global__ void __launch_bounds__(64) k5_fit(const int32_t *__restrict__ lines_a
     }
 }
 
-// one thread per (stream, side): sequential EMA over the stream's frames in batch order
-__global__ void k5_ema(const double *__restrict__ raw, const int *__restrict__ side_n,
-                       const int *__restrict__ stream_id, int n_streams, double *__restrict__ prev_fit,
-                       uint8_t *__restrict__ prev_valid, double smooth, double oms,
-                       lane_record *__restrict__ rec, int n)
+// One CTA per stream.  The EMA is a strictly sequential fp64 recurrence (its roundings must match the
+// reference step by step), so only two threads (left, right) run it -- but out of shared memory: the raw
+// fits of a chunk of frames are staged by the whole CTA first and the smoothed results are written back by
+// the whole CTA afterwards, so the serial loop never waits on global memory.
+constexpr int EMA_CHUNK = 384;
+
+__global__ void __launch_bounds__(256) k5_ema(const double *__restrict__ raw, const int *__restrict__ side_n,
+                                              const int *__restrict__ stream_id, double *__restrict__ prev_fit,
+                                              uint8_t *__restrict__ prev_valid, double smooth, double oms,
+                                              lane_record *__restrict__ rec, int n)
 {
-    int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= n_streams * 2) return;
-    const int s = t >> 1, side = t & 1;
-    double p0 = prev_fit[t * 3], p1 = prev_fit[t * 3 + 1], p2 = prev_fit[t * 3 + 2];
-    bool have = prev_valid[t] != 0;
-    for (int f = 0; f < n; f++) {
-        if ((stream_id ? stream_id[f] : 0) != s) continue;
-        lane_side *o = &rec[f].side[side];
-        int cnt = side_n[2 * f + side];
-        o->n_lines = cnt;
-        if (cnt == 0) { o->valid = 0; continue; }
-        const double *r = raw + ((size_t)f * 2 + side) * 3;
-        double c0 = r[0], c1 = r[1], c2 = r[2];
-        o->raw[0] = c0; o->raw[1] = c1; o->raw[2] = c2;
-        if (have) {
-            c0 = __dadd_rn(__dmul_rn(smooth, p0), __dmul_rn(oms, c0));
-            c1 = __dadd_rn(__dmul_rn(smooth, p1), __dmul_rn(oms, c1));
-            c2 = __dadd_rn(__dmul_rn(smooth, p2), __dmul_rn(oms, c2));
-        }
-        o->valid = 1;
-        o->coeffs[0] = c0; o->coeffs[1] = c1; o->coeffs[2] = c2;
-        o->confidence = fmin(1.0, (double)cnt / 10.0);
-        p0 = c0; p1 = c1; p2 = c2; have = true;
+    __shared__ double s_raw[EMA_CHUNK][2][3], s_out[EMA_CHUNK][2][3];
+    __shared__ int s_cnt[EMA_CHUNK][2];
+    __shared__ unsigned char s_mine[EMA_CHUNK];
+    const int s = blockIdx.x, tid = threadIdx.x;
+    double p0 = 0, p1 = 0, p2 = 0;
+    bool have = false;
+    if (tid < 2) {
+        const int t = s * 2 + tid;
+        p0 = prev_fit[t * 3]; p1 = prev_fit[t * 3 + 1]; p2 = prev_fit[t * 3 + 2];
+        have = prev_valid[t] != 0;
     }
-    prev_fit[t * 3] = p0; prev_fit[t * 3 + 1] = p1; prev_fit[t * 3 + 2] = p2;
-    prev_valid[t] = have ? 1 : 0;
+    for (int base = 0; base < n; base += EMA_CHUNK) {
+        const int m = min(EMA_CHUNK, n - base);
+        for (int i = tid; i < m * 6; i += 256) (&s_raw[0][0][0])[i] = raw[(size_t)base * 6 + i];
+        for (int i = tid; i < m * 2; i += 256) (&s_cnt[0][0])[i] = side_n[(size_t)base * 2 + i];
+        for (int i = tid; i < m; i += 256) s_mine[i] = (stream_id ? stream_id[base + i] : 0) == s;
+        __syncthreads();
+        if (tid < 2) {
+            for (int i = 0; i < m; i++) {
+                if (!s_mine[i] || s_cnt[i][tid] == 0) continue;
+                double c0 = s_raw[i][tid][0], c1 = s_raw[i][tid][1], c2 = s_raw[i][tid][2];
+                if (have) {
+                    c0 = __dadd_rn(__dmul_rn(smooth, p0), __dmul_rn(oms, c0));
+                    c1 = __dadd_rn(__dmul_rn(smooth, p1), __dmul_rn(oms, c1));
+                    c2 = __dadd_rn(__dmul_rn(smooth, p2), __dmul_rn(oms, c2));
+                }
+                s_out[i][tid][0] = c0; s_out[i][tid][1] = c1; s_out[i][tid][2] = c2;
+                p0 = c0; p1 = c1; p2 = c2; have = true;
+            }
+        }
+        __syncthreads();
+        for (int i = tid; i < m * 2; i += 256) {              // records of this stream's frames, both sides
+            const int fr = i >> 1, side = i & 1;
+            if (!s_mine[fr]) continue;
+            lane_side *o = &rec[base + fr].side[side];
+            const int cnt = s_cnt[fr][side];
+            o->n_lines = cnt;
+            o->valid = cnt != 0;
+            if (cnt) {
+                for (int k = 0; k < 3; k++) { o->raw[k] = s_raw[fr][side][k]; o->coeffs[k] = s_out[fr][side][k]; }
+                o->confidence = fmin(1.0, (double)cnt / 10.0);
+            }
+        }
+        __syncthreads();
+    }
+    if (tid < 2) {
+        const int t = s * 2 + tid;
+        prev_fit[t * 3] = p0; prev_fit[t * 3 + 1] = p1; prev_fit[t * 3 + 2] = p2;
+        prev_valid[t] = have ? 1 : 0;
+    }
 }
 
 __device__ __forceinline__ int trunc_i32(double v)
@@ -273,9 +302,8 @@ void launch_fit(const int32_t *lines, const int *n_lines, LaneFitScratch fs, con
 {
     cudaMemsetAsync(fs.side_flags, 0, sizeof(int) * n, st);
     k5_fit<<<n, 64, 0, st>>>(lines, n_lines, fs.raw, fs.side_n, fs.side_flags, g.W, g.max_segments);
-    int t = n_streams * 2;
-    k5_ema<<<(t + 63) / 64, 64, 0, st>>>(fs.raw, fs.side_n, stream_id, n_streams, prev_fit, prev_valid,
-                                         smooth, one_minus_smooth, records, n);
+    k5_ema<<<n_streams, 256, 0, st>>>(fs.raw, fs.side_n, stream_id, prev_fit, prev_valid, smooth, one_minus_smooth,
+                                      records, n);
     k5_points<<<n, 128, 0, st>>>(records, thr, n_edges, n_points, n_lines, rounds, fs.side_flags, g.W,
                                  g.max_segments);
     *launches += 3;
