@@ -4,6 +4,9 @@
 // counting half of np.median (lane_detector.py:79).  Integer-exact:
 //   gray = (3735 B + 19235 G + 9798 R + 2^14) >> 15
 //   blur = (sum_ij w_i w_j gray[y+i-2][x+j-2] + 128) >> 8,  w = [1 4 6 4 1], BORDER_REFLECT_101
+#include <stdlib.h>
+#include <string.h>
+
 #include "lane_common.cuh"
 
 namespace {
@@ -102,6 +105,32 @@ __device__ __forceinline__ uint4 ldg_stream(const uint4 *p)
     return r;
 }
 
+
+// ---- TMA bulk copy (cp.async.bulk, SASS UBLKCP) + mbarrier helpers -------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n"
+        "W_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@!p bra W_%=;\n\t}"
+        ::"r"(bar), "r"(parity) : "memory");
+}
+
 // 16 interleaved BGR pixels (12 words) -> 8 packed u16x2 gray pairs
 __device__ __forceinline__ void gray16(const uint32_t (&w)[12], uint32_t (&g)[8])
 {
@@ -119,13 +148,31 @@ __device__ __forceinline__ void gray16(const uint32_t (&w)[12], uint32_t (&g)[8]
     }
 }
 
+// TMA = true: every warp stages its strip rows in a private shared-memory ring with cp.async.bulk (one 1.5 KB
+// bulk copy per row, completion on an mbarrier), RING rows deep, so RING-1 rows of loads are in flight per warp
+// without holding registers; lanes then read their 48 bytes with three conflict-free LDS.128.
+// TMA = false (default) uses direct 16-byte ld.global.nc loads prefetched one row ahead in registers.
+constexpr int RING = 3;
+constexpr int ROW_BYTES = 32 * SPX * 3;          // 1536
+
+template <bool TMA>
 __global__ void __launch_bounds__(SWARPS * 32) k1_strip(const uint8_t *__restrict__ frames, uint8_t *__restrict__ blur,
                                                         uint32_t *__restrict__ hist, int *__restrict__ task_counter,
                                                         int n_frames, int H, int W, int band_rows)
 {
-    __shared__ __align__(16) uint8_t s_hist[SWARPS][256 * 32];
+    extern __shared__ __align__(128) uint8_t k1_smem[];      // [SWARPS][8192] counters | [SWARPS][RING][1536] ring | barriers
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    uint8_t *wh = s_hist[wid];
+    uint8_t *wh = k1_smem + wid * (256 * 32);
+    uint8_t *ring = k1_smem + SWARPS * (256 * 32) + wid * (RING * ROW_BYTES);
+    unsigned long long *bars = reinterpret_cast<unsigned long long *>(k1_smem + SWARPS * (256 * 32) + SWARPS * RING * ROW_BYTES) + wid * RING;
+    uint32_t issued = 0, consumed = 0;             // monotonic per-warp ring counters (TMA)
+    if (TMA) {
+        if (lane == 0) {
+            for (int i = 0; i < RING; i++) mbar_init(smem_u32(&bars[i]), 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncwarp();
+    }
     {   // zero this warp's private counters
         uint4 *z = reinterpret_cast<uint4 *>(wh);
         for (int i = lane; i < 256 * 32 / 16; i += 32) z[i] = make_uint4(0, 0, 0, 0);
@@ -177,8 +224,37 @@ __global__ void __launch_bounds__(SWARPS * 32) k1_strip(const uint8_t *__restric
             __syncwarp();
         };
 
+        // bulk-copy geometry of this strip: the in-image part of [strip_x0, strip_x0 + 512)
+        const int strip_x0 = strip * STRIP_OUT - SPX;
+        const int copy_x0 = max(strip_x0, 0);
+        const uint32_t copy_bytes = (uint32_t)(min(strip_x0 + 32 * SPX, W) - copy_x0) * 3u;
+        const uint32_t copy_off = (uint32_t)(copy_x0 - strip_x0) * 3u;
+        const uint8_t *frame_base = frames + f * frame_px * 3;
+        auto issue_row = [&](int y) {               // lane 0: arm the slot's barrier and start the copy
+            if (lane == 0) {
+                const uint32_t slot = issued % RING;
+                const uint32_t bar = smem_u32(&bars[slot]);
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // earlier LDS of this slot vs the async write
+                mbar_expect_tx(bar, copy_bytes);
+                bulk_g2s(smem_u32(ring + slot * ROW_BYTES) + copy_off,
+                         frame_base + ((size_t)fold101(y, H) * W + copy_x0) * 3, copy_bytes, bar);
+            }
+            issued++;
+        };
         uint32_t w[12];
         auto load_row = [&](int y) {
+            if (TMA) {
+                const uint32_t slot = consumed % RING;
+                mbar_wait(smem_u32(&bars[slot]), (consumed / RING) & 1u);
+                const uint4 *p = reinterpret_cast<const uint4 *>(ring + slot * ROW_BYTES) + 3 * lane;
+                uint4 a = p[0], b = p[1], c = p[2];
+                w[0] = a.x; w[1] = a.y; w[2] = a.z; w[3] = a.w; w[4] = b.x; w[5] = b.y; w[6] = b.z; w[7] = b.w;
+                w[8] = c.x; w[9] = c.y; w[10] = c.z; w[11] = c.w;
+                consumed++;
+                __syncwarp();                        // every lane has its copy: the slot may be refilled
+                if (y + RING < r1 + 2) issue_row(y + RING);
+                return;
+            }
             const int yy = fold101(y, H);
             if (in_img) {
                 const uint4 *p = reinterpret_cast<const uint4 *>(src + (size_t)yy * W * 3);
@@ -189,11 +265,13 @@ __global__ void __launch_bounds__(SWARPS * 32) k1_strip(const uint8_t *__restric
         };
 #pragma unroll
         for (int j = 0; j < 12; j++) w[j] = 0;
+        if (TMA)
+            for (int i = 0; i < RING && r0 - 2 + i < r1 + 2; i++) issue_row(r0 - 2 + i);
         load_row(r0 - 2);
         for (int y = r0 - 2; y < r1 + 2; y++) {
             uint32_t g[8];
             gray16(w, g);
-            if (y + 1 < r1 + 2) load_row(y + 1);        // prefetch the next row behind the arithmetic
+            if (y + 1 < r1 + 2) load_row(y + 1);        // next row: from the ring (TMA) or prefetched into registers
             uint32_t V[8];
 #pragma unroll
             for (int j = 0; j < 8; j++) {               // [1 1]^4 down the column
@@ -266,9 +344,22 @@ void launch_blur_hist(const uint8_t *frames, uint8_t *blur, uint32_t *hist, int 
             cudaGetDevice(&dev);
             cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
         }
-        const int band_rows = H >= 540 ? 135 : (H >= 120 ? 60 : H);
+        const int band_rows = H >= 540 ? 68 : (H >= 120 ? 60 : H);
         cudaMemsetAsync(task_counter, 0, sizeof(int), st);
-        k1_strip<<<sms * 5, SWARPS * 32, 0, st>>>(frames, blur, hist, task_counter, n, H, W, band_rows);
+        // default: direct 16-byte loads.  LANE_B200_K1=tma selects the bulk-copy staged variant (measured slower on
+        // B200: 0.645 vs 0.546 ms per 256 1080p frames -- the kernel is ALU-issue bound, not load-latency bound)
+        static const bool use_ldg = !(getenv("LANE_B200_K1") && !strcmp(getenv("LANE_B200_K1"), "tma"));
+        const size_t smem_ldg = SWARPS * 256 * 32;
+        const size_t smem_tma = smem_ldg + SWARPS * RING * ROW_BYTES + SWARPS * RING * 8;
+        static bool configured = false;
+        if (!configured) {
+            cudaFuncSetAttribute(k1_strip<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tma);
+            configured = true;
+        }
+        if (use_ldg)
+            k1_strip<false><<<sms * 5, SWARPS * 32, smem_ldg, st>>>(frames, blur, hist, task_counter, n, H, W, band_rows);
+        else
+            k1_strip<true><<<sms * 4, SWARPS * 32, smem_tma, st>>>(frames, blur, hist, task_counter, n, H, W, band_rows);
     } else {
         dim3 grid((W + TW - 1) / TW, (H + TH - 1) / TH, n);
         k1_tile<<<grid, NT, 0, st>>>(frames, blur, hist, H, W);
