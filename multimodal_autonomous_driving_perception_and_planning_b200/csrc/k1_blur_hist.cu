@@ -97,6 +97,12 @@ __device__ __forceinline__ uint32_t dp2a_hi(uint32_t a, uint32_t b, uint32_t c)
     asm("dp2a.hi.u32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
     return d;
 }
+__device__ __forceinline__ uint32_t h2add(uint32_t a, uint32_t b)
+{
+    uint32_t d;
+    asm("add.f16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b));
+    return d;
+}
 __device__ __forceinline__ uint4 ldg_stream(const uint4 *p)
 {
     uint4 r;
@@ -275,10 +281,13 @@ __global__ void __launch_bounds__(SWARPS * 32) k1_strip(const uint8_t *__restric
             uint32_t V[8];
 #pragma unroll
             for (int j = 0; j < 8; j++) {               // [1 1]^4 down the column
-                uint32_t t1 = g[j] + p1[j]; p1[j] = g[j];
-                uint32_t t2 = t1 + p2[j];   p2[j] = t1;
-                uint32_t t3 = t2 + p3[j];   p3[j] = t2;
-                V[j] = t3 + p4[j];          p4[j] = t3;
+                // The first three stages stay below 2048, where binary16 (denormals included) is exact and its bit
+                // pattern is the integer itself, so they run as add.f16x2 on the FMA pipe; that takes 24 adds per
+                // row off the ALU pipe, which is the busiest one in this kernel.  The last stage (<= 4080) is integer.
+                uint32_t t1 = h2add(g[j], p1[j]); p1[j] = g[j];
+                uint32_t t2 = h2add(t1, p2[j]);   p2[j] = t1;
+                uint32_t t3 = h2add(t2, p3[j]);   p3[j] = t2;
+                V[j] = t3 + p4[j];                p4[j] = t3;
             }
             if (y < r0 + 2) continue;                    // pipeline fill: V is the blur column sum of row y-2
             const int yo = y - 2;
