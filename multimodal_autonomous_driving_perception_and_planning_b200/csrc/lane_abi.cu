@@ -11,6 +11,8 @@
 
 void lane_upload_sample_rows(int H);
 
+#define LANE_COPY_EVENTS 8
+
 static thread_local std::string g_create_error;
 
 struct lane_ctx {
@@ -21,7 +23,8 @@ struct lane_ctx {
     double smooth = 0.7, one_minus_smooth = 1 - 0.7;
     bool have_roi = false, have_lut = false, debug = false, profiling = false;
     bool own_stream = true;
-    cudaStream_t st = nullptr;
+    cudaStream_t st = nullptr, copy_st = nullptr;   // compute stream; H2D stream for chunked host batches
+    cudaEvent_t copy_ev[LANE_COPY_EVENTS] = {}, start_ev = nullptr;
     std::string err;
 
     // device buffers
@@ -120,6 +123,10 @@ void free_all(lane_ctx *c)
     if (c->h_prev_valid) cudaFreeHost(c->h_prev_valid);
     for (auto &e : c->ev)
         if (e) cudaEventDestroy(e);
+    for (auto &e : c->copy_ev)
+        if (e) cudaEventDestroy(e);
+    if (c->start_ev) cudaEventDestroy(c->start_ev);
+    if (c->copy_st) cudaStreamDestroy(c->copy_st);
     if (c->own_stream && c->st) cudaStreamDestroy(c->st);
 }
 
@@ -162,14 +169,81 @@ int mark(lane_ctx *c, int i)
     return LANE_OK;
 }
 
-// Enqueue every stage for n device-resident frames.
-int enqueue(lane_ctx *c, const uint8_t *frames_dev, int n, const int32_t *stream_id, int S,
-            const double *prev_fit, const uint8_t *prev_valid)
+// All pixel stages for frames [off, off+m) of the batch (per-frame buffers are indexed by the batch position).
+int run_stages(lane_ctx *c, const uint8_t *frames_dev, int off, int m, const int32_t *stream_id_dev, int S, bool timed)
 {
     const LaneGeom &g = c->g;
     const int H = g.H, W = g.W;
+    const size_t P = (size_t)H * W, WW = (W + 31) / 32, planes = (size_t)H * WW, o = (size_t)off;
     int *L = c->stage_launches;
-    // small host->device state: stream ids + EMA state
+    int rc;
+    const uint8_t *fr = frames_dev + o * P * 3;
+    uint8_t *blur = c->d_blur + o * P;
+    uint32_t *hist = c->d_hist + o * 256;
+    int4 *thr = c->d_thr + o;
+    int *n_edges = c->d_n_edges + o, *n_points = c->d_n_points + o, *rounds = c->d_rounds + o, *n_lines = c->d_n_lines + o;
+    uint32_t *points = c->d_points + o * g.max_points;
+    uint32_t *pmask_bits = c->d_pmask_bits + o * std::max(g.bh, 1) * WW;
+    uint32_t *edge_bits = c->d_edge_bits + o * planes, *cb = c->d_dbg_c + o * planes, *sb = c->d_dbg_s + o * planes;
+    int32_t *lines = c->d_lines + o * g.max_segments * 4;
+
+    if (timed) { rc = mark(c, LANE_STAGE_BLUR_HIST); if (rc) return rc; }
+    launch_blur_hist(fr, blur, hist, m, H, W, c->st, &L[LANE_STAGE_BLUR_HIST], c->d_task_counter, c->force_tile);
+
+    if (timed) { rc = mark(c, LANE_STAGE_CANNY); if (rc) return rc; }
+    c->last_cluster = !c->force_generic_k2 &&
+        launch_canny_cluster(blur, hist, c->d_lut, c->d_lut + 511, c->d_roi_bits, thr, n_edges, rounds, points, n_points,
+                             pmask_bits, edge_bits, cb, sb, c->d_task_counter, g, m, c->st, &L[LANE_STAGE_CANNY]);
+    if (c->last_cluster) {
+        if (timed) { rc = mark(c, LANE_STAGE_COMPACT); if (rc) return rc; }
+    } else {
+        // generic widths / unaligned planes: byte-map kernels, then the same bit-plane outputs
+        rc = ensure_fallback(c); if (rc) return rc;
+        uint8_t *cls = c->d_cls + o * P;
+        int *seedsA = c->d_seedsA + o * c->seed_cap, *seedsB = c->d_seedsB + o * c->seed_cap, *seed_count = c->d_seed_count + o;
+        launch_thresholds(hist, c->d_lut, c->d_lut + 511, thr, m, H, W, c->st, &L[LANE_STAGE_CANNY]);
+        launch_sobel_nms(blur, thr, cls, seedsA, seed_count, c->seed_cap, m, H, W, c->st, &L[LANE_STAGE_CANNY]);
+        if (c->debug) CU(cudaMemcpyAsync(c->d_cls_dbg + o * P, cls, (size_t)m * P, cudaMemcpyDeviceToDevice, c->st));
+        launch_hysteresis(cls, seedsA, seedsB, seed_count, c->seed_cap, rounds, m, H, W, c->st, &L[LANE_STAGE_CANNY]);
+        launch_finalize_edges(cls, n_edges, m, H, W, c->st, &L[LANE_STAGE_CANNY]);
+        if (timed) { rc = mark(c, LANE_STAGE_COMPACT); if (rc) return rc; }
+        launch_compact(cls, c->d_roi, c->d_pmask + o * std::max(g.bw * g.bh, 1), points, n_points, g, m, c->st,
+                       &L[LANE_STAGE_COMPACT]);
+        launch_bytes_to_bits(cls, edge_bits, m, H, W, W, c->st, &L[LANE_STAGE_COMPACT]);
+        launch_mask_rows(edge_bits, c->d_roi_bits, pmask_bits, g, m, c->st, &L[LANE_STAGE_COMPACT]);
+    }
+    if (c->debug)
+        CU(cudaMemcpyAsync(c->d_points_dbg + o * g.max_points, points, sizeof(uint32_t) * (size_t)m * g.max_points,
+                           cudaMemcpyDeviceToDevice, c->st));
+
+    if (timed) { rc = mark(c, LANE_STAGE_PPHT); if (rc) return rc; }
+    if (c->ppht_v1) {
+        if (!c->d_accum) CU(dalloc(&c->d_accum, (size_t)c->max_batch * LANE_NUM_ANGLES * g.numrho));
+        launch_ppht(points, n_points, pmask_bits, c->d_accum + o * LANE_NUM_ANGLES * g.numrho, lines, n_lines, g, c->hp, m,
+                    c->st, &L[LANE_STAGE_PPHT]);
+    } else {
+        // v3 (cells in distributed shared memory) takes every frame it can; v2 (global 16-bit cells) then sweeps
+        // up the frames v3 flagged (point list larger than its shared-memory list), or runs alone if v3 cannot launch.
+        bool v3 = !c->ppht_v2 && c->G3 > 0 &&
+                  launch_ppht_v3(points, n_points, pmask_bits, c->d_pmask_work + o * c->G3 * std::max(g.bh, 1) * WW,
+                                 c->d_win3, c->cells_max3, c->G3, lines, n_lines, g, c->hp, m, c->st, &L[LANE_STAGE_PPHT]);
+        launch_ppht_v2(points, n_points, pmask_bits, c->d_accum16 + o * (c->cells_per_frame / 2), c->d_win,
+                       c->cells_per_frame, lines, n_lines, g, c->hp, m, c->st, &L[LANE_STAGE_PPHT], v3 ? 1 : 0);
+    }
+
+    if (timed) { rc = mark(c, LANE_STAGE_FIT); if (rc) return rc; }
+    LaneFitScratch fs{c->fit.raw + o * 6, c->fit.side_n + o * 2, c->fit.side_flags + o};
+    launch_fit(lines, n_lines, fs, stream_id_dev ? stream_id_dev + o : nullptr, S, c->d_prev_fit, c->d_prev_valid, c->smooth,
+               c->one_minus_smooth, thr, n_edges, n_points, rounds, c->d_records + o, g, m, c->st, &L[LANE_STAGE_FIT]);
+    return LANE_OK;
+}
+
+// Enqueue the whole batch.  Device-resident frames run as one chunk.  Host frames are cut into chunks that are
+// copied on a second stream while the previous chunk computes (the EMA state stays on the device across chunks,
+// which run in order on the compute stream).
+int enqueue(lane_ctx *c, const uint8_t *frames, bool on_device, int n, const int32_t *stream_id, int S,
+            const double *prev_fit, const uint8_t *prev_valid)
+{
     int rc = ensure_streams(c, S);
     if (rc) return rc;
     if (stream_id) CU(cudaMemcpyAsync(c->d_stream_id, stream_id, sizeof(int) * n, cudaMemcpyHostToDevice, c->st));
@@ -177,58 +251,36 @@ int enqueue(lane_ctx *c, const uint8_t *frames_dev, int n, const int32_t *stream
     memcpy(c->h_prev_valid, prev_valid, (size_t)S * 2);
     CU(cudaMemcpyAsync(c->d_prev_fit, c->h_prev_fit, sizeof(double) * S * 6, cudaMemcpyHostToDevice, c->st));
     CU(cudaMemcpyAsync(c->d_prev_valid, c->h_prev_valid, (size_t)S * 2, cudaMemcpyHostToDevice, c->st));
-
-    rc = mark(c, LANE_STAGE_BLUR_HIST); if (rc) return rc;
-    launch_blur_hist(frames_dev, c->d_blur, c->d_hist, n, H, W, c->st, &L[LANE_STAGE_BLUR_HIST], c->d_task_counter,
-                     c->force_tile);
-
-    rc = mark(c, LANE_STAGE_CANNY); if (rc) return rc;
-    c->last_cluster = !c->force_generic_k2 &&
-        launch_canny_cluster(c->d_blur, c->d_hist, c->d_lut, c->d_lut + 511, c->d_roi_bits, c->d_thr, c->d_n_edges,
-                             c->d_rounds, c->d_points, c->d_n_points, c->d_pmask_bits, c->d_edge_bits, c->d_dbg_c,
-                             c->d_dbg_s, c->d_task_counter, g, n, c->st, &L[LANE_STAGE_CANNY]);
-    if (c->last_cluster) {
-        rc = mark(c, LANE_STAGE_COMPACT); if (rc) return rc;
+    const int32_t *sid = stream_id ? c->d_stream_id : nullptr;
+    const uint8_t *frames_dev = frames;
+    if (on_device) {
+        rc = run_stages(c, frames, 0, n, sid, S, c->profiling);
+        if (rc) return rc;
     } else {
-        // generic widths / unaligned planes: byte-map kernels, then the same bit-plane outputs
-        rc = ensure_fallback(c); if (rc) return rc;
-        launch_thresholds(c->d_hist, c->d_lut, c->d_lut + 511, c->d_thr, n, H, W, c->st, &L[LANE_STAGE_CANNY]);
-        launch_sobel_nms(c->d_blur, c->d_thr, c->d_cls, c->d_seedsA, c->d_seed_count, c->seed_cap, n, H, W, c->st,
-                         &L[LANE_STAGE_CANNY]);
-        if (c->debug)
-            CU(cudaMemcpyAsync(c->d_cls_dbg, c->d_cls, (size_t)n * H * W, cudaMemcpyDeviceToDevice, c->st));
-        launch_hysteresis(c->d_cls, c->d_seedsA, c->d_seedsB, c->d_seed_count, c->seed_cap, c->d_rounds, n, H, W,
-                          c->st, &L[LANE_STAGE_CANNY]);
-        launch_finalize_edges(c->d_cls, c->d_n_edges, n, H, W, c->st, &L[LANE_STAGE_CANNY]);
-        rc = mark(c, LANE_STAGE_COMPACT); if (rc) return rc;
-        launch_compact(c->d_cls, c->d_roi, c->d_pmask, c->d_points, c->d_n_points, g, n, c->st, &L[LANE_STAGE_COMPACT]);
-        launch_bytes_to_bits(c->d_cls, c->d_edge_bits, n, H, W, W, c->st, &L[LANE_STAGE_COMPACT]);
-        launch_mask_rows(c->d_edge_bits, c->d_roi_bits, c->d_pmask_bits, g, n, c->st, &L[LANE_STAGE_COMPACT]);
+        const size_t bytes = (size_t)c->g.H * c->g.W * 3;
+        if (!c->d_frames) CU(dalloc(&c->d_frames, (size_t)c->max_batch * bytes));
+        if (!c->copy_st) {
+            CU(cudaStreamCreateWithFlags(&c->copy_st, cudaStreamNonBlocking));
+            for (auto &e : c->copy_ev) CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+            CU(cudaEventCreateWithFlags(&c->start_ev, cudaEventDisableTiming));
+        }
+        frames_dev = c->d_frames;
+        // chunk so that a copy (~50 GB/s) and the compute of the previous chunk overlap; >= 4 chunks when possible
+        const int chunk = std::max(1, std::min(64, (n + 3) / 4));
+        CU(cudaEventRecord(c->start_ev, c->st));                 // the staging buffer is free once earlier work is done
+        CU(cudaStreamWaitEvent(c->copy_st, c->start_ev, 0));
+        int k = 0;
+        for (int off = 0; off < n; off += chunk, k++) {
+            const int m = std::min(chunk, n - off);
+            CU(cudaMemcpyAsync(c->d_frames + (size_t)off * bytes, frames + (size_t)off * bytes, bytes * m,
+                               cudaMemcpyHostToDevice, c->copy_st));
+            cudaEvent_t ev = c->copy_ev[k % LANE_COPY_EVENTS];
+            CU(cudaEventRecord(ev, c->copy_st));
+            CU(cudaStreamWaitEvent(c->st, ev, 0));
+            rc = run_stages(c, c->d_frames, off, m, sid, S, false);
+            if (rc) return rc;
+        }
     }
-    if (c->debug)
-        CU(cudaMemcpyAsync(c->d_points_dbg, c->d_points, sizeof(uint32_t) * (size_t)n * g.max_points,
-                           cudaMemcpyDeviceToDevice, c->st));
-
-    rc = mark(c, LANE_STAGE_PPHT); if (rc) return rc;
-    if (c->ppht_v1) {
-        if (!c->d_accum) CU(dalloc(&c->d_accum, (size_t)c->max_batch * LANE_NUM_ANGLES * g.numrho));
-        launch_ppht(c->d_points, c->d_n_points, c->d_pmask_bits, c->d_accum, c->d_lines, c->d_n_lines, g, c->hp, n,
-                    c->st, &L[LANE_STAGE_PPHT]);
-    } else {
-        // v3 (cells in distributed shared memory) takes every frame it can; v2 (global 16-bit cells) then sweeps
-        // up the frames v3 flagged (point list larger than its shared-memory list), or runs alone if v3 cannot launch.
-        bool v3 = !c->ppht_v2 && c->G3 > 0 &&
-                  launch_ppht_v3(c->d_points, c->d_n_points, c->d_pmask_bits, c->d_pmask_work, c->d_win3, c->cells_max3,
-                                 c->G3, c->d_lines, c->d_n_lines, g, c->hp, n, c->st, &L[LANE_STAGE_PPHT]);
-        launch_ppht_v2(c->d_points, c->d_n_points, c->d_pmask_bits, c->d_accum16, c->d_win, c->cells_per_frame,
-                       c->d_lines, c->d_n_lines, g, c->hp, n, c->st, &L[LANE_STAGE_PPHT], v3 ? 1 : 0);
-    }
-
-    rc = mark(c, LANE_STAGE_FIT); if (rc) return rc;
-    launch_fit(c->d_lines, c->d_n_lines, c->fit, stream_id ? c->d_stream_id : nullptr, S, c->d_prev_fit,
-               c->d_prev_valid, c->smooth, c->one_minus_smooth, c->d_thr, c->d_n_edges, c->d_n_points, c->d_rounds,
-               c->d_records, g, n, c->st, &L[LANE_STAGE_FIT]);
-
     rc = mark(c, LANE_STAGE_D2H); if (rc) return rc;
     CU(cudaMemcpyAsync(c->h_records, c->d_records, sizeof(lane_record) * n, cudaMemcpyDeviceToHost, c->st));
     CU(cudaMemcpyAsync(c->h_prev_fit, c->d_prev_fit, sizeof(double) * S * 6, cudaMemcpyDeviceToHost, c->st));
@@ -239,7 +291,7 @@ int enqueue(lane_ctx *c, const uint8_t *frames_dev, int n, const int32_t *stream
     c->last_n = n;
     c->last_streams = S;
     c->in_flight = true;
-    c->timed = c->profiling;
+    c->timed = c->profiling && on_device;
     return LANE_OK;
 }
 
@@ -480,7 +532,7 @@ int lane_detect_enqueue(lane_ctx *c, const uint8_t *frames_dev, int n, const int
                 return fail(c, LANE_ERR_INVALID, "stream_id[%d]=%d outside [0,%d)", i, stream_id[i], n_streams);
     memset(c->stage_launches, 0, sizeof(c->stage_launches));
     if (c->profiling) CU(cudaEventRecord(c->ev[LANE_STAGE_H2D], c->st));
-    return enqueue(c, frames_dev, n, stream_id, n_streams, prev_fit, prev_valid);
+    return enqueue(c, frames_dev, true, n, stream_id, n_streams, prev_fit, prev_valid);
 }
 
 int lane_detect_collect(lane_ctx *c, double *prev_fit, uint8_t *prev_valid, lane_record *out)
@@ -511,14 +563,7 @@ int lane_detect_batch(lane_ctx *c, const uint8_t *frames, int frames_on_device, 
                 return fail(c, LANE_ERR_INVALID, "stream_id[%d]=%d outside [0,%d)", i, stream_id[i], n_streams);
     memset(c->stage_launches, 0, sizeof(c->stage_launches));
     if (c->profiling) CU(cudaEventRecord(c->ev[LANE_STAGE_H2D], c->st));
-    const uint8_t *dev = frames;
-    if (!frames_on_device) {
-        const size_t bytes = (size_t)c->g.H * c->g.W * 3;
-        if (!c->d_frames) CU(dalloc(&c->d_frames, (size_t)c->max_batch * bytes));
-        CU(cudaMemcpyAsync(c->d_frames, frames, bytes * n, cudaMemcpyHostToDevice, c->st));
-        dev = c->d_frames;
-    }
-    rc = enqueue(c, dev, n, stream_id, n_streams, prev_fit, prev_valid);
+    rc = enqueue(c, frames, frames_on_device != 0, n, stream_id, n_streams, prev_fit, prev_valid);
     if (rc) return rc;
     return lane_detect_collect(c, prev_fit, prev_valid, out);
 }
