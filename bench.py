@@ -292,7 +292,10 @@ def main():
                    roofline={"bound": "hbm", "kernel": "K1 blur_hist (gray + 5x5 blur + histogram)",
                              "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                              "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 (of fallback)",
-                             "traffic": None, "ms_per_launch": k1_ms,
+                             # dram__bytes_read.sum + dram__bytes_write.sum of one k1_strip launch (256 x 1080p), from
+                             # the ncu --set full capture summarised in profiles/r1_final_ncu_summary.md
+                             "traffic": (2.215e9 if (n == 256) else None), "traffic_source": "profiles/r1_final_ncu_summary.md",
+                             "ms_per_launch": k1_ms,
                              "algorithmic_bytes_per_launch": n * ALGO_BYTES_PER_FRAME},
                    stage_ms_per_step={k: v / args.steps for k, v in stage_sum.items()},
                    e2e={"value": e2e_val, "unit": "frames/s", "h2d_bytes_per_step": int(host_frames.nbytes),

@@ -106,7 +106,7 @@ __device__ __forceinline__ uint32_t h2add(uint32_t a, uint32_t b)
 __device__ __forceinline__ uint4 ldg_stream(const uint4 *p)
 {
     uint4 r;
-    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];"
+    asm volatile("ld.global.nc.v4.u32 {%0, %1, %2, %3}, [%4];"
                  : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
     return r;
 }
