@@ -93,6 +93,9 @@ LANE_API int lane_set_threshold_lut(lane_ctx *ctx, const uint8_t *low511, const 
 LANE_API int lane_set_hough_params(lane_ctx *ctx, int threshold, int min_line_length, int max_line_gap);
 /* smoothing_factor and (1 - smoothing_factor) exactly as the host evaluates them (:159-161). */
 LANE_API int lane_set_smoothing(lane_ctx *ctx, double factor, double one_minus_factor);
+/* gaussian_blur = 0 skips cv2.GaussianBlur (lane_detector.py:72): Canny then runs on the plain grayscale plane, as
+ * the reference's SceneClassifier does (src/tagging/scene_classifier.py:145-146).  Default 1. */
+LANE_API int lane_set_preprocess(lane_ctx *ctx, int gaussian_blur);
 /* Keep per-stage intermediates of the next detect calls for the lane_debug_* taps (costs memory traffic). */
 LANE_API int lane_set_debug(lane_ctx *ctx, int keep_intermediates);
 

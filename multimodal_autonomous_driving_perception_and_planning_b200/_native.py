@@ -73,6 +73,7 @@ _PROTOS = {
     "lane_set_hough_params": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int]),
     "lane_set_smoothing": (C.c_int, [C.c_void_p, C.c_double, C.c_double]),
     "lane_set_debug": (C.c_int, [C.c_void_p, C.c_int]),
+    "lane_set_preprocess": (C.c_int, [C.c_void_p, C.c_int]),
     "lane_detect_batch": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p,
                                     C.c_void_p, C.c_void_p]),
     "lane_detect_enqueue": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
@@ -168,6 +169,17 @@ class LaneContext:
     def set_hough_params(self, threshold=50, min_line_length=50, max_line_gap=150):
         self._check(lib().lane_set_hough_params(self._h, int(threshold), int(round(min_line_length)),
                                                 int(round(max_line_gap))))
+
+    def set_preprocess(self, gaussian_blur: bool):
+        """False: skip the 5x5 blur, Canny runs on the plain grayscale plane (scene_classifier.py:145-146)."""
+        self._check(lib().lane_set_preprocess(self._h, int(gaussian_blur)))
+
+    def set_threshold_lut(self, low511: np.ndarray, high511: np.ndarray):
+        low = np.ascontiguousarray(low511, dtype=np.uint8)
+        high = np.ascontiguousarray(high511, dtype=np.uint8)
+        if low.shape != (511,) or high.shape != (511,):
+            raise ValueError("threshold LUTs must have 511 entries (one per 2*median)")
+        self._check(lib().lane_set_threshold_lut(self._h, _ptr(low), _ptr(high)))
 
     def set_profiling(self, on: bool):
         self._check(lib().lane_set_profiling(self._h, int(on)))

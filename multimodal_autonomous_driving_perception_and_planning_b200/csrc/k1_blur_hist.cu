@@ -7,6 +7,8 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <algorithm>
+
 #include "lane_common.cuh"
 
 namespace {
@@ -333,6 +335,25 @@ __global__ void __launch_bounds__(SWARPS * 32) k1_strip(const uint8_t *__restric
     }
 }
 
+// gray plane + histogram without the blur (scene_classifier.py:145-146 runs cv2.Canny on the plain grayscale frame)
+__global__ void __launch_bounds__(256) k1_gray_hist(const uint8_t *__restrict__ frames, uint8_t *__restrict__ out,
+                                                    uint32_t *__restrict__ hist, int P)
+{
+    __shared__ uint32_t lh[256];
+    const int f = blockIdx.y, tid = threadIdx.x;
+    lh[tid] = 0;
+    __syncthreads();
+    const uint8_t *src = frames + (size_t)f * P * 3;
+    uint8_t *dst = out + (size_t)f * P;
+    for (int i = blockIdx.x * 256 + tid; i < P; i += gridDim.x * 256) {
+        const uint32_t v = gray_of(src[3 * i], src[3 * i + 1], src[3 * i + 2]);
+        dst[i] = (uint8_t)v;
+        atomicAdd(&lh[v], 1u);
+    }
+    __syncthreads();
+    if (lh[tid]) atomicAdd(&hist[f * 256 + tid], lh[tid]);
+}
+
 __global__ void k_gray(const uint8_t *__restrict__ frame, uint8_t *__restrict__ gray, int n)
 {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -341,11 +362,17 @@ __global__ void k_gray(const uint8_t *__restrict__ frame, uint8_t *__restrict__ 
 
 }  // namespace
 
-void launch_blur_hist(const uint8_t *frames, uint8_t *blur, uint32_t *hist, int n, int H, int W,
-                      cudaStream_t st, int *launches, int *task_counter, int force_tile)
+void launch_blur_hist(const uint8_t *frames, uint8_t *blur_out, uint32_t *hist, int n, int H, int W,
+                      cudaStream_t st, int *launches, int *task_counter, int force_tile, int blur)
 {
     cudaMemsetAsync(hist, 0, sizeof(uint32_t) * 256 * n, st);
-    const bool aligned = (W % 16 == 0) && (((uintptr_t)frames | (uintptr_t)blur) % 16 == 0);
+    if (!blur) {
+        dim3 grid(std::min((H * W + 255) / 256, 1184), n);
+        k1_gray_hist<<<grid, 256, 0, st>>>(frames, blur_out, hist, H * W);
+        *launches += 1;
+        return;
+    }
+    const bool aligned = (W % 16 == 0) && (((uintptr_t)frames | (uintptr_t)blur_out) % 16 == 0);
     if (aligned && !force_tile) {
         static int sms = 0;
         if (!sms) {
@@ -366,12 +393,12 @@ void launch_blur_hist(const uint8_t *frames, uint8_t *blur, uint32_t *hist, int 
             configured = true;
         }
         if (use_ldg)
-            k1_strip<false><<<sms * 5, SWARPS * 32, smem_ldg, st>>>(frames, blur, hist, task_counter, n, H, W, band_rows);
+            k1_strip<false><<<sms * 5, SWARPS * 32, smem_ldg, st>>>(frames, blur_out, hist, task_counter, n, H, W, band_rows);
         else
-            k1_strip<true><<<sms * 4, SWARPS * 32, smem_tma, st>>>(frames, blur, hist, task_counter, n, H, W, band_rows);
+            k1_strip<true><<<sms * 4, SWARPS * 32, smem_tma, st>>>(frames, blur_out, hist, task_counter, n, H, W, band_rows);
     } else {
         dim3 grid((W + TW - 1) / TW, (H + TH - 1) / TH, n);
-        k1_tile<<<grid, NT, 0, st>>>(frames, blur, hist, H, W);
+        k1_tile<<<grid, NT, 0, st>>>(frames, blur_out, hist, H, W);
     }
     *launches += 1;
 }

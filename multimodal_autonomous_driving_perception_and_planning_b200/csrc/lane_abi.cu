@@ -23,6 +23,7 @@ struct lane_ctx {
     double smooth = 0.7, one_minus_smooth = 1 - 0.7;
     bool have_roi = false, have_lut = false, debug = false, profiling = false;
     bool own_stream = true;
+    int blur = 1;                     // 0: Canny runs on the plain grayscale plane (lane_set_preprocess)
     cudaStream_t st = nullptr, copy_st = nullptr;   // compute stream; H2D stream for chunked host batches
     cudaEvent_t copy_ev[LANE_COPY_EVENTS] = {}, start_ev = nullptr;
     std::string err;
@@ -188,7 +189,8 @@ int run_stages(lane_ctx *c, const uint8_t *frames_dev, int off, int m, const int
     int32_t *lines = c->d_lines + o * g.max_segments * 4;
 
     if (timed) { rc = mark(c, LANE_STAGE_BLUR_HIST); if (rc) return rc; }
-    launch_blur_hist(fr, blur, hist, m, H, W, c->st, &L[LANE_STAGE_BLUR_HIST], c->d_task_counter, c->force_tile);
+    launch_blur_hist(fr, blur, hist, m, H, W, c->st, &L[LANE_STAGE_BLUR_HIST], c->d_task_counter, c->force_tile,
+                     c->blur);
 
     if (timed) { rc = mark(c, LANE_STAGE_CANNY); if (rc) return rc; }
     c->last_cluster = !c->force_generic_k2 &&
@@ -481,6 +483,13 @@ int lane_set_smoothing(lane_ctx *c, double factor, double one_minus_factor)
 {
     if (!c) return LANE_ERR_INVALID;
     c->smooth = factor; c->one_minus_smooth = one_minus_factor;
+    return LANE_OK;
+}
+
+int lane_set_preprocess(lane_ctx *c, int gaussian_blur)
+{
+    if (!c) return LANE_ERR_INVALID;
+    c->blur = gaussian_blur != 0;
     return LANE_OK;
 }
 

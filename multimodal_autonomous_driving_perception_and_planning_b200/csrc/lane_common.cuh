@@ -31,7 +31,7 @@ struct LaneHoughParams {
 
 // ---- K1 ---------------------------------------------------------------------------------
 void launch_blur_hist(const uint8_t *frames, uint8_t *blur, uint32_t *hist, int n, int H, int W,
-                      cudaStream_t st, int *launches, int *task_counter, int force_tile);
+                      cudaStream_t st, int *launches, int *task_counter, int force_tile, int gaussian_blur);
 void launch_gray_debug(const uint8_t *frame, uint8_t *gray, int H, int W, cudaStream_t st);
 
 // ---- K2 ---------------------------------------------------------------------------------

@@ -1,3 +1,4 @@
 from .lane_detector import LaneDetector, LaneLine
+from .road_layout import RoadLayoutAnalyzer, RoadLayoutCues
 
-__all__ = ["LaneDetector", "LaneLine"]
+__all__ = ["LaneDetector", "LaneLine", "RoadLayoutAnalyzer", "RoadLayoutCues"]

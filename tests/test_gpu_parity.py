@@ -307,3 +307,25 @@ def test_config2_full_size_properties():
         assert np.array_equal(e, unpack_edges(gold["edges_packed"][i % 8], 1080, 1920)) if i % 8 < 4 else True
     assert recs["side"]["valid"].all()
     det.close()
+
+
+def test_road_layout_cues_match_cv2():
+    """SceneClassifier's Canny(gray, 50, 150) + HoughLinesP(100, 100, 10) on the whole frame
+    (src/tagging/scene_classifier.py:145-161), same kernels with other parameters, bit-exact vs cv2."""
+    from multimodal_autonomous_driving_perception_and_planning_b200.perception import RoadLayoutAnalyzer
+    rng = np.random.default_rng(3)
+    frames = gen_frames(640, 480, 3) + [rng.integers(0, 256, (480, 640, 3), dtype=np.uint8)]
+    an = RoadLayoutAnalyzer(max_batch=4, max_segments=8192)
+    cues = an.analyze_batch(np.stack(frames))
+    for f, c in zip(frames, cues):
+        gray = cv2.cvtColor(f, cv2.COLOR_BGR2GRAY)
+        edges = cv2.Canny(gray, 50, 150)
+        h, w = gray.shape
+        center = edges[h // 3:2 * h // 3, w // 3:2 * w // 3]
+        assert c.center_density == np.sum(center > 0) / center.size
+        want = cv2.HoughLinesP(edges, 1, np.pi / 180, 100, minLineLength=100, maxLineGap=10)
+        want = np.zeros((0, 4), np.int32) if want is None else want.reshape(-1, 4)
+        assert np.array_equal(c.lines, want)
+        if len(want):
+            assert abs(c.avg_length - np.mean([np.sqrt((l[2] - l[0]) ** 2 + (l[3] - l[1]) ** 2) for l in want])) < 1e-9
+    an.close()
