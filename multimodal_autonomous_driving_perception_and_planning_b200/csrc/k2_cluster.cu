@@ -19,6 +19,7 @@
 //   phase 3  edge bit-plane, edge count, ROI-masked bit-plane (the PPHT mask) and the row-major point
 //            list (offsets by per-row popcounts, band bases exchanged over DSMEM).
 #include <cooperative_groups.h>
+#include <stdio.h>
 
 #include "lane_common.cuh"
 
@@ -326,6 +327,12 @@ __device__ __forceinline__ bool visit(const uint32_t *C, uint32_t *S, int r, int
 __global__ void __launch_bounds__(K2T) k2_canny_cluster(K2Args A)
 {
     extern __shared__ uint32_t smem[];
+#ifdef LANE_K2_PROF
+    long long t0 = clock64(), tL = 0, tC0 = 0, tX = 0, tP3 = 0, tA = 0, tB = 0, tCc = 0, tD = 0, tmark = t0;
+#define K2TICK(acc) do { long long n_ = clock64(); acc += n_ - tmark; tmark = n_; } while (0)
+#else
+#define K2TICK(acc) do { } while (0)
+#endif
     cg::cluster_group cluster = cg::this_cluster();
     const int G = (int)cluster.num_blocks(), rank = (int)cluster.block_rank();
     const int f = blockIdx.x / G;
@@ -352,44 +359,124 @@ __global__ void __launch_bounds__(K2T) k2_canny_cluster(K2Args A)
         const int seg_rows = (Rv + nseg - 1) / nseg;
         uint32_t *S_up = rank > 0 ? cluster.map_shared_rank(S, rank - 1) : nullptr;
         uint32_t *S_dn = rank < G - 1 ? cluster.map_shared_rank(S, rank + 1) : nullptr;
-        for (;;) {
-            for (;;) {                                   // sweeps until this band is stable
+        // sweeps until this band is stable; returns whether any pixel was promoted
+        // One pass = column-serial sweeps: a thread walks its 32-px column word down and up a run of rows, so a chain
+        // crosses the run vertically in one pass; whenever a word changes, the same thread chases the change sideways
+        // through the neighbouring words of that row, so near-horizontal chains do not need one pass per word.
+        // Races between threads are benign: S only grows and every update is a valid promotion.
+        auto visit3 = [&](int r, int w) {                 // the word and its two neighbours in the row
+            bool c = visit(C, S, r, w, WW);
+            if (w > 0) c |= visit(C, S, r, w - 1, WW);
+            if (w + 1 < WW) c |= visit(C, S, r, w + 1, WW);
+            return c;
+        };
+        auto visit_chase = [&](int r, int w) {            // a promotion is followed along its chain right away:
+            if (!visit(C, S, r, w, WW)) return false;
+            for (int ww = w + 1; ww < WW && visit(C, S, r, ww, WW); ww++) {}      // sideways in the row,
+            for (int ww = w - 1; ww >= 0 && visit(C, S, r, ww, WW); ww--) {}
+            for (int rr = r + 1; rr < Rv && visit3(rr, w); rr++) {}                // down and up the band (also past
+            for (int rr = r - 1; rr >= 0 && visit3(rr, w); rr--) {}                // this thread's own run of rows)
+            return true;
+        };
+        // Only rows that still hold weak-but-not-strong pixels can change, and there are few of them: every thread keeps
+        // a bit mask of such rows in its column run (<= 128 rows) and sweeps just those, downwards then upwards.
+        const bool one_item = WW * nseg <= K2T && seg_rows <= 128;
+        const int my_w = tid % WW, my_seg = tid / WW;
+        const int my_ra = my_seg * seg_rows, my_rb = min(my_ra + seg_rows, Rv);
+        const bool mine = one_item && tid < WW * nseg && my_ra < my_rb;
+        uint32_t pr[4] = {0, 0, 0, 0};
+        if (mine) {
+#pragma unroll
+            for (int j = 0; j < 4; j++)
+                for (int b = 0; b < 32; b++) {
+                    const int r = my_ra + 32 * j + b;
+                    if (r < my_rb && (C[r * WW + my_w] & ~S[(r + 1) * WW + my_w])) pr[j] |= 1u << b;
+                }
+        }
+        auto converge = [&]() {
+            bool any_change = false;
+            for (;;) {
                 bool ch = false;
-                for (int item = tid; item < WW * nseg; item += K2T) {
-                    const int w = item % WW, seg = item / WW;
-                    const int ra = seg * seg_rows, rb = min(ra + seg_rows, Rv);
-                    for (int r = ra; r < rb; r++) ch |= visit(C, S, r, w, WW);
-                    for (int r = rb - 2; r >= ra; r--) ch |= visit(C, S, r, w, WW);
+                if (one_item) {
+                    if (mine) {
+#pragma unroll
+                        for (int j = 0; j < 4; j++) {                 // downwards
+                            uint32_t m = pr[j];
+                            while (m) {
+                                const int b = __ffs(m) - 1, r = my_ra + 32 * j + b;
+                                m &= m - 1;
+                                ch |= visit_chase(r, my_w);
+                                if (!(C[r * WW + my_w] & ~S[(r + 1) * WW + my_w])) pr[j] &= ~(1u << b);
+                            }
+                        }
+#pragma unroll
+                        for (int j = 3; j >= 0; j--) {                // upwards
+                            uint32_t m = pr[j];
+                            while (m) {
+                                const int b = 31 - __clz(m), r = my_ra + 32 * j + b;
+                                m &= ~(1u << b);
+                                ch |= visit_chase(r, my_w);
+                                if (!(C[r * WW + my_w] & ~S[(r + 1) * WW + my_w])) pr[j] &= ~(1u << b);
+                            }
+                        }
+                    }
+                } else {
+                    for (int item = tid; item < WW * nseg; item += K2T) {
+                        const int w = item % WW, seg = item / WW;
+                        const int ra = seg * seg_rows, rb = min(ra + seg_rows, Rv);
+                        for (int r = ra; r < rb; r++) ch |= visit_chase(r, w);
+                        for (int r = rb - 2; r >= ra; r--) ch |= visit_chase(r, w);
+                    }
                 }
                 if (!__syncthreads_or(ch)) break;
+                any_change = true;
             }
-            rounds++;
-            if (G == 1) break;
-            cluster.sync();                              // every band locally stable
-            bool hc = false;
+            return any_change;
+        };
+        converge();
+        K2TICK(tC0);
+        rounds = 1;
+        // Bands then trade boundary rows.  A round ends the loop when NO band promoted anything after seeing its
+        // neighbours' latest rows -- the usual case is one round (edges that cross a band boundary are strong on
+        // both sides already), so the whole frame costs two cluster barriers.
+        while (G > 1) {
+            cluster.sync();                              // every band locally stable: boundary rows are final for this round
             for (int w = tid; w < WW; w += K2T) {
-                if (S_up) { uint32_t v = S_up[(size_t)R * WW + w]; if (v != S[w]) { S[w] = v; hc = true; } }
-                if (S_dn && Rv > 0) {
-                    uint32_t v = S_dn[WW + w];
-                    if (v != S[(size_t)(Rv + 1) * WW + w]) { S[(size_t)(Rv + 1) * WW + w] = v; hc = true; }
-                }
+                if (S_up) S[w] = S_up[(size_t)R * WW + w];
+                if (S_dn && Rv > 0) S[(size_t)(Rv + 1) * WW + w] = S_dn[WW + w];
             }
-            const int flag = __syncthreads_or(hc);
-            if (tid == 0) s_flag = flag;
+            __syncthreads();
+            const bool changed = converge();
+            if (tid == 0) s_flag = changed;
             cluster.sync();
             int any = 0;
             if (tid < G) any = *cluster.map_shared_rank(&s_flag, tid);
             any = __syncthreads_or(any);
             if (!any) break;
+            rounds++;
         }
     }
 
-    // ---- phase 3: outputs
+    K2TICK(tX);
+    // ---- phase 3: outputs.  One fully parallel pass writes the edge plane, counts edges and forms the ROI-masked
+    // plane in shared memory (the candidate plane is no longer needed, its storage is reused), so that the
+    // row-major point list below never waits on global memory.
+    const LaneGeom &g = A.g;
+    const int y0 = max(b0, g.by0), y1 = min(b1, g.by1);
+    const uint32_t *roi = A.roi_bits;
+    uint32_t *Mk = C;                                     // [Rv][WW] masked edges of this band
     int cnt = 0;
     for (int i = tid; i < Rv * WW; i += K2T) {
-        const uint32_t s = S[WW + i];
-        A.edge_bits[((size_t)f * H + b0) * WW + i] = s;
-        cnt += __popc(s);
+        const uint32_t sv = S[WW + i];
+        const int y = b0 + i / WW;
+        A.edge_bits[((size_t)f * H + b0) * WW + i] = sv;
+        cnt += __popc(sv);
+        uint32_t m = 0;
+        if (y >= g.by0 && y < g.by1) {
+            m = sv & roi[(size_t)b0 * WW + i];
+            A.pmask_bits[((size_t)f * g.bh + (y - g.by0)) * WW + (i - (i / WW) * WW)] = m;
+        }
+        Mk[i] = m;
     }
     for (int o = 16; o; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
     if (lane == 0) s_red[wid] = cnt;
@@ -400,19 +487,14 @@ __global__ void __launch_bounds__(K2T) k2_canny_cluster(K2Args A)
         if (t) atomicAdd(&A.n_edges[f], t);
         if (rank == 0) A.rounds[f] = rounds;
     }
-    // ROI rows of this band
-    const LaneGeom &g = A.g;
-    const int y0 = max(b0, g.by0), y1 = min(b1, g.by1);
-    const uint32_t *roi = A.roi_bits;
-    for (int y = y0 + wid; y < y1; y += K2T / 32) {
+    K2TICK(tA);
+    // a thread per ROI row: count, block scan, then write the row's points (rows are short lists; all rows in parallel)
+    const int nrows = max(y1 - y0, 0);
+    for (int i = tid; i < nrows; i += K2T) {
+        const uint32_t *row = Mk + (size_t)(y0 + i - b0) * WW;
         int c = 0;
-        for (int w = lane; w < WW; w += 32) {
-            const uint32_t m = S[(size_t)(y - b0 + 1) * WW + w] & roi[(size_t)y * WW + w];
-            A.pmask_bits[((size_t)f * g.bh + (y - g.by0)) * WW + w] = m;
-            c += __popc(m);
-        }
-        for (int o = 16; o; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
-        if (lane == 0) rowoff[y - b0] = c;
+        for (int w = 0; w < WW; w++) c += __popc(row[w]);
+        rowoff[y0 + i - b0] = c;
     }
     __syncthreads();
     if (wid == 0) {                                       // exclusive scan of the row counts
@@ -431,7 +513,9 @@ __global__ void __launch_bounds__(K2T) k2_canny_cluster(K2Args A)
         if (lane == 0) s_total = run;
     }
     __syncthreads();
+    K2TICK(tB);
     if (G > 1) cluster.sync();
+    K2TICK(tCc);
     if (tid == 0) {
         int base = 0;
         for (int r = 0; r < rank; r++) base += *cluster.map_shared_rank(&s_total, r);
@@ -440,28 +524,25 @@ __global__ void __launch_bounds__(K2T) k2_canny_cluster(K2Args A)
     }
     __syncthreads();
     uint32_t *out = A.points + (size_t)f * g.max_points + s_base;
-    for (int y = y0 + wid; y < y1; y += K2T / 32) {
-        int pos = rowoff[y - b0];
-        for (int wb = 0; wb < WW; wb += 32) {
-            const int w = wb + lane;
-            uint32_t m = 0;
-            if (w < WW) m = S[(size_t)(y - b0 + 1) * WW + w] & roi[(size_t)y * WW + w];
-            const int c = __popc(m);
-            int inc = c;
-            for (int o = 1; o < 32; o <<= 1) {
-                int t = __shfl_up_sync(0xffffffffu, inc, o);
-                if (lane >= o) inc += t;
-            }
-            int p = pos + inc - c;
+    for (int i = tid; i < nrows; i += K2T) {
+        const int y = y0 + i;
+        const uint32_t *row = Mk + (size_t)(y - b0) * WW;
+        int p = rowoff[y - b0];
+        for (int w = 0; w < WW; w++) {
+            uint32_t m = row[w];
             while (m) {
                 const int b = __ffs(m) - 1;
                 out[p++] = ((uint32_t)y << 16) | (uint32_t)(w * 32 + b);
                 m &= m - 1;
             }
-            pos += __shfl_sync(0xffffffffu, inc, 31);
         }
     }
+    K2TICK(tD);
     if (G > 1) cluster.sync();                            // keep s_total alive until every band has read it
+#ifdef LANE_K2_PROF
+    K2TICK(tP3);
+    if (tid == 0 && f == 0) printf("k2b rank=%d total=%lld load=%lld converge0=%lld rounds(%d)=%lld p3: write=%lld counts=%lld csync=%lld points=%lld final=%lld\n", rank, clock64() - t0, tL, tC0, rounds, tX, tA, tB, tCc, tD, tP3);
+#endif
 }
 
 // byte map -> bit-plane (generic-width fallback path)
