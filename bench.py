@@ -93,7 +93,7 @@ class ClockSampler:
         self.proc = None
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "100",
+                ["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "20",
                  "-i", str(index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._pump, daemon=True)
             self.thread.start()
@@ -129,8 +129,8 @@ class ClockSampler:
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--frames", type=int, default=256, help="frames per GPU per step")
     ap.add_argument("--distinct", type=int, default=64, help="distinct generator frames per stream (tiled in time)")
@@ -225,6 +225,8 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    sampler = ClockSampler(local) if rank == 0 else None
+    t_load0 = time.perf_counter()
     for _ in range(max(args.warmup, 3)):
         recs = step()
     found = int(recs["side"]["valid"].sum())
@@ -233,7 +235,6 @@ def main():
     ctx.set_profiling(True)
     stage_sum = {k: 0.0 for k in _native.STAGE_NAMES}
     launches = 0
-    sampler = ClockSampler(local) if rank == 0 else None
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t0 = time.perf_counter()
@@ -247,7 +248,7 @@ def main():
     e1.record(stream)
     barrier()
     t1 = time.perf_counter()
-    clocks = sampler.stop(t0, t1) if sampler else None
+    timed_window = (t0, t1)
     dev_ms = e0.elapsed_time(e1)
     ctx.set_profiling(False)
     if world > 1:
@@ -275,6 +276,13 @@ def main():
         dist.all_reduce(tm, op=dist.ReduceOp.MAX)
         e2e_s = float(tm.item())
     e2e_val = args.gpus * n * e2e_steps / e2e_s
+    clocks = None
+    if sampler:
+        # nvidia-smi samples every 20 ms: the timed region alone is tens of ms, so the record spans everything that ran
+        # under load (warm-up, timed region, e2e leg) and says how many samples fell inside the timed region itself
+        clocks = sampler.stop(t_load0, time.perf_counter())
+        clocks["window"] = "warm-up + timed region + e2e leg"
+        clocks["samples_in_timed_region"] = sum(1 for (t, _) in sampler.lines if timed_window[0] <= t <= timed_window[1])
 
     if rank == 0:
         peaks = {}

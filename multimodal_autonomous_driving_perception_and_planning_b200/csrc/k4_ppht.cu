@@ -1019,9 +1019,11 @@ int lane_ppht_plan_v3(const int2 *win, int cells_total, int2 *win3, int *cells_m
     int width[LANE_NUM_ANGLES];
     for (int n = 0; n < LANE_NUM_ANGLES; n++)
         width[n] = (n + 1 < LANE_NUM_ANGLES ? win[n + 1].y : cells_total) - win[n].y;
+    const int forced = getenv("LANE_PPHT_G") ? atoi(getenv("LANE_PPHT_G")) : 0;      // tuning knob
     for (int pass = 0; pass < 2; pass++)
     for (int G = 1; G <= 16; G *= 2) {
-        const size_t budget = pass == 0 ? 112 * 1024 : 226 * 1024;   // first try to fit two CTAs per SM
+        if (forced && G != forced) continue;
+        const size_t budget = pass == 0 && !forced ? 112 * 1024 : 226 * 1024;   // first try to fit two CTAs per SM
         int off[16] = {0};
         for (int n = 0; n < LANE_NUM_ANGLES; n++) {
             win3[n] = make_int2(win[n].x, off[n % G]);
