@@ -20,6 +20,7 @@
 //            list (offsets by per-row popcounts, band bases exchanged over DSMEM).
 #include <cooperative_groups.h>
 #include <stdio.h>
+#include <stdlib.h>
 
 #include "lane_common.cuh"
 
@@ -585,7 +586,8 @@ bool launch_canny_cluster(const uint8_t *blur, const uint32_t *hist, const uint8
     const int H = g.H, W = g.W, WW = (W + 31) / 32;
     if (W % 16 != 0 || ((uintptr_t)blur % 16) != 0) return false;
     int G = 1;
-    while (G < 16 && H > 160 * G) G *= 2;
+    const int rows_per_band = getenv("LANE_K2_ROWS") ? atoi(getenv("LANE_K2_ROWS")) : 160;   // tuning knob
+    while (G < 16 && H > rows_per_band * G) G *= 2;
     size_t smem = 0;
     int R = 0;
     for (;; G *= 2) {
