@@ -2,8 +2,9 @@
 //
 // Stage map (reference lines are under /root/reference/src/perception/lane_detector.py):
 //   K1  k1_blur_hist.cu   gray (:69) + 5x5 binomial blur (:72) + 256-bin histogram (:79)
-//   K2  k2_canny.cu       median/thresholds (:79-81) + Sobel + NMS + hysteresis (:83)
-//       k2_compact.cu     ROI mask (:86-90) + row-major point list (HoughLinesP's nzloc)
+//   K2  k2_cluster.cu     median/thresholds (:79-81) + Sobel + NMS (k2a), then hysteresis (:83) + ROI mask
+//                         (:86-90) + row-major point list (HoughLinesP's nzloc) in one cluster per frame (k2b)
+//       k2_canny.cu       byte-map fallback of the same stages for sizes the bit-plane path does not take
 //   K3  k3_hough.cu       standard Hough accumulator + peaks (north-star add-on)
 //   K4  k4_ppht.cu        exact cv2.HoughLinesP (:94-101)
 //   K5  k5_fit.cu         side split (:105-134), polyfit + EMA + points (:136-176), offset (:253-272)

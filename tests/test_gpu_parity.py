@@ -329,3 +329,50 @@ def test_road_layout_cues_match_cv2():
         if len(want):
             assert abs(c.avg_length - np.mean([np.sqrt((l[2] - l[0]) ** 2 + (l[3] - l[1]) ** 2) for l in want])) < 1e-9
     an.close()
+
+
+def _random_scene(rng, h, w):
+    """Random structured frame: background gradient, random lines / rectangles / circles, mild noise."""
+    yy, xx = np.mgrid[0:h, 0:w]
+    base = (rng.integers(20, 200) + rng.integers(-60, 60) * yy / h + rng.integers(-60, 60) * xx / w)
+    img = np.clip(np.stack([base + rng.integers(-20, 20) for _ in range(3)], -1), 0, 255).astype(np.uint8)
+    for _ in range(int(rng.integers(3, 25))):
+        col = tuple(int(v) for v in rng.integers(0, 256, 3))
+        p = rng.integers(-20, max(h, w) + 20, 4)
+        kind = rng.integers(0, 3)
+        if kind == 0:
+            cv2.line(img, (int(p[0]), int(p[1])), (int(p[2]), int(p[3])), col, int(rng.integers(1, 6)))
+        elif kind == 1:
+            cv2.rectangle(img, (int(p[0]), int(p[1])), (int(p[2]), int(p[3])), col, int(rng.choice([-1, 1, 2])))
+        else:
+            cv2.circle(img, (int(p[0]) % w, int(p[1]) % h), int(rng.integers(3, 60)), col, int(rng.choice([-1, 1, 3])))
+    if rng.random() < 0.5:
+        img = np.clip(img.astype(np.int16) + rng.integers(-6, 7, img.shape), 0, 255).astype(np.uint8)
+    return img
+
+
+@pytest.mark.parametrize("seed", range(10))
+def test_randomised_scenes_against_cv2(seed):
+    """Property-style sweep: random sizes (aligned and not), random structured content; the Canny map, the masked
+    point list and the HoughLinesP segments must equal what cv2 itself computes with the reference's calls."""
+    rng = np.random.default_rng(1000 + seed)
+    h = int(rng.integers(40, 420))
+    w = int(rng.choice([rng.integers(3, 40) * 16, rng.integers(50, 640)]))
+    frames = [_random_scene(rng, h, w) for _ in range(3)]
+    # odd seeds use looser Hough literals so small frames still produce many segments
+    thr, min_len, gap = (50, 50, 150) if seed % 2 == 0 else (int(rng.integers(8, 30)), int(rng.integers(5, 30)),
+                                                              int(rng.integers(0, 40)))
+    det = LaneDetector(max_batch=3, max_segments=4096, debug=True)
+    det._context(h, w, 3).set_hough_params(thr, min_len, gap)
+    det.detect_batch(np.stack(frames))
+    ref = Cv2LaneOracle()
+    for i, f in enumerate(frames):
+        edges = ref.edges(ref.blurred(f))
+        masked = ref.masked(edges)
+        lines = cv2.HoughLinesP(masked, rho=1, theta=np.pi / 180, threshold=thr, minLineLength=min_len,
+                                maxLineGap=gap)
+        want = np.zeros((0, 4), np.int32) if lines is None else lines.reshape(-1, 4)
+        assert np.array_equal(det._ctx.tap(_native.TAP_EDGES, i), edges), (seed, i, h, w)
+        assert det.last_records[i]["n_roi_points"] == int((masked != 0).sum())
+        assert np.array_equal(det._ctx.tap(_native.TAP_SEGMENTS, i), want), (seed, i, h, w, thr, min_len, gap)
+    det.close()
