@@ -10,6 +10,7 @@
 #include <algorithm>
 
 #include "lane_common.cuh"
+#include <type_traits>
 
 namespace {
 
@@ -163,11 +164,12 @@ __device__ __forceinline__ void gray16(const uint32_t (&w)[12], uint32_t (&g)[8]
 constexpr int RING = 3;
 constexpr int ROW_BYTES = 32 * SPX * 3;          // 1536
 
-template <bool TMA>
-__global__ void __launch_bounds__(SWARPS * 32) k1_strip(const uint8_t *__restrict__ frames, uint8_t *__restrict__ blur,
+template <bool TMA, int MINB = 0>
+__global__ void __launch_bounds__(SWARPS * 32, MINB) k1_strip(const uint8_t *__restrict__ frames, uint8_t *__restrict__ blur,
                                                         uint32_t *__restrict__ hist, int *__restrict__ task_counter,
                                                         int n_frames, int H, int W, int band_rows)
 {
+    __shared__ uint32_t k1_tot[SWARPS][256];
     extern __shared__ __align__(128) uint8_t k1_smem[];      // [SWARPS][8192] counters | [SWARPS][RING][1536] ring | barriers
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     uint8_t *wh = k1_smem + wid * (256 * 32);
@@ -207,12 +209,15 @@ __global__ void __launch_bounds__(SWARPS * 32) k1_strip(const uint8_t *__restric
         const uint8_t *src = frames + f * frame_px * 3 + (size_t)max(xl, 0) * 3;
         uint8_t *dst = blur + f * frame_px + max(xl, 0);
 
-        uint32_t p1[8], p2[8], p3[8], p4[8];
+        // column-filter state, two generations deep: rows alternate between slot 0 and slot 1 (the row loop is
+        // unrolled by two below) so "previous row" is the other slot and no register moves are needed
+        uint32_t sg[2][8], s1[2][8], s2[2][8], s3[2][8];
 #pragma unroll
-        for (int j = 0; j < 8; j++) p1[j] = p2[j] = p3[j] = p4[j] = 0;
-        uint32_t tot[8];
+        for (int j = 0; j < 8; j++)
+            sg[0][j] = sg[1][j] = s1[0][j] = s1[1][j] = s2[0][j] = s2[1][j] = s3[0][j] = s3[1][j] = 0;
+        // per-task 32-bit totals live in shared memory (touched once per flush), not in 8 registers
 #pragma unroll
-        for (int b = 0; b < 8; b++) tot[b] = 0;
+        for (int b = 0; b < 8; b++) k1_tot[wid][b * 32 + lane] = 0;
         int since_flush = 0;
 
         auto flush = [&]() {
@@ -226,7 +231,7 @@ __global__ void __launch_bounds__(SWARPS * 32) k1_strip(const uint8_t *__restric
                 s = __dp4a(a.z, 0x01010101u, s); s = __dp4a(a.w, 0x01010101u, s);
                 s = __dp4a(c.x, 0x01010101u, s); s = __dp4a(c.y, 0x01010101u, s);
                 s = __dp4a(c.z, 0x01010101u, s); s = __dp4a(c.w, 0x01010101u, s);
-                tot[b] += s;
+                k1_tot[wid][b * 32 + lane] += s;
                 row[0] = make_uint4(0, 0, 0, 0); row[1] = make_uint4(0, 0, 0, 0);
             }
             __syncwarp();
@@ -276,9 +281,10 @@ __global__ void __launch_bounds__(SWARPS * 32) k1_strip(const uint8_t *__restric
         if (TMA)
             for (int i = 0; i < RING && r0 - 2 + i < r1 + 2; i++) issue_row(r0 - 2 + i);
         load_row(r0 - 2);
-        for (int y = r0 - 2; y < r1 + 2; y++) {
-            uint32_t g[8];
-            gray16(w, g);
+        const uint32_t hbase = smem_u32(wh) + lane;         // this lane's column of the private counters
+        auto row_step = [&](auto slot, int y) {
+            constexpr int c = decltype(slot)::value, o = c ^ 1;
+            gray16(w, sg[c]);
             if (y + 1 < r1 + 2) load_row(y + 1);        // next row: from the ring (TMA) or prefetched into registers
             uint32_t V[8];
 #pragma unroll
@@ -286,12 +292,12 @@ __global__ void __launch_bounds__(SWARPS * 32) k1_strip(const uint8_t *__restric
                 // The first three stages stay below 2048, where binary16 (denormals included) is exact and its bit
                 // pattern is the integer itself, so they run as add.f16x2 on the FMA pipe; that takes 24 adds per
                 // row off the ALU pipe, which is the busiest one in this kernel.  The last stage (<= 4080) is integer.
-                uint32_t t1 = h2add(g[j], p1[j]); p1[j] = g[j];
-                uint32_t t2 = h2add(t1, p2[j]);   p2[j] = t1;
-                uint32_t t3 = h2add(t2, p3[j]);   p3[j] = t2;
-                V[j] = t3 + p4[j];                p4[j] = t3;
+                s1[c][j] = h2add(sg[c][j], sg[o][j]);
+                s2[c][j] = h2add(s1[c][j], s1[o][j]);
+                s3[c][j] = h2add(s2[c][j], s2[o][j]);
+                V[j] = s3[c][j] + s3[o][j];
             }
-            if (y < r0 + 2) continue;                    // pipeline fill: V is the blur column sum of row y-2
+            if (y < r0 + 2) return;                      // pipeline fill: V is the blur column sum of row y-2
             const int yo = y - 2;
             uint32_t L7 = __shfl_up_sync(0xffffffffu, V[7], 1);
             uint32_t R0 = __shfl_down_sync(0xffffffffu, V[0], 1);
@@ -308,30 +314,39 @@ __global__ void __launch_bounds__(SWARPS * 32) k1_strip(const uint8_t *__restric
                 const uint32_t vm = j == 0 ? L7 : V[j - 1], vp = j == 7 ? R0 : V[j + 1];
                 Hs[j] = vm + vp + 0x00800080u + 4u * (O[j] + O[j + 1]) + 6u * V[j];
             }
-            uint4 o;
-            o.x = __byte_perm(Hs[0], Hs[1], 0x7531);
-            o.y = __byte_perm(Hs[2], Hs[3], 0x7531);
-            o.z = __byte_perm(Hs[4], Hs[5], 0x7531);
-            o.w = __byte_perm(Hs[6], Hs[7], 0x7531);
+            uint4 ov;
+            ov.x = __byte_perm(Hs[0], Hs[1], 0x7531);
+            ov.y = __byte_perm(Hs[2], Hs[3], 0x7531);
+            ov.z = __byte_perm(Hs[4], Hs[5], 0x7531);
+            ov.w = __byte_perm(Hs[6], Hs[7], 0x7531);
             if (is_out) {
-                *reinterpret_cast<uint4 *>(dst + (size_t)yo * W) = o;
-                uint8_t *hp = wh + lane;
-                const uint32_t ow[4] = {o.x, o.y, o.z, o.w};
+                *reinterpret_cast<uint4 *>(dst + (size_t)yo * W) = ov;
+                const uint32_t ow[4] = {ov.x, ov.y, ov.z, ov.w};
 #pragma unroll
                 for (int q = 0; q < 4; q++) {
 #pragma unroll
                     for (int k = 0; k < 4; k++) {
-                        uint32_t v = (ow[q] >> (8 * k)) & 0xFFu;
-                        hp[v * 32] += 1;
+                        // counter address = base + 32 * byte k of the word, in one dot-product instruction (FMA pipe)
+                        const uint32_t addr = __dp4a(ow[q], 0x20u << (8 * k), hbase);
+                        uint32_t t;
+                        asm volatile("ld.shared.u8 %0, [%1];" : "=r"(t) : "r"(addr));
+                        t += 1;
+                        asm volatile("st.shared.u8 [%0], %1;" ::"r"(addr), "r"(t) : "memory");
                     }
                 }
             }
             if (++since_flush == FLUSH_ROWS) { flush(); since_flush = 0; }
+        };
+        for (int y = r0 - 2;;) {
+            row_step(std::integral_constant<int, 0>{}, y);
+            if (++y >= r1 + 2) break;
+            row_step(std::integral_constant<int, 1>{}, y);
+            if (++y >= r1 + 2) break;
         }
         flush();
 #pragma unroll
         for (int b = 0; b < 8; b++)
-            if (tot[b]) atomicAdd(&hist[f * 256 + b * 32 + lane], tot[b]);
+            if (const uint32_t t = k1_tot[wid][b * 32 + lane]) atomicAdd(&hist[f * 256 + b * 32 + lane], t);
     }
 }
 
@@ -392,8 +407,11 @@ void launch_blur_hist(const uint8_t *frames, uint8_t *blur_out, uint32_t *hist, 
             cudaFuncSetAttribute(k1_strip<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tma);
             configured = true;
         }
-        if (use_ldg)
-            k1_strip<false><<<sms * 5, SWARPS * 32, smem_ldg, st>>>(frames, blur_out, hist, task_counter, n, H, W, band_rows);
+        static const int minb = getenv("LANE_K1_MINB") ? atoi(getenv("LANE_K1_MINB")) : 5;
+        if (use_ldg && minb == 5)
+            k1_strip<false, 5><<<sms * 5, SWARPS * 32, smem_ldg, st>>>(frames, blur_out, hist, task_counter, n, H, W, band_rows);
+        else if (use_ldg)
+            k1_strip<false, 0><<<sms * 4, SWARPS * 32, smem_ldg, st>>>(frames, blur_out, hist, task_counter, n, H, W, band_rows);
         else
             k1_strip<true><<<sms * 4, SWARPS * 32, smem_tma, st>>>(frames, blur_out, hist, task_counter, n, H, W, band_rows);
     } else {
