@@ -167,7 +167,7 @@ constexpr int ROW_BYTES = 32 * SPX * 3;          // 1536
 template <bool TMA, int MINB = 0>
 __global__ void __launch_bounds__(SWARPS * 32, MINB) k1_strip(const uint8_t *__restrict__ frames, uint8_t *__restrict__ blur,
                                                         uint32_t *__restrict__ hist, int *__restrict__ task_counter,
-                                                        int n_frames, int H, int W, int band_rows)
+                                                        int n_frames, int H, int W, int band_rows, int tail_frames, int tail_rows)
 {
     __shared__ uint32_t k1_tot[SWARPS][256];
     extern __shared__ __align__(128) uint8_t k1_smem[];      // [SWARPS][8192] counters | [SWARPS][RING][1536] ring | barriers
@@ -189,8 +189,11 @@ __global__ void __launch_bounds__(SWARPS * 32, MINB) k1_strip(const uint8_t *__r
     }
     __syncwarp();
     const int n_strips = (W + STRIP_OUT - 1) / STRIP_OUT;
-    const int n_bands = (H + band_rows - 1) / band_rows;
-    const int n_tasks = n_frames * n_bands * n_strips;
+    // tasks are handed out in order: the first n_frames - tail_frames frames in bands of band_rows rows, the last
+    // tail_frames frames in thinner bands, so the warps run dry within a short task of each other at the end
+    const int n_bands = (H + band_rows - 1) / band_rows, n_bands_t = (H + tail_rows - 1) / tail_rows;
+    const int n_main = (n_frames - tail_frames) * n_bands * n_strips;
+    const int n_tasks = n_main + tail_frames * n_bands_t * n_strips;
     const size_t frame_px = (size_t)H * W;
 
     for (;;) {
@@ -198,10 +201,12 @@ __global__ void __launch_bounds__(SWARPS * 32, MINB) k1_strip(const uint8_t *__r
         if (lane == 0) task = atomicAdd(task_counter, 1);
         task = __shfl_sync(0xffffffffu, task, 0);
         if (task >= n_tasks) break;
-        const int strip = task % n_strips;
-        const int band = (task / n_strips) % n_bands;
-        const int f = task / (n_strips * n_bands);
-        const int r0 = band * band_rows, r1 = min(r0 + band_rows, H);
+        const bool tail = task >= n_main;
+        const int tt = tail ? task - n_main : task, nb = tail ? n_bands_t : n_bands, br = tail ? tail_rows : band_rows;
+        const int strip = tt % n_strips;
+        const int band = (tt / n_strips) % nb;
+        const int f = tt / (n_strips * nb) + (tail ? n_frames - tail_frames : 0);
+        const int r0 = band * br, r1 = min(r0 + br, H);
         const int xl = strip * STRIP_OUT - SPX + SPX * lane;          // first pixel of this lane
         const bool in_img = xl >= 0 && xl < W;
         const bool is_out = in_img && lane >= 1 && lane <= 30;
@@ -395,7 +400,20 @@ void launch_blur_hist(const uint8_t *frames, uint8_t *blur_out, uint32_t *hist, 
             cudaGetDevice(&dev);
             cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
         }
-        const int band_rows = H >= 540 ? 68 : (H >= 120 ? 60 : H);
+        // band height: 102 rows (3.9 % halo rows) when there is plenty of work, thinner when a small batch would
+        // otherwise leave most of the sms*5*SWARPS warps without a task; the last sixteenth of the frames is cut into
+        // bands a third as high to shorten the end-of-kernel tail
+        const int n_strips = (W + STRIP_OUT - 1) / STRIP_OUT, warps = sms * 5 * SWARPS;
+        static const int band_env = getenv("LANE_K1_BAND") ? atoi(getenv("LANE_K1_BAND")) : 0;
+        static const int tail_env = getenv("LANE_K1_TAIL") ? atoi(getenv("LANE_K1_TAIL")) : -1;
+        int band_rows = band_env > 0 ? band_env : (H >= 540 ? 102 : (H >= 120 ? 60 : H));
+        {
+            const long rows_per_warp = ((long)n * H * n_strips + 2 * warps - 1) / (2 * warps);   // >= 2 tasks per warp
+            if (!band_env) band_rows = (int)std::max(12L, std::min((long)band_rows, rows_per_warp));
+        }
+        int tail_frames = tail_env >= 0 ? std::min(tail_env, n) : (n >= 16 ? n / 16 : 0);
+        const int tail_rows = std::max(12, band_rows / 3);
+        if (tail_rows >= band_rows) tail_frames = 0;
         cudaMemsetAsync(task_counter, 0, sizeof(int), st);
         // default: direct 16-byte loads.  LANE_B200_K1=tma selects the bulk-copy staged variant (measured slower on
         // B200: 0.645 vs 0.546 ms per 256 1080p frames -- the kernel is ALU-issue bound, not load-latency bound)
@@ -408,12 +426,13 @@ void launch_blur_hist(const uint8_t *frames, uint8_t *blur_out, uint32_t *hist, 
             configured = true;
         }
         static const int minb = getenv("LANE_K1_MINB") ? atoi(getenv("LANE_K1_MINB")) : 5;
-        if (use_ldg && minb == 5)
-            k1_strip<false, 5><<<sms * 5, SWARPS * 32, smem_ldg, st>>>(frames, blur_out, hist, task_counter, n, H, W, band_rows);
-        else if (use_ldg)
-            k1_strip<false, 0><<<sms * 4, SWARPS * 32, smem_ldg, st>>>(frames, blur_out, hist, task_counter, n, H, W, band_rows);
+        if (use_ldg && minb == 5) {
+            k1_strip<false, 5><<<sms * 5, SWARPS * 32, smem_ldg, st>>>(frames, blur_out, hist, task_counter, n, H, W, band_rows,
+                                                                     tail_frames, tail_rows);
+        } else if (use_ldg)
+            k1_strip<false, 0><<<sms * 4, SWARPS * 32, smem_ldg, st>>>(frames, blur_out, hist, task_counter, n, H, W, band_rows, tail_frames, tail_rows);
         else
-            k1_strip<true><<<sms * 4, SWARPS * 32, smem_tma, st>>>(frames, blur_out, hist, task_counter, n, H, W, band_rows);
+            k1_strip<true><<<sms * 4, SWARPS * 32, smem_tma, st>>>(frames, blur_out, hist, task_counter, n, H, W, band_rows, tail_frames, tail_rows);
     } else {
         dim3 grid((W + TW - 1) / TW, (H + TH - 1) / TH, n);
         k1_tile<<<grid, NT, 0, st>>>(frames, blur_out, hist, H, W);
