@@ -19,10 +19,12 @@
 //   phase 3  edge bit-plane, edge count, ROI-masked bit-plane (the PPHT mask) and the row-major point
 //            list (offsets by per-row popcounts, band bases exchanged over DSMEM).
 #include <cooperative_groups.h>
+#include <cuda_fp16.h>
 #include <stdio.h>
 #include <stdlib.h>
 
 #include "lane_common.cuh"
+#include <type_traits>
 
 namespace cg = cooperative_groups;
 
@@ -68,77 +70,6 @@ __device__ __forceinline__ uint32_t h2max(uint32_t a, uint32_t b)
     return d;
 }
 
-template <int P>
-__device__ __forceinline__ int half_of(const uint32_t (&M)[8])
-{
-    return (int)((M[P >> 1] >> ((P & 1) * 16)) & 0xFFFFu);
-}
-template <int P>
-__device__ __forceinline__ int left_of(const uint32_t (&M)[8], uint32_t mL)
-{
-    if constexpr (P == 0) return (int)(mL >> 16);
-    else return half_of<P - 1>(M);
-}
-template <int P>
-__device__ __forceinline__ int right_of(const uint32_t (&M)[8], uint32_t mR)
-{
-    if constexpr (P == 15) return (int)(mR & 0xFFFFu);
-    else return half_of<P + 1>(M);
-}
-
-// sector class of one candidate pixel: 0 horizontal, 1 vertical, 2 diagonal s=+1, 3 diagonal s=-1
-template <int P>
-__device__ __forceinline__ void classify_px(const uint32_t (&M)[8], const uint32_t (&dx)[8], const uint32_t (&dy)[8],
-                                            int low, int high, uint32_t &cand, uint32_t &strong, uint32_t &cls)
-{
-    const int m = half_of<P>(M);
-    if (m > low) {
-        const uint32_t xr = dx[P >> 1] >> ((P & 1) * 16), yr = dy[P >> 1] >> ((P & 1) * 16);
-        const int a = (int)(xr & 0x7FFFu), b = (int)(yr & 0x7FFFu);
-        const int tg22x = a * 13573, ay = b << 15;
-        uint32_t c;
-        if (ay < tg22x) c = 0;
-        else if (ay > tg22x + (a << 16)) c = 1;
-        else c = 2u + (((xr ^ yr) >> 15) & 1u);
-        cand |= 1u << P;
-        cls |= c << (2 * P);
-        if (m > high) strong |= 1u << P;
-    }
-}
-
-template <int P>
-__device__ __forceinline__ void nms_px(const uint32_t (&M0)[8], const uint32_t (&M1)[8], const uint32_t (&M2)[8],
-                                       uint32_t l0, uint32_t r0, uint32_t l1, uint32_t r1, uint32_t l2, uint32_t r2,
-                                       uint32_t cand, uint32_t cls, uint32_t &keep)
-{
-    if (cand & (1u << P)) {
-        const int m = half_of<P>(M1);
-        const uint32_t c = (cls >> (2 * P)) & 3u;
-        int n1, n2;
-        bool ge;          // second comparison is >= for the axis-aligned sectors
-        if (c == 0) { n1 = left_of<P>(M1, l1); n2 = right_of<P>(M1, r1); ge = true; }
-        else if (c == 1) { n1 = half_of<P>(M0); n2 = half_of<P>(M2); ge = true; }
-        else if (c == 2) { n1 = left_of<P>(M0, l0); n2 = right_of<P>(M2, r2); ge = false; }
-        else { n1 = right_of<P>(M0, r0); n2 = left_of<P>(M2, l2); ge = false; }
-        if (m > n1 && (ge ? m >= n2 : m > n2)) keep |= 1u << P;
-    }
-}
-
-template <int P>
-struct ForPx {
-    template <typename F>
-    __device__ __forceinline__ static void run(F &&f)
-    {
-        ForPx<P - 1>::run(f);
-        f.template operator()<P>();
-    }
-};
-template <>
-struct ForPx<-1> {
-    template <typename F>
-    __device__ __forceinline__ static void run(F &&) {}
-};
-
 // median of the blurred plane (x2) from its histogram; warp-collective
 __device__ int median_x2_warp(const uint32_t *h, long long P, int lane)
 {
@@ -167,9 +98,20 @@ __device__ int median_x2_warp(const uint32_t *h, long long P, int lane)
     return v0 + v1;
 }
 
-// phase 1 for one (strip, row range) task; writes C/S words of rows [q0,q1) into the band's planes
-__device__ void canny_rows(int H, int W, int WW, const uint8_t *blur_f, int strip, int q0, int q1, int row0,
-                           uint32_t *Cw, uint32_t *Sw, int lane, int low, int high)
+// Sobel + NMS for one (strip, row range) task; writes the C/S words of rows [q0,q1) of the frame's planes.
+//
+// Dense part (every pixel, two per instruction): column sums T(c) = B(c) + B(c+1) give the Sobel column filters as
+// T(c-1) + T(c) and T(c) - T(c-1); the row loop is unrolled by two with compile-time slots so the two generations of
+// B and T rotate by renaming.  The magnitude row and the signed gradients go to a per-warp shared-memory ring (3 rows
+// of M, 2 of dx/dy) as 16-bit values, and a packed compare gives the 16-bit candidate mask of the lane.
+// Sparse part (candidates only, one row later when the row below exists): every lane walks the set bits of its own
+// mask and does the sector test (TG22 fixed point) and the 3x3 non-maximum test with plain 16-bit loads from the
+// ring -- neighbours in other lanes' columns are just addresses, no shuffles or compile-time pixel indices.
+constexpr int K2A_RS = 512 + 16;                         // M ring row stride in u16 (8 px of padding either side)
+constexpr int K2A_WSM = 3 * K2A_RS + 4 * 512;            // u16 per warp: M[3][RS] | DX[2][512] | DY[2][512]
+
+__device__ __forceinline__ void canny_rows(int H, int W, int WW, const uint8_t *blur_f, int strip, int q0, int q1,
+                                           uint32_t *Cw, uint32_t *Sw, int lane, int low, int high, uint16_t *wsm)
 {
     const int xl = strip * STRIP_OUT - SPX + SPX * lane;
     const bool in_img = xl >= 0 && xl < W;
@@ -177,41 +119,49 @@ __device__ void canny_rows(int H, int W, int WW, const uint8_t *blur_f, int stri
     const uint8_t *src = blur_f + max(xl, 0);
     const int word = strip * (STRIP_OUT / 32) + ((lane - 1) >> 1);
     const bool writer = (lane & 1) && lane <= 29 && in_img && word < WW;
+    const uint32_t lane_mask = in_img ? 0x7FFF7FFFu : 0u;   // |.| mask of the packed gradients; 0 outside the image
+    const uint32_t low2 = (uint32_t)low | ((uint32_t)low << 16);
+    const uint32_t xb = SPX * lane;
+    const uint32_t own_mask = (lane >= 1 && lane <= 30 && in_img) ? 0xFFFFu : 0u;   // halo lanes only feed neighbours
+    uint16_t *Mring = wsm + 8;                               // + slot * K2A_RS
+    uint16_t *DXr = wsm + 3 * K2A_RS, *DYr = DXr + 2 * 512;  // + (row & 1) * 512
 
-    uint32_t B0[8], B1[8], M0[8], M1[8];
-    uint32_t l0 = 0, r0 = 0, l1 = 0, r1 = 0;
-    uint32_t cand1 = 0, strong1 = 0, cls1 = 0;
-#pragma unroll
-    for (int j = 0; j < 8; j++) B0[j] = B1[j] = M0[j] = M1[j] = 0;
-
+    uint32_t Bs[2][8], Ts[2][8];
     auto load_raw = [&](int y) {
-        const int yy = min(max(y, 0), H - 1);          // BORDER_REPLICATE rows
+        const uint32_t off = (uint32_t)min(max(y, 0), H - 1) * (uint32_t)W;          // BORDER_REPLICATE rows
         uint4 v = make_uint4(0, 0, 0, 0);
-        if (in_img) v = __ldg(reinterpret_cast<const uint4 *>(src + (size_t)yy * W));
+        if (in_img) v = __ldg(reinterpret_cast<const uint4 *>(src + off));
         return v;
     };
-    auto unpack = [&](const uint4 &v, uint32_t (&B)[8]) {   // bytes -> zero-interleaved pairs (= f16x2 denormals)
-        B[0] = __byte_perm(v.x, 0, 0x4140); B[1] = __byte_perm(v.x, 0, 0x4342);
-        B[2] = __byte_perm(v.y, 0, 0x4140); B[3] = __byte_perm(v.y, 0, 0x4342);
-        B[4] = __byte_perm(v.z, 0, 0x4140); B[5] = __byte_perm(v.z, 0, 0x4342);
-        B[6] = __byte_perm(v.w, 0, 0x4140); B[7] = __byte_perm(v.w, 0, 0x4342);
+    auto unpack = [&](const uint4 &v, uint32_t (&b)[8]) {   // bytes -> zero-interleaved pairs (= f16x2 denormals)
+        b[0] = __byte_perm(v.x, 0, 0x4140); b[1] = __byte_perm(v.x, 0, 0x4342);
+        b[2] = __byte_perm(v.y, 0, 0x4140); b[3] = __byte_perm(v.y, 0, 0x4342);
+        b[4] = __byte_perm(v.z, 0, 0x4140); b[5] = __byte_perm(v.z, 0, 0x4342);
+        b[6] = __byte_perm(v.w, 0, 0x4140); b[7] = __byte_perm(v.w, 0, 0x4342);
     };
-    unpack(load_raw(q0 - 2), B0);
-    unpack(load_raw(q0 - 1), B1);
+    unpack(load_raw(q0 - 2), Bs[0]);
+    unpack(load_raw(q0 - 1), Bs[1]);
+#pragma unroll
+    for (int j = 0; j < 8; j++) Ts[1][j] = h2add(Bs[0][j], Bs[1][j]);       // T(q0-2)
     uint4 vnext = load_raw(q0);                         // row c+1 of the first step
+    uint32_t out_idx = (uint32_t)q0 * WW + word;        // plane word of row n
+    uint32_t cand_prev = 0;                             // candidates of row c-1
+    int sa = 0, sb = K2A_RS, sc = 2 * K2A_RS;           // ring slots of rows c-2, c-1, c
 
-    for (int c = q0 - 1; c <= q1; c++) {               // c = row whose gradient is formed this step
-        uint32_t B2[8];
-        unpack(vnext, B2);
+    auto step = [&](auto slot, int c) {                 // c = row whose gradient is formed this step
+        constexpr int k = decltype(slot)::value, o = k ^ 1;
+        unpack(vnext, Bs[k]);                            // row c+1
         if (c < q1) vnext = load_raw(c + 2);             // prefetch the next step's row behind the arithmetic
-        uint32_t M2[8], l2 = 0, r2 = 0, cand2 = 0, strong2 = 0, cls2 = 0;
-        const bool row_ok = c >= 0 && c < H;            // the magnitude plane has a zero border
+        // the magnitude plane has a zero border: rows outside the frame and lanes outside the image give M = 0
+        const uint32_t absm = (c >= 0 && c < H) ? lane_mask : 0u;
+        uint32_t cand_new;
         {
             uint32_t Sc[8], Dc[8];
 #pragma unroll
             for (int j = 0; j < 8; j++) {
-                Sc[j] = h2fma2(B1[j], h2add(B0[j], B2[j]));      // column [1 2 1]
-                Dc[j] = h2sub(B2[j], B0[j]);                      // column [-1 0 1]
+                Ts[k][j] = h2add(Bs[k][j], Bs[o][j]);            // T(c) = B(c+1) + B(c)
+                Sc[j] = h2add(Ts[k][j], Ts[o][j]);               // column [1 2 1]
+                Dc[j] = h2sub(Ts[k][j], Ts[o][j]);               // column [-1 0 1]
             }
             uint32_t SL = __shfl_up_sync(0xffffffffu, Sc[7], 1), SR = __shfl_down_sync(0xffffffffu, Sc[0], 1);
             uint32_t DL = __shfl_up_sync(0xffffffffu, Dc[7], 1), DR = __shfl_down_sync(0xffffffffu, Dc[0], 1);
@@ -225,43 +175,69 @@ __device__ void canny_rows(int H, int W, int WW, const uint8_t *blur_f, int stri
                 Do[j] = __byte_perm(Dc[j - 1], Dc[j], 0x5432);
             }
             So[8] = __byte_perm(Sc[7], SR, 0x5432); Do[8] = __byte_perm(Dc[7], DR, 0x5432);
-            uint32_t dx[8], dy[8], mx = 0;
+            uint32_t dx[8], dy[8], Mw[8], acc = 0;
 #pragma unroll
             for (int j = 0; j < 8; j++) {
                 dx[j] = h2sub(So[j + 1], So[j]);
                 dy[j] = h2fma2(Dc[j], h2add(Do[j], Do[j + 1]));
-                M2[j] = h2add(dx[j] & 0x7FFF7FFFu, dy[j] & 0x7FFF7FFFu);
-                if (!(row_ok && in_img)) M2[j] = 0;
-                mx = h2max(mx, M2[j]);
+                Mw[j] = h2add(dx[j] & absm, dy[j] & absm);
+                const uint32_t gt = __hgt2_mask(*reinterpret_cast<const __half2 *>(&Mw[j]),
+                                                *reinterpret_cast<const __half2 *>(&low2));      // 0xFFFF per half: M > low
+                acc |= gt & ((1u << (2 * j)) | (1u << (2 * j + 17)));
             }
-            l2 = __shfl_up_sync(0xffffffffu, M2[7], 1);
-            r2 = __shfl_down_sync(0xffffffffu, M2[0], 1);
-            if (left_edge) l2 = 0;
-            if (right_edge) r2 = 0;
-            if ((int)max(mx & 0xFFFFu, mx >> 16) > low) {       // sparse: only lanes with a candidate
-                auto f = [&]<int P>() { classify_px<P>(M2, dx, dy, low, high, cand2, strong2, cls2); };
-                ForPx<15>::run(f);
-            }
+            cand_new = (acc | (acc >> 16)) & own_mask;
+            uint4 *mrow = reinterpret_cast<uint4 *>(Mring + sc + xb);
+            mrow[0] = make_uint4(Mw[0], Mw[1], Mw[2], Mw[3]); mrow[1] = make_uint4(Mw[4], Mw[5], Mw[6], Mw[7]);
+            uint4 *xrow = reinterpret_cast<uint4 *>(DXr + (c & 1) * 512 + xb);
+            xrow[0] = make_uint4(dx[0], dx[1], dx[2], dx[3]); xrow[1] = make_uint4(dx[4], dx[5], dx[6], dx[7]);
+            uint4 *yrow = reinterpret_cast<uint4 *>(DYr + (c & 1) * 512 + xb);
+            yrow[0] = make_uint4(dy[0], dy[1], dy[2], dy[3]); yrow[1] = make_uint4(dy[4], dy[5], dy[6], dy[7]);
         }
-        if (c >= q0 + 1) {                                       // NMS of row n = c-1 (rows n-1, n, n+1 in M0, M1, M2)
+        __syncwarp();                                            // row c of the ring is visible to every lane
+        if (c >= q0 + 1) {                                       // NMS of row n = c-1 (rows n-1, n, n+1 in slots sa, sb, sc)
             const int n = c - 1;
-            uint32_t keep = 0;
-            if (cand1) {
-                auto f = [&]<int P>() { nms_px<P>(M0, M1, M2, l0, r0, l1, r1, l2, r2, cand1, cls1, keep); };
-                ForPx<15>::run(f);
+            const uint16_t *Ma = Mring + sa, *Mb = Mring + sb, *Mc = Mring + sc;
+            const uint16_t *dxp = DXr + (n & 1) * 512, *dyp = DYr + (n & 1) * 512;
+            uint32_t keep = 0, strong = 0, rem = cand_prev;
+            while (rem) {
+                const int p = __ffs(rem) - 1;
+                rem &= rem - 1;
+                const uint32_t x = xb + p;
+                const int m = Mb[x];
+                const uint32_t xr = dxp[x], yr = dyp[x];
+                const int a = (int)(xr & 0x7FFFu), b = (int)(yr & 0x7FFFu);
+                const int tg22x = a * 13573, ay = b << 15;
+                const uint16_t *p1, *p2;
+                int ge;                                          // second comparison is >= for the axis-aligned sectors
+                if (ay < tg22x) { p1 = Mb + x - 1; p2 = Mb + x + 1; ge = 1; }                     // horizontal gradient
+                else if (ay > tg22x + (a << 16)) { p1 = Ma + x; p2 = Mc + x; ge = 1; }              // vertical
+                else {                                           // diagonal: along (+1,+1) when the signs agree
+                    const int d = ((xr ^ yr) & 0x8000u) ? 1 : -1;
+                    p1 = Ma + x + d; p2 = Mc + x - d; ge = 0;
+                }
+                const int n1 = *p1, n2 = *p2;
+                if (m > n1 && m + ge > n2) {
+                    keep |= 1u << p;
+                    if (m > high) strong |= 1u << p;
+                }
             }
-            const uint32_t v = keep | ((keep & strong1) << 16);
-            const uint32_t o = __shfl_down_sync(0xffffffffu, v, 1);
+            const uint32_t v = keep | (strong << 16);
+            const uint32_t ov = __shfl_down_sync(0xffffffffu, v, 1);
             if (writer) {
-                const int lr = n - row0;
-                Cw[(size_t)lr * WW + word] = (v & 0xFFFFu) | (o << 16);
-                Sw[(size_t)lr * WW + word] = (v >> 16) | (o & 0xFFFF0000u);
+                Cw[out_idx] = (v & 0xFFFFu) | (ov << 16);
+                Sw[out_idx] = (v >> 16) | (ov & 0xFFFF0000u);
             }
+            out_idx += WW;
         }
-#pragma unroll
-        for (int j = 0; j < 8; j++) { B0[j] = B1[j]; B1[j] = B2[j]; M0[j] = M1[j]; M1[j] = M2[j]; }
-        l0 = l1; r0 = r1; l1 = l2; r1 = r2;
-        cand1 = cand2; strong1 = strong2; cls1 = cls2;
+        __syncwarp();                                            // all reads of slot sa done before it is rewritten
+        cand_prev = cand_new;
+        const int t = sa; sa = sb; sb = sc; sc = t;
+    };
+    for (int c = q0 - 1;;) {
+        step(std::integral_constant<int, 0>{}, c);
+        if (++c > q1) break;
+        step(std::integral_constant<int, 1>{}, c);
+        if (++c > q1) break;
     }
 }
 
@@ -278,6 +254,7 @@ __global__ void __launch_bounds__(K2A_WARPS * 32, 5) k2a_sobel_nms(const uint8_t
                                                                uint32_t *__restrict__ c_bits, uint32_t *__restrict__ s_bits,
                                                                int *__restrict__ task_counter, int n_frames, int H, int W)
 {
+    __shared__ __align__(16) uint16_t k2a_sm[K2A_WARPS][K2A_WSM];
     const int lane = threadIdx.x & 31;
     const int WW = (W + 31) / 32;
     const int n_strips = (W + STRIP_OUT - 1) / STRIP_OUT;
@@ -294,8 +271,8 @@ __global__ void __launch_bounds__(K2A_WARPS * 32, 5) k2a_sobel_nms(const uint8_t
         if (low > high) { int t = low; low = high; high = t; }
         if (band == 0 && strip == 0 && lane == 0) thr[f] = make_int4(m2, low, high, 0);
         const int q0 = band * K2A_BAND, q1 = min(q0 + K2A_BAND, H);
-        canny_rows(H, W, WW, blur + (size_t)f * H * W, strip, q0, q1, 0, c_bits + (size_t)f * H * WW,
-                   s_bits + (size_t)f * H * WW, lane, low, high);
+        canny_rows(H, W, WW, blur + (size_t)f * H * W, strip, q0, q1, c_bits + (size_t)f * H * WW,
+                   s_bits + (size_t)f * H * WW, lane, low, high, k2a_sm[threadIdx.x >> 5]);
     }
 }
 
