@@ -18,6 +18,7 @@
 //            a cluster barrier until no band saw a change.
 //   phase 3  edge bit-plane, edge count, ROI-masked bit-plane (the PPHT mask) and the row-major point
 //            list (offsets by per-row popcounts, band bases exchanged over DSMEM).
+#include <algorithm>
 #include <cooperative_groups.h>
 #include <cuda_fp16.h>
 #include <stdio.h>
@@ -246,31 +247,38 @@ __device__ __forceinline__ void canny_rows(int H, int W, int WW, const uint8_t *
 // Warps pull (frame, band, strip) tasks from a global counter and write the candidate plane C and the
 // strong plane S (32 px per word) to global memory; perfectly load-balanced, no barriers at all.
 constexpr int K2A_WARPS = 4;
-constexpr int K2A_BAND = 64;
 
-__global__ void __launch_bounds__(K2A_WARPS * 32, 5) k2a_sobel_nms(const uint8_t *__restrict__ blur, const uint32_t *__restrict__ hist,
+template <int MINB>
+__global__ void __launch_bounds__(K2A_WARPS * 32, MINB) k2a_sobel_nms(const uint8_t *__restrict__ blur, const uint32_t *__restrict__ hist,
                                                                const uint8_t *__restrict__ lut_low,
                                                                const uint8_t *__restrict__ lut_high, int4 *__restrict__ thr,
                                                                uint32_t *__restrict__ c_bits, uint32_t *__restrict__ s_bits,
-                                                               int *__restrict__ task_counter, int n_frames, int H, int W)
+                                                               int *__restrict__ task_counter, int n_frames, int H, int W,
+                                                               int band_rows, int tail_frames, int tail_rows)
 {
     __shared__ __align__(16) uint16_t k2a_sm[K2A_WARPS][K2A_WSM];
     const int lane = threadIdx.x & 31;
     const int WW = (W + 31) / 32;
     const int n_strips = (W + STRIP_OUT - 1) / STRIP_OUT;
-    const int n_bands = (H + K2A_BAND - 1) / K2A_BAND;
-    const int n_tasks = n_frames * n_bands * n_strips;
+    // tasks in hand-out order: the first n_frames - tail_frames frames in bands of band_rows rows, the rest in thinner
+    // bands so the end-of-kernel tail is short (same scheme as K1)
+    const int n_bands = (H + band_rows - 1) / band_rows, n_bands_t = (H + tail_rows - 1) / tail_rows;
+    const int n_main = (n_frames - tail_frames) * n_bands * n_strips;
+    const int n_tasks = n_main + tail_frames * n_bands_t * n_strips;
     for (;;) {
         int task = 0;
         if (lane == 0) task = atomicAdd(task_counter, 1);
         task = __shfl_sync(0xffffffffu, task, 0);
         if (task >= n_tasks) break;
-        const int strip = task % n_strips, band = (task / n_strips) % n_bands, f = task / (n_strips * n_bands);
+        const bool tail = task >= n_main;
+        const int tt = tail ? task - n_main : task, nb = tail ? n_bands_t : n_bands, br = tail ? tail_rows : band_rows;
+        const int strip = tt % n_strips, band = (tt / n_strips) % nb;
+        const int f = tt / (n_strips * nb) + (tail ? n_frames - tail_frames : 0);
         const int m2 = median_x2_warp(hist + f * 256, (long long)H * W, lane);
         int low = lut_low[m2], high = lut_high[m2];
         if (low > high) { int t = low; low = high; high = t; }
         if (band == 0 && strip == 0 && lane == 0) thr[f] = make_int4(m2, low, high, 0);
-        const int q0 = band * K2A_BAND, q1 = min(q0 + K2A_BAND, H);
+        const int q0 = band * br, q1 = min(q0 + br, H);
         canny_rows(H, W, WW, blur + (size_t)f * H * W, strip, q0, q1, c_bits + (size_t)f * H * WW,
                    s_bits + (size_t)f * H * WW, lane, low, high, k2a_sm[threadIdx.x >> 5]);
     }
@@ -584,7 +592,26 @@ bool launch_canny_cluster(const uint8_t *blur, const uint32_t *hist, const uint8
         configured = true;
     }
     cudaMemsetAsync(task_counter, 0, sizeof(int), st);
-    k2a_sobel_nms<<<sms * 5, K2A_WARPS * 32, 0, st>>>(blur, hist, lut_low, lut_high, thr, c_bits, s_bits, task_counter, n, H, W);
+    {
+        static const int band_env = getenv("LANE_K2A_BAND") ? atoi(getenv("LANE_K2A_BAND")) : 0;
+        static const int tail_env = getenv("LANE_K2A_TAIL") ? atoi(getenv("LANE_K2A_TAIL")) : -1;
+        static const int minb = getenv("LANE_K2A_MINB") ? atoi(getenv("LANE_K2A_MINB")) : 6;
+        const int n_strips = (W + STRIP_OUT - 1) / STRIP_OUT, warps = sms * minb * K2A_WARPS;
+        int band_rows = band_env > 0 ? band_env : 64;
+        if (!band_env) {        // small batches: at least two tasks per resident warp, bands no thinner than 12 rows
+            const long rows_per_warp = ((long)n * H * n_strips + 2 * warps - 1) / (2 * warps);
+            band_rows = (int)std::max(12L, std::min((long)band_rows, rows_per_warp));
+        }
+        int tail_frames = tail_env >= 0 ? std::min(tail_env, n) : (n >= 16 ? n / 16 : 0);
+        const int tail_rows = std::max(12, band_rows / 3);
+        if (tail_rows >= band_rows) tail_frames = 0;
+        if (minb == 6)
+            k2a_sobel_nms<6><<<sms * 6, K2A_WARPS * 32, 0, st>>>(blur, hist, lut_low, lut_high, thr, c_bits, s_bits, task_counter,
+                                                                 n, H, W, band_rows, tail_frames, tail_rows);
+        else
+            k2a_sobel_nms<5><<<sms * 5, K2A_WARPS * 32, 0, st>>>(blur, hist, lut_low, lut_high, thr, c_bits, s_bits, task_counter,
+                                                                 n, H, W, band_rows, tail_frames, tail_rows);
+    }
     K2Args A;
     A.c_bits = c_bits; A.s_bits = s_bits; A.roi_bits = roi_bits;
     A.n_edges = n_edges; A.rounds = rounds; A.n_points = n_points; A.points = points;
