@@ -64,12 +64,6 @@ __device__ __forceinline__ uint32_t h2fma2(uint32_t a, uint32_t b)   // 2*a + b
     asm("fma.rn.f16x2 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(0x40004000u), "r"(b));
     return d;
 }
-__device__ __forceinline__ uint32_t h2max(uint32_t a, uint32_t b)
-{
-    uint32_t d;
-    asm("max.f16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b));
-    return d;
-}
 
 // median of the blurred plane (x2) from its histogram; warp-collective
 __device__ int median_x2_warp(const uint32_t *h, long long P, int lane)
@@ -293,7 +287,10 @@ __device__ __forceinline__ uint32_t flood_word(uint32_t n, uint32_t c)
     return __brev(dn);
 }
 
-__device__ __forceinline__ bool visit(const uint32_t *C, uint32_t *S, int r, int w, int WW)
+// One hysteresis step on word (r, w) of the band: promote the weak pixels of the word that touch a strong pixel
+// of the 3x3 word neighbourhood, then flood along the runs inside the word.  On a change the eight neighbouring
+// words are flagged in the dirty map D, which is what later passes look at instead of re-checking every word.
+__device__ __forceinline__ bool visit(const uint32_t *C, uint32_t *S, uint8_t *D, int Rv, int r, int w, int WW)
 {
     const uint32_t c = C[r * WW + w];
     uint32_t *sp = S + (r + 1) * WW + w;
@@ -307,14 +304,19 @@ __device__ __forceinline__ bool visit(const uint32_t *C, uint32_t *S, int r, int
     uint32_t n = s | (c & dil);
     if (n == s) return false;
     *sp = flood_word(n, c);
+    {
+        const int w0 = max(w - 1, 0), w1 = min(w + 1, WW - 1);
+        for (int rr2 = max(r - 1, 0); rr2 <= min(r + 1, Rv - 1); rr2++)
+            for (int ww = w0; ww <= w1; ww++) D[rr2 * WW + ww] = 1;
+    }
     return true;
 }
 
-__global__ void __launch_bounds__(K2T) k2_canny_cluster(K2Args A)
+__global__ void __launch_bounds__(K2T, 3) k2_canny_cluster(K2Args A)
 {
-    extern __shared__ uint32_t smem[];
+    extern __shared__ __align__(128) uint32_t smem[];
 #ifdef LANE_K2_PROF
-    long long t0 = clock64(), tL = 0, tC0 = 0, tX = 0, tP3 = 0, tA = 0, tB = 0, tCc = 0, tD = 0, tmark = t0;
+    int npass = 0; long long tPm = 0; long long t0 = clock64(), tL = 0, tC0 = 0, tX = 0, tP3 = 0, tA = 0, tB = 0, tCc = 0, tD = 0, tmark = t0;
 #define K2TICK(acc) do { long long n_ = clock64(); acc += n_ - tmark; tmark = n_; } while (0)
 #else
 #define K2TICK(acc) do { } while (0)
@@ -328,15 +330,37 @@ __global__ void __launch_bounds__(K2T) k2_canny_cluster(K2Args A)
     uint32_t *C = smem;                         // [R][WW]
     uint32_t *S = smem + (size_t)R * WW;        // [R+2][WW], row 0 / Rv+1 = neighbour bands
     int *rowoff = reinterpret_cast<int *>(S + (size_t)(R + 2) * WW);   // [R+1]
+    uint8_t *D = reinterpret_cast<uint8_t *>(rowoff + R + 1);          // [R][WW] dirty flags of the hysteresis passes
     __shared__ int s_flag, s_total, s_base, s_red[K2T / 32];
+    __shared__ __align__(8) unsigned long long s_bar;
 
-    // ---- phase 1 ran in k2a_sobel_nms: load this band's candidate / strong planes
+    // ---- phase 1 ran in k2a_sobel_nms: load this band's candidate / strong planes.  A band is one contiguous
+    // run of Rv*WW words in each plane, so two bulk copies (TMA, completion on an mbarrier) bring it in.
     {
         const uint32_t *cg = A.c_bits + ((size_t)f * H + b0) * WW, *sg = A.s_bits + ((size_t)f * H + b0) * WW;
-        for (int i = tid; i < Rv * WW; i += K2T) { C[i] = cg[i]; S[WW + i] = sg[i]; }
+        const bool bulk = (WW % 4 == 0) && Rv > 0;
+        if (bulk) {
+            const uint32_t bar = smem_u32(&s_bar);
+            if (tid == 0) {
+                mbar_init(bar, 1);
+                asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+            }
+            __syncthreads();
+            if (tid == 0) {
+                const uint32_t bytes = (uint32_t)Rv * WW * 4u;
+                mbar_expect_tx(bar, 2 * bytes);
+                bulk_g2s(smem_u32(C), cg, bytes, bar);
+                bulk_g2s(smem_u32(S + WW), sg, bytes, bar);
+            }
+        } else {
+            for (int i = tid; i < Rv * WW; i += K2T) { C[i] = cg[i]; S[WW + i] = sg[i]; }
+        }
         for (int i = tid; i < WW; i += K2T) { S[i] = 0; S[(size_t)(Rv + 1) * WW + i] = 0; }
+        for (int i = tid; i < (Rv * WW + 3) / 4; i += K2T) reinterpret_cast<uint32_t *>(D)[i] = 0;
+        if (bulk) mbar_wait(smem_u32(&s_bar), 0);
     }
     __syncthreads();
+    K2TICK(tL);
 
     // ---- phase 2: hysteresis
     int rounds = 0;
@@ -351,15 +375,15 @@ __global__ void __launch_bounds__(K2T) k2_canny_cluster(K2Args A)
         // through the neighbouring words of that row, so near-horizontal chains do not need one pass per word.
         // Races between threads are benign: S only grows and every update is a valid promotion.
         auto visit3 = [&](int r, int w) {                 // the word and its two neighbours in the row
-            bool c = visit(C, S, r, w, WW);
-            if (w > 0) c |= visit(C, S, r, w - 1, WW);
-            if (w + 1 < WW) c |= visit(C, S, r, w + 1, WW);
+            bool c = visit(C, S, D, Rv, r, w, WW);
+            if (w > 0) c |= visit(C, S, D, Rv, r, w - 1, WW);
+            if (w + 1 < WW) c |= visit(C, S, D, Rv, r, w + 1, WW);
             return c;
         };
         auto visit_chase = [&](int r, int w) {            // a promotion is followed along its chain right away:
-            if (!visit(C, S, r, w, WW)) return false;
-            for (int ww = w + 1; ww < WW && visit(C, S, r, ww, WW); ww++) {}      // sideways in the row,
-            for (int ww = w - 1; ww >= 0 && visit(C, S, r, ww, WW); ww--) {}
+            if (!visit(C, S, D, Rv, r, w, WW)) return false;
+            for (int ww = w + 1; ww < WW && visit(C, S, D, Rv, r, ww, WW); ww++) {}      // sideways in the row,
+            for (int ww = w - 1; ww >= 0 && visit(C, S, D, Rv, r, ww, WW); ww--) {}
             for (int rr = r + 1; rr < Rv && visit3(rr, w); rr++) {}                // down and up the band (also past
             for (int rr = r - 1; rr >= 0 && visit3(rr, w); rr--) {}                // this thread's own run of rows)
             return true;
@@ -373,34 +397,38 @@ __global__ void __launch_bounds__(K2T) k2_canny_cluster(K2Args A)
         uint32_t pr[4] = {0, 0, 0, 0};
         if (mine) {
 #pragma unroll
-            for (int j = 0; j < 4; j++)
-                for (int b = 0; b < 32; b++) {
-                    const int r = my_ra + 32 * j + b;
-                    if (r < my_rb && (C[r * WW + my_w] & ~S[(r + 1) * WW + my_w])) pr[j] |= 1u << b;
-                }
+            for (int j = 0; j < 4; j++) {
+                const int base = my_ra + 32 * j, nb = min(my_rb - base, 32);
+                uint32_t m = 0;
+#pragma unroll 4
+                for (int b = 0; b < nb; b++)
+                    if (C[(base + b) * WW + my_w] & ~S[(base + b + 1) * WW + my_w]) m |= 1u << b;
+                pr[j] = m;
+            }
         }
-        auto converge = [&]() {
+        K2TICK(tPm);
+        // full = true: every pending row is checked once (top to bottom).  Afterwards only words flagged dirty by a
+        // promotion next to them (or by a new boundary row) are looked at, until a pass finds nothing to do.
+        auto converge = [&](bool full) {
             bool any_change = false;
             for (;;) {
+#ifdef LANE_K2_PROF
+                npass++;
+#endif
                 bool ch = false;
                 if (one_item) {
                     if (mine) {
 #pragma unroll
-                        for (int j = 0; j < 4; j++) {                 // downwards
+                        for (int j = 0; j < 4; j++) {
                             uint32_t m = pr[j];
                             while (m) {
                                 const int b = __ffs(m) - 1, r = my_ra + 32 * j + b;
                                 m &= m - 1;
-                                ch |= visit_chase(r, my_w);
-                                if (!(C[r * WW + my_w] & ~S[(r + 1) * WW + my_w])) pr[j] &= ~(1u << b);
-                            }
-                        }
-#pragma unroll
-                        for (int j = 3; j >= 0; j--) {                // upwards
-                            uint32_t m = pr[j];
-                            while (m) {
-                                const int b = 31 - __clz(m), r = my_ra + 32 * j + b;
-                                m &= ~(1u << b);
+                                uint8_t *d = D + r * WW + my_w;
+                                if (!full) {
+                                    if (!*d) continue;
+                                }
+                                *d = 0;
                                 ch |= visit_chase(r, my_w);
                                 if (!(C[r * WW + my_w] & ~S[(r + 1) * WW + my_w])) pr[j] &= ~(1u << b);
                             }
@@ -410,16 +438,21 @@ __global__ void __launch_bounds__(K2T) k2_canny_cluster(K2Args A)
                     for (int item = tid; item < WW * nseg; item += K2T) {
                         const int w = item % WW, seg = item / WW;
                         const int ra = seg * seg_rows, rb = min(ra + seg_rows, Rv);
-                        for (int r = ra; r < rb; r++) ch |= visit_chase(r, w);
-                        for (int r = rb - 2; r >= ra; r--) ch |= visit_chase(r, w);
+                        for (int r = ra; r < rb; r++) {
+                            uint8_t *d = D + r * WW + w;
+                            if (!full && !*d) continue;
+                            *d = 0;
+                            ch |= visit_chase(r, w);
+                        }
                     }
                 }
+                full = false;
                 if (!__syncthreads_or(ch)) break;
                 any_change = true;
             }
             return any_change;
         };
-        converge();
+        converge(true);
         K2TICK(tC0);
         rounds = 1;
         // Bands then trade boundary rows.  A round ends the loop when NO band promoted anything after seeing its
@@ -430,9 +463,10 @@ __global__ void __launch_bounds__(K2T) k2_canny_cluster(K2Args A)
             for (int w = tid; w < WW; w += K2T) {
                 if (S_up) S[w] = S_up[(size_t)R * WW + w];
                 if (S_dn && Rv > 0) S[(size_t)(Rv + 1) * WW + w] = S_dn[WW + w];
+                if (Rv > 0) { D[w] = 1; D[(Rv - 1) * WW + w] = 1; }     // only the boundary rows can react to the new halo rows
             }
             __syncthreads();
-            const bool changed = converge();
+            const bool changed = converge(false);
             if (tid == 0) s_flag = changed;
             cluster.sync();
             int any = 0;
@@ -452,17 +486,29 @@ __global__ void __launch_bounds__(K2T) k2_canny_cluster(K2Args A)
     const uint32_t *roi = A.roi_bits;
     uint32_t *Mk = C;                                     // [Rv][WW] masked edges of this band
     int cnt = 0;
-    for (int i = tid; i < Rv * WW; i += K2T) {
-        const uint32_t sv = S[WW + i];
-        const int y = b0 + i / WW;
-        A.edge_bits[((size_t)f * H + b0) * WW + i] = sv;
-        cnt += __popc(sv);
-        uint32_t m = 0;
-        if (y >= g.by0 && y < g.by1) {
-            m = sv & roi[(size_t)b0 * WW + i];
-            A.pmask_bits[((size_t)f * g.bh + (y - g.by0)) * WW + (i - (i / WW) * WW)] = m;
+    {
+        uint32_t *eb = A.edge_bits + ((size_t)f * H + b0) * WW;
+        uint32_t *pm = A.pmask_bits + (size_t)f * g.bh * WW;
+        const uint32_t *rb = roi + (size_t)b0 * WW;
+        const int cols = min(WW, K2T), rstep = max(1, K2T / WW);
+        const int w0 = tid % cols, r0 = tid / cols;
+        if (r0 < rstep) {
+            for (int w = w0; w < WW; w += cols) {
+#pragma unroll 4
+                for (int r = r0; r < Rv; r += rstep) {
+                    const int i = r * WW + w, y = b0 + r;
+                    const uint32_t sv = S[WW + i];
+                    eb[i] = sv;
+                    cnt += __popc(sv);
+                    uint32_t m = 0;
+                    if (y >= g.by0 && y < g.by1) {
+                        m = sv & rb[i];
+                        pm[(size_t)(y - g.by0) * WW + w] = m;
+                    }
+                    Mk[i] = m;
+                }
+            }
         }
-        Mk[i] = m;
     }
     for (int o = 16; o; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
     if (lane == 0) s_red[wid] = cnt;
@@ -527,7 +573,7 @@ __global__ void __launch_bounds__(K2T) k2_canny_cluster(K2Args A)
     if (G > 1) cluster.sync();                            // keep s_total alive until every band has read it
 #ifdef LANE_K2_PROF
     K2TICK(tP3);
-    if (tid == 0 && f == 0) printf("k2b rank=%d total=%lld load=%lld converge0=%lld rounds(%d)=%lld p3: write=%lld counts=%lld csync=%lld points=%lld final=%lld\n", rank, clock64() - t0, tL, tC0, rounds, tX, tA, tB, tCc, tD, tP3);
+    if (tid == 0 && f == 0) printf("k2b rank=%d total=%lld load=%lld pmask=%lld passes=%d converge0=%lld rounds(%d)=%lld p3: write=%lld counts=%lld csync=%lld points=%lld final=%lld\n", rank, clock64() - t0, tL, tPm, npass, tC0, rounds, tX, tA, tB, tCc, tD, tP3);
 #endif
 }
 
@@ -577,7 +623,7 @@ bool launch_canny_cluster(const uint8_t *blur, const uint32_t *hist, const uint8
     int R = 0;
     for (;; G *= 2) {
         R = (H + G - 1) / G;
-        smem = sizeof(uint32_t) * ((size_t)R * WW + (size_t)(R + 2) * WW) + sizeof(int) * (R + 1);
+        smem = sizeof(uint32_t) * ((size_t)R * WW + (size_t)(R + 2) * WW) + sizeof(int) * (R + 1) + ((size_t)R * WW + 4);
         if (smem <= 200 * 1024 || G >= 16) break;
     }
     if (smem > 220 * 1024) return false;
