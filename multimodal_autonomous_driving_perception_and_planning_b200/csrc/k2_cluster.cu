@@ -290,26 +290,54 @@ __device__ __forceinline__ uint32_t flood_word(uint32_t n, uint32_t c)
 // One hysteresis step on word (r, w) of the band: promote the weak pixels of the word that touch a strong pixel
 // of the 3x3 word neighbourhood, then flood along the runs inside the word.  On a change the eight neighbouring
 // words are flagged in the dirty map D, which is what later passes look at instead of re-checking every word.
-__device__ __forceinline__ bool visit(const uint32_t *C, uint32_t *S, uint8_t *D, int Rv, int r, int w, int WW)
+__device__ __forceinline__ void mark_sides(volatile uint8_t *D, int Rv, int r, int w, int WW, uint32_t nb)
+{
+    // newly set bits reach a neighbouring word only from bit 0 / bit 31
+    const int ra = max(r - 1, 0), rb = min(r + 1, Rv - 1);
+    if ((nb & 1u) && w > 0)
+        for (int q = ra; q <= rb; q++) D[q * WW + w - 1] = 1;
+    if ((nb >> 31) && w < WW - 1)
+        for (int q = ra; q <= rb; q++) D[q * WW + w + 1] = 1;
+}
+
+// returns the bits newly set in word (r, w); 0 = nothing changed
+__device__ __forceinline__ uint32_t visit(const uint32_t *C, uint32_t *S, int r, int w, int WW)
 {
     const uint32_t c = C[r * WW + w];
     uint32_t *sp = S + (r + 1) * WW + w;
     const uint32_t s = *sp;
-    if ((c & ~s) == 0) return false;
+    if ((c & ~s) == 0) return 0;
     const uint32_t v = sp[-WW] | s | sp[WW];
     uint32_t l = 0, rr = 0;
     if (w > 0) l = sp[-WW - 1] | sp[-1] | sp[WW - 1];
     if (w < WW - 1) rr = sp[-WW + 1] | sp[1] | sp[WW + 1];
     const uint32_t dil = v | (v << 1) | (v >> 1) | (l >> 31) | (rr << 31);
     uint32_t n = s | (c & dil);
-    if (n == s) return false;
-    *sp = flood_word(n, c);
-    {
-        const int w0 = max(w - 1, 0), w1 = min(w + 1, WW - 1);
-        for (int rr2 = max(r - 1, 0); rr2 <= min(r + 1, Rv - 1); rr2++)
-            for (int ww = w0; ww <= w1; ww++) D[rr2 * WW + ww] = 1;
+    if (n == s) return 0;
+    n = flood_word(n, c);
+    return n & ~atomicOr(sp, n);        // atomic: a concurrent walker's bits in this word must not be lost
+}
+
+// Follow a promotion straight up or down its column word: only the pixels of the next row that touch the bits
+// just set can change, so a step is two loads, a dilation and an in-word flood.  Everything the walk does not
+// handle itself (the row behind it, the words to either side) is flagged dirty for the next pass.
+__device__ __forceinline__ void chase_column(const uint32_t *C, uint32_t *S, volatile uint8_t *D, int Rv, int r, int w, int WW,
+                                             uint32_t nb, int dir)
+{
+    for (;;) {
+        r += dir;
+        if (r < 0 || r >= Rv) return;
+        const uint32_t c = C[r * WW + w];
+        uint32_t *sp = S + (r + 1) * WW + w;
+        const uint32_t s = *sp;
+        const uint32_t t = c & ~s & (nb | (nb << 1) | (nb >> 1));
+        if (!t) return;
+        const uint32_t n = flood_word(s | t, c);
+        nb = n & ~atomicOr(sp, n);
+        if (!nb) return;                           // somebody else got here first and is following it
+        mark_sides(D, Rv, r, w, WW, nb);
+        D[(r - dir) * WW + w] = 1;                 // the row behind may hold pixels that touch only the new bits
     }
-    return true;
 }
 
 __global__ void __launch_bounds__(K2T, 3) k2_canny_cluster(K2Args A)
@@ -330,7 +358,7 @@ __global__ void __launch_bounds__(K2T, 3) k2_canny_cluster(K2Args A)
     uint32_t *C = smem;                         // [R][WW]
     uint32_t *S = smem + (size_t)R * WW;        // [R+2][WW], row 0 / Rv+1 = neighbour bands
     int *rowoff = reinterpret_cast<int *>(S + (size_t)(R + 2) * WW);   // [R+1]
-    uint8_t *D = reinterpret_cast<uint8_t *>(rowoff + R + 1);          // [R][WW] dirty flags of the hysteresis passes
+    volatile uint8_t *D = reinterpret_cast<volatile uint8_t *>(rowoff + R + 1);          // [R][WW] dirty flags of the hysteresis passes
     __shared__ int s_flag, s_total, s_base, s_red[K2T / 32];
     __shared__ __align__(8) unsigned long long s_bar;
 
@@ -356,7 +384,7 @@ __global__ void __launch_bounds__(K2T, 3) k2_canny_cluster(K2Args A)
             for (int i = tid; i < Rv * WW; i += K2T) { C[i] = cg[i]; S[WW + i] = sg[i]; }
         }
         for (int i = tid; i < WW; i += K2T) { S[i] = 0; S[(size_t)(Rv + 1) * WW + i] = 0; }
-        for (int i = tid; i < (Rv * WW + 3) / 4; i += K2T) reinterpret_cast<uint32_t *>(D)[i] = 0;
+        for (int i = tid; i < (Rv * WW + 3) / 4; i += K2T) reinterpret_cast<volatile uint32_t *>(D)[i] = 0;
         if (bulk) mbar_wait(smem_u32(&s_bar), 0);
     }
     __syncthreads();
@@ -373,19 +401,13 @@ __global__ void __launch_bounds__(K2T, 3) k2_canny_cluster(K2Args A)
         // One pass = column-serial sweeps: a thread walks its 32-px column word down and up a run of rows, so a chain
         // crosses the run vertically in one pass; whenever a word changes, the same thread chases the change sideways
         // through the neighbouring words of that row, so near-horizontal chains do not need one pass per word.
-        // Races between threads are benign: S only grows and every update is a valid promotion.
-        auto visit3 = [&](int r, int w) {                 // the word and its two neighbours in the row
-            bool c = visit(C, S, D, Rv, r, w, WW);
-            if (w > 0) c |= visit(C, S, D, Rv, r, w - 1, WW);
-            if (w + 1 < WW) c |= visit(C, S, D, Rv, r, w + 1, WW);
-            return c;
-        };
-        auto visit_chase = [&](int r, int w) {            // a promotion is followed along its chain right away:
-            if (!visit(C, S, D, Rv, r, w, WW)) return false;
-            for (int ww = w + 1; ww < WW && visit(C, S, D, Rv, r, ww, WW); ww++) {}      // sideways in the row,
-            for (int ww = w - 1; ww >= 0 && visit(C, S, D, Rv, r, ww, WW); ww--) {}
-            for (int rr = r + 1; rr < Rv && visit3(rr, w); rr++) {}                // down and up the band (also past
-            for (int rr = r - 1; rr >= 0 && visit3(rr, w); rr--) {}                // this thread's own run of rows)
+        // S only grows (atomicOr), every update is a valid promotion, and whoever sets a bit flags the words it can affect.
+        auto visit_chase = [&](int r, int w) {            // a promotion is followed along its column right away
+            const uint32_t nb = visit(C, S, r, w, WW);
+            if (!nb) return false;
+            mark_sides(D, Rv, r, w, WW, nb);
+            chase_column(C, S, D, Rv, r, w, WW, nb, +1);
+            chase_column(C, S, D, Rv, r, w, WW, nb, -1);
             return true;
         };
         // Only rows that still hold weak-but-not-strong pixels can change, and there are few of them: every thread keeps
@@ -424,7 +446,7 @@ __global__ void __launch_bounds__(K2T, 3) k2_canny_cluster(K2Args A)
                             while (m) {
                                 const int b = __ffs(m) - 1, r = my_ra + 32 * j + b;
                                 m &= m - 1;
-                                uint8_t *d = D + r * WW + my_w;
+                                volatile uint8_t *d = D + r * WW + my_w;
                                 if (!full) {
                                     if (!*d) continue;
                                 }
@@ -439,7 +461,7 @@ __global__ void __launch_bounds__(K2T, 3) k2_canny_cluster(K2Args A)
                         const int w = item % WW, seg = item / WW;
                         const int ra = seg * seg_rows, rb = min(ra + seg_rows, Rv);
                         for (int r = ra; r < rb; r++) {
-                            uint8_t *d = D + r * WW + w;
+                            volatile uint8_t *d = D + r * WW + w;
                             if (!full && !*d) continue;
                             *d = 0;
                             ch |= visit_chase(r, w);
