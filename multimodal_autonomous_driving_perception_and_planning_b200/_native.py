@@ -13,7 +13,8 @@ import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
-LIB_PATH = os.path.join(CSRC, "liblane_b200.so")
+# LANE_B200_LIB: an alternative build of the same library (A/B timing of kernel variants); never a CPU path
+LIB_PATH = os.environ.get("LANE_B200_LIB") or os.path.join(CSRC, "liblane_b200.so")
 
 NUM_POINTS = 50
 NUM_STAGES = 7

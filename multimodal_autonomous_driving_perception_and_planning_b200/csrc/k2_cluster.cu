@@ -315,28 +315,50 @@ __device__ __forceinline__ uint32_t visit(const uint32_t *C, uint32_t *S, int r,
     uint32_t n = s | (c & dil);
     if (n == s) return 0;
     n = flood_word(n, c);
-    return n & ~atomicOr(sp, n);        // atomic: a concurrent walker's bits in this word must not be lost
+    *sp = n;                            // plain store: only the thread that owns (r, w) ever writes this word
+    return n & ~s;
 }
 
-// Follow a promotion straight up or down its column word: only the pixels of the next row that touch the bits
-// just set can change, so a step is two loads, a dilation and an in-word flood.  Everything the walk does not
-// handle itself (the row behind it, the words to either side) is flagged dirty for the next pass.
-__device__ __forceinline__ void chase_column(const uint32_t *C, uint32_t *S, volatile uint8_t *D, int Rv, int r, int w, int WW,
-                                             uint32_t nb, int dir)
+__device__ __forceinline__ void mark_sides_cold(uint32_t dA, int Rv, int r, int w, int WW, uint32_t nb)
 {
+    // shared-memory byte address form of mark_sides (rare path of the column walk)
+    const int ra = max(r - 1, 0), rb = min(r + 1, Rv - 1);
+    const uint32_t one = 1;
+    if ((nb & 1u) && w > 0)
+        for (int q = ra; q <= rb; q++) asm volatile("st.shared.u8 [%0], %1;" ::"r"(dA + (q - r) * WW - 1), "r"(one) : "memory");
+    if ((nb >> 31) && w < WW - 1)
+        for (int q = ra; q <= rb; q++) asm volatile("st.shared.u8 [%0], %1;" ::"r"(dA + (q - r) * WW + 1), "r"(one) : "memory");
+}
+
+// Follow a promotion straight up or down its column word, inside the run of rows [ra, rb) this thread owns: only the
+// pixels of the next row that touch the bits just set can change, so a step is two loads, a dilation and an in-word
+// flood.  Every S word has exactly one writer (its owner), so plain stores suffice.  Everything the walk does not
+// handle itself -- the row behind it, the words to either side, the first row of the next owner -- is flagged dirty
+// for the next pass.  One thread walks alone here while the rest of the CTA waits, so the loop is written for a short
+// dependent-instruction chain: 32-bit shared addresses stepped by a constant, the side flags out of line.
+__device__ __forceinline__ void chase_column(uint32_t cA, uint32_t sA, uint32_t dA, int Rv, int ra, int rb, int r, int w,
+                                             int WW, uint32_t nb, int dir)
+{
+    const int wstep = dir * WW * 4, dstep = dir * WW;      // cA = &C[r][w], sA = &S[r+1][w], dA = &D[r][w]
+    const uint32_t one = 1;
     for (;;) {
         r += dir;
-        if (r < 0 || r >= Rv) return;
-        const uint32_t c = C[r * WW + w];
-        uint32_t *sp = S + (r + 1) * WW + w;
-        const uint32_t s = *sp;
-        const uint32_t t = c & ~s & (nb | (nb << 1) | (nb >> 1));
+        dA += dstep;
+        if (r < ra || r >= rb) {                            // leaving my rows: the next owner takes over
+            if (r >= 0 && r < Rv) asm volatile("st.shared.u8 [%0], %1;" ::"r"(dA), "r"(one) : "memory");
+            return;
+        }
+        cA += wstep; sA += wstep;
+        uint32_t c, sv;
+        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(c) : "r"(cA));
+        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(sv) : "r"(sA));
+        const uint32_t t = c & ~sv & (nb | (nb << 1) | (nb >> 1));
         if (!t) return;
-        const uint32_t n = flood_word(s | t, c);
-        nb = n & ~atomicOr(sp, n);
-        if (!nb) return;                           // somebody else got here first and is following it
-        mark_sides(D, Rv, r, w, WW, nb);
-        D[(r - dir) * WW + w] = 1;                 // the row behind may hold pixels that touch only the new bits
+        const uint32_t n = flood_word(sv | t, c);
+        asm volatile("st.shared.u32 [%0], %1;" ::"r"(sA), "r"(n) : "memory");
+        nb = n & ~sv;
+        asm volatile("st.shared.u8 [%0], %1;" ::"r"(dA - dstep), "r"(one) : "memory");   // the row behind
+        if (nb & 0x80000001u) mark_sides_cold(dA, Rv, r, w, WW, nb);
     }
 }
 
@@ -401,13 +423,15 @@ __global__ void __launch_bounds__(K2T, 3) k2_canny_cluster(K2Args A)
         // One pass = column-serial sweeps: a thread walks its 32-px column word down and up a run of rows, so a chain
         // crosses the run vertically in one pass; whenever a word changes, the same thread chases the change sideways
         // through the neighbouring words of that row, so near-horizontal chains do not need one pass per word.
-        // S only grows (atomicOr), every update is a valid promotion, and whoever sets a bit flags the words it can affect.
-        auto visit_chase = [&](int r, int w) {            // a promotion is followed along its column right away
+        // S only grows, every word has one writer, and whoever sets a bit flags the words it can affect.
+        auto visit_chase = [&](int r, int w, int ra, int rb) {   // a promotion is followed along its column right away
             const uint32_t nb = visit(C, S, r, w, WW);
             if (!nb) return false;
             mark_sides(D, Rv, r, w, WW, nb);
-            chase_column(C, S, D, Rv, r, w, WW, nb, +1);
-            chase_column(C, S, D, Rv, r, w, WW, nb, -1);
+            const uint32_t cA = smem_u32(C + r * WW + w), sA = smem_u32(S + (r + 1) * WW + w);
+            const uint32_t dA = smem_u32(const_cast<uint8_t *>(D) + r * WW + w);
+            chase_column(cA, sA, dA, Rv, ra, rb, r, w, WW, nb, +1);
+            chase_column(cA, sA, dA, Rv, ra, rb, r, w, WW, nb, -1);
             return true;
         };
         // Only rows that still hold weak-but-not-strong pixels can change, and there are few of them: every thread keeps
@@ -451,7 +475,7 @@ __global__ void __launch_bounds__(K2T, 3) k2_canny_cluster(K2Args A)
                                     if (!*d) continue;
                                 }
                                 *d = 0;
-                                ch |= visit_chase(r, my_w);
+                                ch |= visit_chase(r, my_w, my_ra, my_rb);
                                 if (!(C[r * WW + my_w] & ~S[(r + 1) * WW + my_w])) pr[j] &= ~(1u << b);
                             }
                         }
@@ -464,7 +488,7 @@ __global__ void __launch_bounds__(K2T, 3) k2_canny_cluster(K2Args A)
                             volatile uint8_t *d = D + r * WW + w;
                             if (!full && !*d) continue;
                             *d = 0;
-                            ch |= visit_chase(r, w);
+                            ch |= visit_chase(r, w, ra, rb);
                         }
                     }
                 }
@@ -509,9 +533,9 @@ __global__ void __launch_bounds__(K2T, 3) k2_canny_cluster(K2Args A)
     uint32_t *Mk = C;                                     // [Rv][WW] masked edges of this band
     int cnt = 0;
     {
-        uint32_t *eb = A.edge_bits + ((size_t)f * H + b0) * WW;
-        uint32_t *pm = A.pmask_bits + (size_t)f * g.bh * WW;
-        const uint32_t *rb = roi + (size_t)b0 * WW;
+        uint32_t *__restrict__ eb = A.edge_bits + ((size_t)f * H + b0) * WW;
+        uint32_t *__restrict__ pm = A.pmask_bits + (size_t)f * g.bh * WW;
+        const uint32_t *__restrict__ rb = roi + (size_t)b0 * WW;
         const int cols = min(WW, K2T), rstep = max(1, K2T / WW);
         const int w0 = tid % cols, r0 = tid / cols;
         if (r0 < rstep) {
@@ -522,11 +546,9 @@ __global__ void __launch_bounds__(K2T, 3) k2_canny_cluster(K2Args A)
                     const uint32_t sv = S[WW + i];
                     eb[i] = sv;
                     cnt += __popc(sv);
-                    uint32_t m = 0;
-                    if (y >= g.by0 && y < g.by1) {
-                        m = sv & rb[i];
-                        pm[(size_t)(y - g.by0) * WW + w] = m;
-                    }
+                    const bool in_roi = y >= g.by0 && y < g.by1;
+                    const uint32_t m = in_roi ? (sv & __ldg(rb + i)) : 0u;
+                    if (in_roi) pm[(size_t)(y - g.by0) * WW + w] = m;
                     Mk[i] = m;
                 }
             }
