@@ -315,7 +315,7 @@ __device__ __forceinline__ uint32_t visit(const uint32_t *C, uint32_t *S, int r,
     uint32_t n = s | (c & dil);
     if (n == s) return 0;
     n = flood_word(n, c);
-    *sp = n;                            // plain store: only the thread that owns (r, w) ever writes this word
+    atomicOr(sp, n);                    // result not awaited: bits somebody else set meanwhile only cause redundant flags
     return n & ~s;
 }
 
@@ -330,32 +330,27 @@ __device__ __forceinline__ void mark_sides_cold(uint32_t dA, int Rv, int r, int 
         for (int q = ra; q <= rb; q++) asm volatile("st.shared.u8 [%0], %1;" ::"r"(dA + (q - r) * WW + 1), "r"(one) : "memory");
 }
 
-// Follow a promotion straight up or down its column word, inside the run of rows [ra, rb) this thread owns: only the
-// pixels of the next row that touch the bits just set can change, so a step is two loads, a dilation and an in-word
-// flood.  Every S word has exactly one writer (its owner), so plain stores suffice.  Everything the walk does not
-// handle itself -- the row behind it, the words to either side, the first row of the next owner -- is flagged dirty
-// for the next pass.  One thread walks alone here while the rest of the CTA waits, so the loop is written for a short
-// dependent-instruction chain: 32-bit shared addresses stepped by a constant, the side flags out of line.
-__device__ __forceinline__ void chase_column(uint32_t cA, uint32_t sA, uint32_t dA, int Rv, int ra, int rb, int r, int w,
-                                             int WW, uint32_t nb, int dir)
+// Follow a promotion straight up or down its column word: only the pixels of the next row that touch the bits just
+// set can change, so a step is two loads, a dilation and an in-word flood.  Everything the walk does not handle itself
+// (the row behind it, the words to either side) is flagged dirty for the next pass.  Few threads walk while the rest
+// of the CTA waits, so the loop is written for a short dependent-instruction chain: 32-bit shared addresses stepped
+// by a constant, fire-and-forget atomic ORs (other walkers may be in the same word), the side flags out of the way.
+__device__ __forceinline__ void chase_column(uint32_t cA, uint32_t sA, uint32_t dA, int Rv, int r, int w, int WW,
+                                             uint32_t nb, int dir)
 {
     const int wstep = dir * WW * 4, dstep = dir * WW;      // cA = &C[r][w], sA = &S[r+1][w], dA = &D[r][w]
     const uint32_t one = 1;
     for (;;) {
         r += dir;
-        dA += dstep;
-        if (r < ra || r >= rb) {                            // leaving my rows: the next owner takes over
-            if (r >= 0 && r < Rv) asm volatile("st.shared.u8 [%0], %1;" ::"r"(dA), "r"(one) : "memory");
-            return;
-        }
-        cA += wstep; sA += wstep;
+        if ((unsigned)r >= (unsigned)Rv) return;
+        cA += wstep; sA += wstep; dA += dstep;
         uint32_t c, sv;
         asm volatile("ld.shared.u32 %0, [%1];" : "=r"(c) : "r"(cA));
         asm volatile("ld.shared.u32 %0, [%1];" : "=r"(sv) : "r"(sA));
         const uint32_t t = c & ~sv & (nb | (nb << 1) | (nb >> 1));
         if (!t) return;
         const uint32_t n = flood_word(sv | t, c);
-        asm volatile("st.shared.u32 [%0], %1;" ::"r"(sA), "r"(n) : "memory");
+        asm volatile("red.shared.or.b32 [%0], %1;" ::"r"(sA), "r"(n) : "memory");
         nb = n & ~sv;
         asm volatile("st.shared.u8 [%0], %1;" ::"r"(dA - dstep), "r"(one) : "memory");   // the row behind
         if (nb & 0x80000001u) mark_sides_cold(dA, Rv, r, w, WW, nb);
@@ -366,7 +361,7 @@ __global__ void __launch_bounds__(K2T, 3) k2_canny_cluster(K2Args A)
 {
     extern __shared__ __align__(128) uint32_t smem[];
 #ifdef LANE_K2_PROF
-    int npass = 0; long long tPm = 0; long long t0 = clock64(), tL = 0, tC0 = 0, tX = 0, tP3 = 0, tA = 0, tB = 0, tCc = 0, tD = 0, tmark = t0;
+    int npass = 0; long long tps[8] = {0, 0, 0, 0, 0, 0, 0, 0}; long long tPm = 0; long long t0 = clock64(), tL = 0, tC0 = 0, tX = 0, tP3 = 0, tA = 0, tB = 0, tCc = 0, tD = 0, tmark = t0;
 #define K2TICK(acc) do { long long n_ = clock64(); acc += n_ - tmark; tmark = n_; } while (0)
 #else
 #define K2TICK(acc) do { } while (0)
@@ -412,83 +407,52 @@ __global__ void __launch_bounds__(K2T, 3) k2_canny_cluster(K2Args A)
     __syncthreads();
     K2TICK(tL);
 
-    // ---- phase 2: hysteresis
+    // ---- phase 2: hysteresis.  Work items are single 32-px words.  The first pass looks at every word of the band
+    // (thread t takes words t, t+256, ... so the words of one column, where vertical chains sit, land on different
+    // threads); a promotion is followed up and down its column at once, and flags the words beside it in the dirty
+    // map.  Later passes only look at flagged words, until a pass changes nothing.  S only grows, all updates are
+    // atomic ORs, and whoever sets a bit flags every word that bit can affect, so the fixed point is the closure.
     int rounds = 0;
     {
-        const int nseg = max(1, K2T / WW);
-        const int seg_rows = (Rv + nseg - 1) / nseg;
         uint32_t *S_up = rank > 0 ? cluster.map_shared_rank(S, rank - 1) : nullptr;
         uint32_t *S_dn = rank < G - 1 ? cluster.map_shared_rank(S, rank + 1) : nullptr;
-        // sweeps until this band is stable; returns whether any pixel was promoted
-        // One pass = column-serial sweeps: a thread walks its 32-px column word down and up a run of rows, so a chain
-        // crosses the run vertically in one pass; whenever a word changes, the same thread chases the change sideways
-        // through the neighbouring words of that row, so near-horizontal chains do not need one pass per word.
-        // S only grows, every word has one writer, and whoever sets a bit flags the words it can affect.
-        auto visit_chase = [&](int r, int w, int ra, int rb) {   // a promotion is followed along its column right away
+        const int n_words = Rv * WW;
+        auto visit_chase = [&](int i) {                   // i = r * WW + w
+            const int r = i / WW, w = i - r * WW;
             const uint32_t nb = visit(C, S, r, w, WW);
             if (!nb) return false;
             mark_sides(D, Rv, r, w, WW, nb);
-            const uint32_t cA = smem_u32(C + r * WW + w), sA = smem_u32(S + (r + 1) * WW + w);
-            const uint32_t dA = smem_u32(const_cast<uint8_t *>(D) + r * WW + w);
-            chase_column(cA, sA, dA, Rv, ra, rb, r, w, WW, nb, +1);
-            chase_column(cA, sA, dA, Rv, ra, rb, r, w, WW, nb, -1);
+            const uint32_t cA = smem_u32(C + i), sA = smem_u32(S + WW + i);
+            const uint32_t dA = smem_u32(const_cast<uint8_t *>(D) + i);
+            chase_column(cA, sA, dA, Rv, r, w, WW, nb, +1);
+            chase_column(cA, sA, dA, Rv, r, w, WW, nb, -1);
             return true;
         };
-        // Only rows that still hold weak-but-not-strong pixels can change, and there are few of them: every thread keeps
-        // a bit mask of such rows in its column run (<= 128 rows) and sweeps just those, downwards then upwards.
-        const bool one_item = WW * nseg <= K2T && seg_rows <= 128;
-        const int my_w = tid % WW, my_seg = tid / WW;
-        const int my_ra = my_seg * seg_rows, my_rb = min(my_ra + seg_rows, Rv);
-        const bool mine = one_item && tid < WW * nseg && my_ra < my_rb;
-        uint32_t pr[4] = {0, 0, 0, 0};
-        if (mine) {
-#pragma unroll
-            for (int j = 0; j < 4; j++) {
-                const int base = my_ra + 32 * j, nb = min(my_rb - base, 32);
-                uint32_t m = 0;
-#pragma unroll 4
-                for (int b = 0; b < nb; b++)
-                    if (C[(base + b) * WW + my_w] & ~S[(base + b + 1) * WW + my_w]) m |= 1u << b;
-                pr[j] = m;
-            }
-        }
         K2TICK(tPm);
-        // full = true: every pending row is checked once (top to bottom).  Afterwards only words flagged dirty by a
-        // promotion next to them (or by a new boundary row) are looked at, until a pass finds nothing to do.
         auto converge = [&](bool full) {
             bool any_change = false;
             for (;;) {
 #ifdef LANE_K2_PROF
+                if (npass < 8) tps[npass] = clock64() - t0;
                 npass++;
 #endif
                 bool ch = false;
-                if (one_item) {
-                    if (mine) {
-#pragma unroll
-                        for (int j = 0; j < 4; j++) {
-                            uint32_t m = pr[j];
-                            while (m) {
-                                const int b = __ffs(m) - 1, r = my_ra + 32 * j + b;
-                                m &= m - 1;
-                                volatile uint8_t *d = D + r * WW + my_w;
-                                if (!full) {
-                                    if (!*d) continue;
-                                }
-                                *d = 0;
-                                ch |= visit_chase(r, my_w, my_ra, my_rb);
-                                if (!(C[r * WW + my_w] & ~S[(r + 1) * WW + my_w])) pr[j] &= ~(1u << b);
-                            }
+                if (full) {
+#pragma unroll 4
+                    for (int i = tid; i < n_words; i += K2T)
+                        if (C[i] & ~S[WW + i]) {
+                            D[i] = 0;
+                            ch |= visit_chase(i);
                         }
-                    }
                 } else {
-                    for (int item = tid; item < WW * nseg; item += K2T) {
-                        const int w = item % WW, seg = item / WW;
-                        const int ra = seg * seg_rows, rb = min(ra + seg_rows, Rv);
-                        for (int r = ra; r < rb; r++) {
-                            volatile uint8_t *d = D + r * WW + w;
-                            if (!full && !*d) continue;
-                            *d = 0;
-                            ch |= visit_chase(r, w, ra, rb);
+                    const volatile uint32_t *D4 = reinterpret_cast<const volatile uint32_t *>(D);
+                    for (int q = tid; q < (n_words + 3) / 4; q += K2T) {
+                        uint32_t fl = D4[q];
+                        while (fl) {                          // clear and visit exactly the flags that were seen set
+                            const int k = (__ffs(fl) - 1) >> 3, i = 4 * q + k;
+                            fl &= ~(0xFFu << (8 * k));
+                            D[i] = 0;
+                            if (i < n_words) ch |= visit_chase(i);
                         }
                     }
                 }
@@ -617,7 +581,7 @@ __global__ void __launch_bounds__(K2T, 3) k2_canny_cluster(K2Args A)
     if (G > 1) cluster.sync();                            // keep s_total alive until every band has read it
 #ifdef LANE_K2_PROF
     K2TICK(tP3);
-    if (tid == 0 && f == 0) printf("k2b rank=%d total=%lld load=%lld pmask=%lld passes=%d converge0=%lld rounds(%d)=%lld p3: write=%lld counts=%lld csync=%lld points=%lld final=%lld\n", rank, clock64() - t0, tL, tPm, npass, tC0, rounds, tX, tA, tB, tCc, tD, tP3);
+    if (tid == 0 && f == 0) printf("k2b rank=%d total=%lld load=%lld pmask=%lld passes=%d [%lld %lld %lld %lld %lld %lld] converge0=%lld rounds(%d)=%lld p3: write=%lld counts=%lld csync=%lld points=%lld final=%lld\n", rank, clock64() - t0, tL, tPm, npass, tps[0], tps[1], tps[2], tps[3], tps[4], tps[5], tC0, rounds, tX, tA, tB, tCc, tD, tP3);
 #endif
 }
 
