@@ -496,26 +496,54 @@ __global__ void __launch_bounds__(K2T, 3) k2_canny_cluster(K2Args A)
     const uint32_t *roi = A.roi_bits;
     uint32_t *Mk = C;                                     // [Rv][WW] masked edges of this band
     int cnt = 0;
-    {
-        uint32_t *__restrict__ eb = A.edge_bits + ((size_t)f * H + b0) * WW;
-        uint32_t *__restrict__ pm = A.pmask_bits + (size_t)f * g.bh * WW;
-        const uint32_t *__restrict__ rb = roi + (size_t)b0 * WW;
-        const int cols = min(WW, K2T), rstep = max(1, K2T / WW);
-        const int w0 = tid % cols, r0 = tid / cols;
-        if (r0 < rstep) {
-            for (int w = w0; w < WW; w += cols) {
-#pragma unroll 4
-                for (int r = r0; r < Rv; r += rstep) {
-                    const int i = r * WW + w, y = b0 + r;
-                    const uint32_t sv = S[WW + i];
-                    eb[i] = sv;
-                    cnt += __popc(sv);
-                    const bool in_roi = y >= g.by0 && y < g.by1;
-                    const uint32_t m = in_roi ? (sv & __ldg(rb + i)) : 0u;
-                    if (in_roi) pm[(size_t)(y - g.by0) * WW + w] = m;
-                    Mk[i] = m;
-                }
+    uint32_t *eb = A.edge_bits + ((size_t)f * H + b0) * WW;
+    uint32_t *pm = A.pmask_bits + (size_t)f * g.bh * WW;
+    const bool bulk_out = (WW % 4 == 0) && Rv > 0;
+    if (bulk_out) {
+        // The band of the edge plane is the strong plane as it stands, one contiguous block: a single bulk store.
+        // The ROI rows of the mask arrive by bulk copy into the (now free) candidate plane, are ANDed with the edges
+        // in place and leave by a second bulk store; threads touch only shared memory.
+        const int nroi = max(y1 - y0, 0);
+        uint32_t *Mroi = Mk + (size_t)(y0 - b0) * WW;
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // hysteresis stores -> async proxy
+        __syncthreads();
+        if (tid == 0) {
+            asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                         ::"l"(eb), "r"(smem_u32(S + WW)), "r"((uint32_t)Rv * WW * 4u) : "memory");
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            if (nroi > 0) {
+                const uint32_t bar = smem_u32(&s_bar);
+                mbar_expect_tx(bar, (uint32_t)nroi * WW * 4u);
+                bulk_g2s(smem_u32(Mroi), roi + (size_t)y0 * WW, (uint32_t)nroi * WW * 4u, bar);
             }
+        }
+        for (int i = tid; i < Rv * WW; i += K2T) cnt += __popc(S[WW + i]);
+        if (nroi > 0) {
+            mbar_wait(smem_u32(&s_bar), 1);                               // second use of the barrier: phase parity 1
+            const uint32_t *Sroi = S + WW + (size_t)(y0 - b0) * WW;
+            for (int i = tid; i < nroi * WW; i += K2T) Mroi[i] &= Sroi[i];
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncthreads();
+            if (tid == 0) {
+                asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                             ::"l"(pm + (size_t)(y0 - g.by0) * WW), "r"(smem_u32(Mroi)), "r"((uint32_t)nroi * WW * 4u) : "memory");
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            }
+        }
+        if (tid == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // S is reused below
+    } else {
+        const uint32_t *rb = roi + (size_t)b0 * WW;
+        for (int i = tid; i < Rv * WW; i += K2T) {
+            const int r = i / WW, y = b0 + r;
+            const uint32_t sv = S[WW + i];
+            eb[i] = sv;
+            cnt += __popc(sv);
+            uint32_t m = 0;
+            if (y >= g.by0 && y < g.by1) {
+                m = sv & rb[i];
+                pm[(size_t)(y - g.by0) * WW + (i - r * WW)] = m;
+            }
+            Mk[i] = m;
         }
     }
     for (int o = 16; o; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
@@ -528,12 +556,16 @@ __global__ void __launch_bounds__(K2T, 3) k2_canny_cluster(K2Args A)
         if (rank == 0) A.rounds[f] = rounds;
     }
     K2TICK(tA);
-    // a thread per ROI row: count, block scan, then write the row's points (rows are short lists; all rows in parallel)
+    // a thread per ROI row: running count per word (kept in the strong plane's storage, which is free now) and the
+    // row total; block scan of the totals; then every (row, word) writes its own points, all in parallel
     const int nrows = max(y1 - y0, 0);
+    uint32_t *Pfx = S + WW;                               // [Rv][WW] points of the row before word w
     for (int i = tid; i < nrows; i += K2T) {
         const uint32_t *row = Mk + (size_t)(y0 + i - b0) * WW;
+        uint32_t *pf = Pfx + (size_t)(y0 + i - b0) * WW;
         int c = 0;
-        for (int w = 0; w < WW; w++) c += __popc(row[w]);
+#pragma unroll 4
+        for (int w = 0; w < WW; w++) { pf[w] = c; c += __popc(row[w]); }
         rowoff[y0 + i - b0] = c;
     }
     __syncthreads();
@@ -564,24 +596,29 @@ __global__ void __launch_bounds__(K2T, 3) k2_canny_cluster(K2Args A)
     }
     __syncthreads();
     uint32_t *out = A.points + (size_t)f * g.max_points + s_base;
-    for (int i = tid; i < nrows; i += K2T) {
-        const int y = y0 + i;
-        const uint32_t *row = Mk + (size_t)(y - b0) * WW;
-        int p = rowoff[y - b0];
-        for (int w = 0; w < WW; w++) {
-            uint32_t m = row[w];
-            while (m) {
-                const int b = __ffs(m) - 1;
-                out[p++] = ((uint32_t)y << 16) | (uint32_t)(w * 32 + b);
-                m &= m - 1;
-            }
-        }
+    {
+        const int cols = min(WW, K2T), rstep = max(1, K2T / WW);
+        const int w0 = tid % cols, r0 = tid / cols;
+        if (r0 < rstep)
+            for (int w = w0; w < WW; w += cols)
+                for (int i = r0; i < nrows; i += rstep) {
+                    const int lr = y0 + i - b0;
+                    uint32_t m = Mk[(size_t)lr * WW + w];
+                    if (!m) continue;
+                    int p = rowoff[lr] + (int)Pfx[(size_t)lr * WW + w];
+                    const uint32_t hi = ((uint32_t)(y0 + i) << 16) | (uint32_t)(w * 32);
+                    while (m) {
+                        out[p++] = hi | (uint32_t)(__ffs(m) - 1);
+                        m &= m - 1;
+                    }
+                }
     }
     K2TICK(tD);
     if (G > 1) cluster.sync();                            // keep s_total alive until every band has read it
+    if (tid == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
 #ifdef LANE_K2_PROF
     K2TICK(tP3);
-    if (tid == 0 && f == 0) printf("k2b rank=%d total=%lld load=%lld pmask=%lld passes=%d [%lld %lld %lld %lld %lld %lld] converge0=%lld rounds(%d)=%lld p3: write=%lld counts=%lld csync=%lld points=%lld final=%lld\n", rank, clock64() - t0, tL, tPm, npass, tps[0], tps[1], tps[2], tps[3], tps[4], tps[5], tC0, rounds, tX, tA, tB, tCc, tD, tP3);
+    if (tid == 0 && f == 128) printf("k2b rank=%d total=%lld load=%lld pmask=%lld passes=%d [%lld %lld %lld %lld %lld %lld] converge0=%lld rounds(%d)=%lld p3: write=%lld counts=%lld csync=%lld points=%lld final=%lld\n", rank, clock64() - t0, tL, tPm, npass, tps[0], tps[1], tps[2], tps[3], tps[4], tps[5], tC0, rounds, tX, tA, tB, tCc, tD, tP3);
 #endif
 }
 
