@@ -14,7 +14,8 @@ value   frames/s with the frames already resident in HBM when the timed region s
 e2e     frames/s through the public API (LaneDetector.detect_batch) with HOST (pinned) frames:
         host->device copy and device->host records inside the timed region.
 roofline  K1 (fused gray+blur+histogram), algorithmic 4 B/px (3 B/px BGR read + 1 B/px plane write,
-        SURVEY.md 8d) over its CUDA-event time measured live on the launching stream.
+        SURVEY.md 8d) over its CUDA-event time measured live on the launching stream; roofline.edge_path
+        is the same 4 B/px over K1 + K2a + K2b (everything from BGR frames to the edge map and point list).
 cpu_baseline  the reference's OpenCV path (oracle/cv2_pipeline.py: the reference call sequence on
         the same cv2/numpy) on this box's host cores, bounded sample.
 """
@@ -293,6 +294,8 @@ def main():
         peak = float(peaks.get("hbm_gbs", 6650.0))
         k1_ms = stage_sum["blur_hist"] / args.steps
         achieved = n * ALGO_BYTES_PER_FRAME / (k1_ms / 1e3) / 1e9 if k1_ms > 0 else 0.0
+        canny_ms = (stage_sum["canny"] + stage_sum["compact"]) / args.steps
+        edge_achieved = n * ALGO_BYTES_PER_FRAME / ((k1_ms + canny_ms) / 1e3) / 1e9 if k1_ms > 0 else 0.0
         out = dict(base, value=value, ms_per_step=dev_ms / args.steps, dtype="u8/int32/f64",
                    config={"workload": workload, "frames_per_gpu_per_step": n, "resolution": [W, H],
                            "l2_policy": "inputs larger than L2 (1.6 GB of frames per step vs 126 MB L2)",
@@ -302,9 +305,13 @@ def main():
                              "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 (of fallback)",
                              # dram__bytes_read.sum + dram__bytes_write.sum of one k1_strip launch (256 x 1080p), from
                              # the ncu --set full capture summarised in profiles/r1_final_ncu_summary.md
-                             "traffic": (2.215e9 if (n == 256) else None), "traffic_source": "profiles/r1_final_ncu_summary.md",
+                             "traffic": (2.173e9 if (n == 256) else None), "traffic_source": "profiles/r1_final_ncu_summary.md",
                              "ms_per_launch": k1_ms,
-                             "algorithmic_bytes_per_launch": n * ALGO_BYTES_PER_FRAME},
+                             "algorithmic_bytes_per_launch": n * ALGO_BYTES_PER_FRAME,
+                             # SURVEY 8d also asks for the same 4 B/px over ALL edge kernels (BGR in -> edge map out):
+                             # K1 + K2a (Sobel/NMS) + K2b (hysteresis/ROI/compaction); those two are issue/latency bound
+                             "edge_path": {"kernels": "K1 + K2a + K2b", "ms": k1_ms + canny_ms,
+                                           "achieved": edge_achieved, "frac": edge_achieved / peak}},
                    stage_ms_per_step={k: v / args.steps for k, v in stage_sum.items()},
                    e2e={"value": e2e_val, "unit": "frames/s", "h2d_bytes_per_step": int(host_frames.nbytes),
                         "d2h_bytes_per_step": int(rec_bytes), "api": "LaneDetector.detect_batch(numpy pinned)"},
