@@ -159,6 +159,18 @@ LANE_API int lane_debug_tap(lane_ctx *ctx, int what, int frame_index, void *host
 LANE_API int lane_hough_accumulator(lane_ctx *ctx, int frame_index, int32_t *accum_host, int threshold,
                            int32_t *peaks_host, int max_peaks, int *n_peaks);
 
+/* ---- frame ingest (the step before the path) -------------------------------------------
+ * Replaces the pixel work of VideoDataLoader.read_frame / read_frame_at
+ * (/root/reference/data/loaders/video_loader.py:96-131): `frame = cv2.resize(frame, self.target_size)` (:108, :128),
+ * OpenCV's default INTER_LINEAR on uint8, for a whole batch of equally sized frames, bit-exact.
+ * src: uint8 [n][src_h][src_w][channels], dst: uint8 [n][dst_h][dst_w][channels], channels = 1 or 3, both dense.
+ * on_device = 1: both are device pointers on `device`, the kernel is enqueued on `cuda_stream` (a cudaStream_t,
+ * NULL = default stream) and the call returns without synchronising -- this is how resized frames are handed to
+ * lane_detect_batch(frames_on_device = 1) without ever leaving HBM.  on_device = 0: both are host pointers, the
+ * call copies in, resizes, copies out and synchronises.  Needs no context; errors via lane_last_error(NULL). */
+LANE_API int lane_resize_batch(const uint8_t *src, int n, int src_h, int src_w, int channels, uint8_t *dst, int dst_h,
+                               int dst_w, int on_device, int device, void *cuda_stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -2,7 +2,8 @@
 bhavyageethika/multimodal_autonomous_driving_perception_and_planning
 (``src/perception/lane_detector.py``).  See DESIGN.md / INTEGRATION.md at the repo root."""
 from .generators import SyntheticDataGenerator, multi_camera_batch
+from .loaders import FrameIngest
 from .perception import LaneDetector, LaneLine
 
-__all__ = ["LaneDetector", "LaneLine", "SyntheticDataGenerator", "multi_camera_batch"]
+__all__ = ["FrameIngest", "LaneDetector", "LaneLine", "SyntheticDataGenerator", "multi_camera_batch"]
 __version__ = "0.1.0"

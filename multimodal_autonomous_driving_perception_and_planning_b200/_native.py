@@ -65,6 +65,8 @@ def build(verbose: bool = False) -> str:
 _lib = None
 
 _PROTOS = {
+    "lane_resize_batch": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int,
+                                     C.c_int, C.c_void_p]),
     "lane_abi_version": (C.c_int, []),
     "lane_last_error": (C.c_char_p, [C.c_void_p]),
     "lane_ctx_create": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p)]),

@@ -14,6 +14,7 @@ void lane_upload_sample_rows(int H);
 #define LANE_COPY_EVENTS 8
 
 static thread_local std::string g_create_error;
+void lane_set_global_error(const char *msg) { g_create_error = msg ? msg : ""; }
 
 struct lane_ctx {
     int device = 0;

@@ -30,6 +30,9 @@ struct LaneHoughParams {
     int threshold, min_len, max_gap;
 };
 
+// message returned by lane_last_error(NULL): context creation and the context-free entry points
+void lane_set_global_error(const char *msg);
+
 // ---- K1 ---------------------------------------------------------------------------------
 void launch_blur_hist(const uint8_t *frames, uint8_t *blur, uint32_t *hist, int n, int H, int W,
                       cudaStream_t st, int *launches, int *task_counter, int force_tile, int gaussian_blur);

@@ -376,3 +376,54 @@ def test_randomised_scenes_against_cv2(seed):
         assert det.last_records[i]["n_roi_points"] == int((masked != 0).sum())
         assert np.array_equal(det._ctx.tap(_native.TAP_SEGMENTS, i), want), (seed, i, h, w, thr, min_len, gap)
     det.close()
+
+
+# ---- frame ingest: batched cv2.resize on the device -------------------------------------
+RESIZE_CASES = [(1920, 1080, 640, 480), (1920, 1080, 1280, 720), (640, 480, 1920, 1080), (1000, 700, 333, 217),
+                (333, 217, 1000, 700), (64, 48, 640, 480), (5, 7, 33, 21), (1280, 720, 1279, 719), (17, 9, 1, 1)]
+
+
+@pytest.mark.parametrize("sw,sh,dw,dh", RESIZE_CASES)
+@pytest.mark.parametrize("cn", [3, 1])
+def test_resize_batch_matches_cv2_and_oracle(sw, sh, dw, dh, cn):
+    from multimodal_autonomous_driving_perception_and_planning_b200 import FrameIngest
+    from oracle import resize as orz
+    rng = np.random.default_rng(sw + 3 * dh + cn)
+    frames = rng.integers(0, 256, (3, sh, sw, cn), dtype=np.uint8)
+    got = FrameIngest((dw, dh)).resize_batch(frames)
+    want = np.stack([cv2.resize(f, (dw, dh)).reshape(dh, dw, cn) for f in frames])
+    assert got.shape == want.shape and got.dtype == np.uint8
+    assert np.array_equal(got, want)
+    assert np.array_equal(got[0], orz.resize_linear(frames[0], (dw, dh)).reshape(dh, dw, cn))
+
+
+def test_resize_on_device_feeds_detector_without_leaving_hbm():
+    """1080p generator frames -> FrameIngest(640x480) on the device -> LaneDetector.detect_batch(CUDA tensor):
+    the same lanes as cv2.resize + the cv2 reference pipeline frame by frame."""
+    import torch
+    from multimodal_autonomous_driving_perception_and_planning_b200 import FrameIngest
+    from multimodal_autonomous_driving_perception_and_planning_b200 import multi_camera_batch
+    big = multi_camera_batch(1, 6, 1920, 1080)[0]
+    dev_small = FrameIngest((640, 480)).resize_batch(torch.from_numpy(big).cuda())
+    assert dev_small.is_cuda and tuple(dev_small.shape) == (6, 480, 640, 3)
+    small = np.stack([cv2.resize(f, (640, 480)) for f in big])
+    assert np.array_equal(dev_small.cpu().numpy(), small)
+    det = LaneDetector(max_batch=6)
+    lanes = det.detect_batch(dev_small)
+    ref = Cv2LaneOracle()
+    for i, f in enumerate(small):
+        lf, rf = ref.detect(f)
+        for got, want in ((lanes[i][0], lf), (lanes[i][1], rf)):
+            assert (got is None) == (want is None)
+            if got is not None:
+                assert np.allclose(got.polynomial, want.coeffs, rtol=1e-3, atol=1e-6)
+    det.close()
+
+
+def test_resize_errors():
+    from multimodal_autonomous_driving_perception_and_planning_b200 import FrameIngest
+    with pytest.raises(cv2.error):
+        FrameIngest((8, 8)).resize_batch(np.zeros((1, 4, 4, 3), np.float32))
+    with pytest.raises(cv2.error):
+        FrameIngest((8, 8)).resize_batch(np.zeros((1, 4, 4, 2), np.uint8))
+    assert FrameIngest(None).resize_batch(np.zeros((1, 4, 4, 3), np.uint8)).shape == (1, 4, 4, 3)
