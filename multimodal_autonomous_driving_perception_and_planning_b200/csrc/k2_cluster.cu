@@ -58,6 +58,12 @@ __device__ __forceinline__ uint32_t h2sub(uint32_t a, uint32_t b)
     asm("sub.f16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b));
     return d;
 }
+__device__ __forceinline__ uint32_t h2abs_sum(uint32_t a, uint32_t b)   // |a| + |b| (the abs folds into HADD2's operand modifiers)
+{
+    uint32_t d;
+    asm("{\n\t.reg .b32 ta, tb;\n\tabs.f16x2 ta, %1;\n\tabs.f16x2 tb, %2;\n\tadd.f16x2 %0, ta, tb;\n\t}" : "=r"(d) : "r"(a), "r"(b));
+    return d;
+}
 __device__ __forceinline__ uint32_t h2fma2(uint32_t a, uint32_t b)   // 2*a + b
 {
     uint32_t d;
@@ -114,7 +120,6 @@ __device__ __forceinline__ void canny_rows(int H, int W, int WW, const uint8_t *
     const uint8_t *src = blur_f + max(xl, 0);
     const int word = strip * (STRIP_OUT / 32) + ((lane - 1) >> 1);
     const bool writer = (lane & 1) && lane <= 29 && in_img && word < WW;
-    const uint32_t lane_mask = in_img ? 0x7FFF7FFFu : 0u;   // |.| mask of the packed gradients; 0 outside the image
     const uint32_t low2 = (uint32_t)low | ((uint32_t)low << 16);
     const uint32_t xb = SPX * lane;
     const uint32_t own_mask = (lane >= 1 && lane <= 30 && in_img) ? 0xFFFFu : 0u;   // halo lanes only feed neighbours
@@ -134,6 +139,13 @@ __device__ __forceinline__ void canny_rows(int H, int W, int WW, const uint8_t *
         b[4] = __byte_perm(v.z, 0, 0x4140); b[5] = __byte_perm(v.z, 0, 0x4342);
         b[6] = __byte_perm(v.w, 0, 0x4140); b[7] = __byte_perm(v.w, 0, 0x4342);
     };
+    if (!in_img) {                                         // zero magnitude beyond the image border, for the whole task
+#pragma unroll
+        for (int sl = 0; sl < 3; sl++) {
+            uint4 *z = reinterpret_cast<uint4 *>(Mring + sl * K2A_RS + xb);
+            z[0] = make_uint4(0, 0, 0, 0); z[1] = make_uint4(0, 0, 0, 0);
+        }
+    }
     unpack(load_raw(q0 - 2), Bs[0]);
     unpack(load_raw(q0 - 1), Bs[1]);
 #pragma unroll
@@ -147,8 +159,9 @@ __device__ __forceinline__ void canny_rows(int H, int W, int WW, const uint8_t *
         constexpr int k = decltype(slot)::value, o = k ^ 1;
         unpack(vnext, Bs[k]);                            // row c+1
         if (c < q1) vnext = load_raw(c + 2);             // prefetch the next step's row behind the arithmetic
-        // the magnitude plane has a zero border: rows outside the frame and lanes outside the image give M = 0
-        const uint32_t absm = (c >= 0 && c < H) ? lane_mask : 0u;
+        // the magnitude plane has a zero border: rows outside the frame give M = 0 (lanes outside the image never
+        // store their M; their ring entries were zeroed once)
+        const bool row_ok = c >= 0 && c < H;
         uint32_t cand_new;
         {
             uint32_t Sc[8], Dc[8];
@@ -175,14 +188,19 @@ __device__ __forceinline__ void canny_rows(int H, int W, int WW, const uint8_t *
             for (int j = 0; j < 8; j++) {
                 dx[j] = h2sub(So[j + 1], So[j]);
                 dy[j] = h2fma2(Dc[j], h2add(Do[j], Do[j + 1]));
-                Mw[j] = h2add(dx[j] & absm, dy[j] & absm);
+                Mw[j] = h2abs_sum(dx[j], dy[j]);
                 const uint32_t gt = __hgt2_mask(*reinterpret_cast<const __half2 *>(&Mw[j]),
                                                 *reinterpret_cast<const __half2 *>(&low2));      // 0xFFFF per half: M > low
                 acc |= gt & ((1u << (2 * j)) | (1u << (2 * j + 17)));
             }
             cand_new = (acc | (acc >> 16)) & own_mask;
             uint4 *mrow = reinterpret_cast<uint4 *>(Mring + sc + xb);
-            mrow[0] = make_uint4(Mw[0], Mw[1], Mw[2], Mw[3]); mrow[1] = make_uint4(Mw[4], Mw[5], Mw[6], Mw[7]);
+            if (!row_ok) {                                       // warp-uniform, first / last row of the frame only
+                cand_new = 0;
+#pragma unroll
+                for (int j = 0; j < 8; j++) Mw[j] = 0;
+            }
+            if (in_img) { mrow[0] = make_uint4(Mw[0], Mw[1], Mw[2], Mw[3]); mrow[1] = make_uint4(Mw[4], Mw[5], Mw[6], Mw[7]); }
             uint4 *xrow = reinterpret_cast<uint4 *>(DXr + (c & 1) * 512 + xb);
             xrow[0] = make_uint4(dx[0], dx[1], dx[2], dx[3]); xrow[1] = make_uint4(dx[4], dx[5], dx[6], dx[7]);
             uint4 *yrow = reinterpret_cast<uint4 *>(DYr + (c & 1) * 512 + xb);
