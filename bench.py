@@ -135,7 +135,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--frames", type=int, default=256, help="frames per GPU per step")
     ap.add_argument("--distinct", type=int, default=64, help="distinct generator frames per stream (tiled in time)")
-    ap.add_argument("--cpu-frames", type=int, default=256, help="CPU baseline sample: frames per host core")
+    ap.add_argument("--cpu-frames", type=int, default=1024, help="CPU baseline sample: frames per host core")
     ap.add_argument("--skip-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
     ap.add_argument("--skip-e2e", action="store_true", help="skip the e2e leg (profiling runs)")
     args = ap.parse_args()
