@@ -171,6 +171,23 @@ LANE_API int lane_hough_accumulator(lane_ctx *ctx, int frame_index, int32_t *acc
 LANE_API int lane_resize_batch(const uint8_t *src, int n, int src_h, int src_w, int channels, uint8_t *dst, int dst_h,
                                int dst_w, int on_device, int device, void *cuda_stream);
 
+/* ---- scene statistics (second half) -----------------------------------------------------
+ * Integer sums behind SceneClassifier's image cues (/root/reference/src/tagging/scene_classifier.py):
+ *   avg_brightness = np.mean(cvtColor(frame, BGR2GRAY))                       (:237-238)  = sum_gray / (H*W)
+ *   laplacian_var  = cv2.Laplacian(gray, cv2.CV_64F).var()                    (:254)      = E[L^2] - E[L]^2
+ *   green_ratio    = sum(inRange(cvtColor(frame, BGR2HSV), (35,40,40), (85,255,255)) > 0) / size   (:183-186)
+ * The device returns exact integers; the caller forms the float64 quantities (see scene_stats.py). */
+typedef struct lane_frame_stat {
+    uint64_t sum_gray;              /* sum of the BGR2GRAY plane */
+    int64_t sum_laplacian;          /* sum of L = 3x3 Laplacian (ksize 1, BORDER_REFLECT_101) of the gray plane */
+    uint64_t sum_laplacian_sq;      /* sum of L*L */
+    uint64_t green_pixels;          /* pixels with 35 <= H <= 85, S >= 40, V >= 40 in OpenCV's 8-bit HSV */
+} lane_frame_stat;
+/* frames: uint8 [n][height][width][3] BGR, host (on_device = 0) or device pointer; out: n records in host memory.
+ * Blocking (synchronises `cuda_stream`).  Needs no context; errors via lane_last_error(NULL). */
+LANE_API int lane_frame_stats(const uint8_t *frames, int on_device, int n, int height, int width, lane_frame_stat *out,
+                              int device, void *cuda_stream);
+
 #ifdef __cplusplus
 }
 #endif

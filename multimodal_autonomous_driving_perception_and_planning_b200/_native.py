@@ -65,6 +65,7 @@ def build(verbose: bool = False) -> str:
 _lib = None
 
 _PROTOS = {
+    "lane_frame_stats": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p]),
     "lane_resize_batch": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int,
                                      C.c_int, C.c_void_p]),
     "lane_abi_version": (C.c_int, []),

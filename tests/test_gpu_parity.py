@@ -427,3 +427,33 @@ def test_resize_errors():
     with pytest.raises(cv2.error):
         FrameIngest((8, 8)).resize_batch(np.zeros((1, 4, 4, 2), np.uint8))
     assert FrameIngest(None).resize_batch(np.zeros((1, 4, 4, 3), np.uint8)).shape == (1, 4, 4, 3)
+
+
+# ---- scene statistics (second half) --------------------------------------------------------
+def test_scene_stats_match_cv2_expressions():
+    """avg_brightness, laplacian_var and green_ratio of SceneClassifier (scene_classifier.py:183-186, :237-254)."""
+    import torch
+    from multimodal_autonomous_driving_perception_and_planning_b200 import multi_camera_batch
+    from multimodal_autonomous_driving_perception_and_planning_b200.perception.scene_stats import SceneStatsAnalyzer
+    from oracle import scene_stats as oss
+    rng = np.random.default_rng(5)
+    batches = [multi_camera_batch(1, 3, 1920, 1080)[0], multi_camera_batch(1, 3, 640, 480)[0],
+               rng.integers(0, 256, (2, 97, 131, 3), dtype=np.uint8), rng.integers(0, 256, (2, 1, 9, 3), dtype=np.uint8),
+               rng.integers(0, 256, (2, 200, 1, 3), dtype=np.uint8)]
+    grass = np.zeros((2, 130, 260, 3), np.uint8)
+    grass[...] = (40, 160, 60)
+    grass[:, ::3] = (90, 200, 30)
+    grass[:, :, ::7] = (200, 200, 200)
+    batches.append(grass)
+    an = SceneStatsAnalyzer()
+    for frames in batches:
+        for got_all in (an.analyze_batch(frames), an.analyze_batch(torch.from_numpy(frames).cuda())):
+            for f, got in zip(frames, got_all):
+                want = oss.frame_sums(f)
+                assert (got.sum_gray, got.sum_laplacian, got.sum_laplacian_sq, got.green_pixels) == \
+                    (want.sum_gray, want.sum_laplacian, want.sum_laplacian_sq, want.green_pixels)
+                gray = cv2.cvtColor(f, cv2.COLOR_BGR2GRAY)
+                green = cv2.inRange(cv2.cvtColor(f, cv2.COLOR_BGR2HSV), (35, 40, 40), (85, 255, 255))
+                assert got.avg_brightness == np.mean(gray)
+                assert got.green_ratio == np.sum(green > 0) / green.size
+                assert got.laplacian_var == pytest.approx(cv2.Laplacian(gray, cv2.CV_64F).var(), rel=1e-12, abs=1e-12)

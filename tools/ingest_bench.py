@@ -37,3 +37,29 @@ for (sw, sh, dw, dh, n) in [(1920, 1080, 640, 480, 256), (1920, 1080, 1280, 720,
     print(json.dumps({"ingest": f"{n} x {sw}x{sh} -> {dw}x{dh}", "ms": ms, "frames_per_s": n / (ms / 1e3),
                       "algorithmic_GBps": algo / (ms / 1e3) / 1e9, "frac_of_measured_hbm": algo / (ms / 1e3) / 1e9 / peak,
                       "cpu_fps_1thread_default_cv2": cpu_fps, "bit_exact_vs_cv2": ok}), flush=True)
+
+# ---- scene statistics (K6): one pass over the BGR frames, 3 B/px read, nothing written
+from multimodal_autonomous_driving_perception_and_planning_b200.perception.scene_stats import SceneStatsAnalyzer
+import ctypes as C
+from multimodal_autonomous_driving_perception_and_planning_b200 import _native
+for (sw, sh, n) in [(1920, 1080, 256)]:
+    base = multi_camera_batch(1, 8, sw, sh)[0]
+    src = torch.from_numpy(np.concatenate([base] * (n // 8))).cuda()
+    an = SceneStatsAnalyzer()
+    for _ in range(2):
+        an.analyze_batch(src)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(10):
+        res = an.analyze_batch(src)          # blocking call (records come back to the host)
+    ms = (time.perf_counter() - t0) / 10 * 1e3
+    t0 = time.perf_counter()
+    for f in base:
+        g = cv2.cvtColor(f, cv2.COLOR_BGR2GRAY); np.mean(g); cv2.Laplacian(g, cv2.CV_64F).var()
+        m = cv2.inRange(cv2.cvtColor(f, cv2.COLOR_BGR2HSV), (35, 40, 40), (85, 255, 255)); np.sum(m > 0) / m.size
+    cpu_fps = len(base) / (time.perf_counter() - t0)
+    algo = n * sh * sw * 3
+    print(json.dumps({"scene_stats": f"{n} x {sw}x{sh}", "ms_wall_per_call": ms, "frames_per_s": n / (ms / 1e3),
+                      "algorithmic_GBps": algo / (ms / 1e3) / 1e9, "frac_of_measured_hbm": algo / (ms / 1e3) / 1e9 / peak,
+                      "cpu_fps_default_cv2": cpu_fps, "avg_brightness": res[0].avg_brightness,
+                      "laplacian_var": res[0].laplacian_var, "green_ratio": res[0].green_ratio}), flush=True)
