@@ -590,7 +590,7 @@ __global__ void __launch_bounds__(416, 2) k4_ppht_v3(const uint32_t *__restrict_
     __shared__ int s_good;
     __shared__ int s_nhits;
     __shared__ unsigned s_whit[2][24], s_wib[2][24];   // pass-1 ballots of one round, per direction
-    __shared__ int s_wlast[2], s_wdone[2];
+    __shared__ int s_wlast[2], s_wdone[2], s_wrounds[2];
     __shared__ WalkSetup s_walk;
 
     unsigned rank;
@@ -845,7 +845,7 @@ __global__ void __launch_bounds__(416, 2) k4_ppht_v3(const uint32_t *__restrict_
                         const int k = nvw >= 2 ? kdir : dp;
                         const int wl = nvw >= 2 ? (wid - k * half) : 0;   // warp index inside the direction group
                         const int gsteps = half * 32 * WPT;
-                        if (tid < 2) { s_wlast[tid] = 0; s_wdone[tid] = 0; }
+                        if (tid < 2) { s_wlast[tid] = 0; s_wdone[tid] = 0; s_wrounds[tid] = 0; }
                         bar_v();
                         for (int base = 0;; base += gsteps) {
                             if (k < 2 && !s_wdone[k]) {
@@ -868,6 +868,7 @@ __global__ void __launch_bounds__(416, 2) k4_ppht_v3(const uint32_t *__restrict_
                             bar_v();
                             if (tid < 2 && !s_wdone[tid] && (nvw >= 2 || tid == k)) {   // gap logic over this round's bit string
                                 const int kk = tid;
+                                s_wrounds[kk]++;
                                 int last = s_wlast[kk];
                                 bool done = false;
                                 for (int q = 0; q < half * WPT && !done; q++) {
@@ -927,8 +928,22 @@ __global__ void __launch_bounds__(416, 2) k4_ppht_v3(const uint32_t *__restrict_
                     for (int base = 0; base < ns; base += per_round) {
                         if (tid == 0) s_nhits = 0;
                         bar_v();
+                        // A walk that fit one pass-1 round left its hit bits in shared memory: they are exactly the set
+                        // mask pixels along the line (the private mask has not changed since), so the mask is cleared
+                        // with fire-and-forget atomics and nothing is read back.  Longer walks probe the mask again.
+                        const bool have_bits = s_wrounds[k] == 1;
                         for (int s = base + tid; s < min(ns, base + per_round); s += NVT) {
                             int j1, i1;
+                            if (have_bits) {
+                                // step 0 is the trigger pixel itself in both directions: direction 0 has taken it
+                                if (((s_whit[k][s >> 5] >> (s & 31)) & 1u) && !(k == 1 && s == 0)) {
+                                    step_pixel(w, k, s, j1, i1);
+                                    atomicAnd(&pm[(i1 - g.by0) * WW + (j1 >> 5)], ~(1u << (j1 & 31)));
+                                    const int h = atomicAdd(&s_nhits, 1);
+                                    s_hx[h] = (float)j1; s_hy[h] = (float)i1;
+                                }
+                                continue;
+                            }
                             step_pixel(w, k, s, j1, i1);
                             if (i1 >= g.by0 && i1 < g.by1 && j1 >= 0 && j1 < g.W) {
                                 const uint32_t bit = 1u << (j1 & 31);
