@@ -85,7 +85,8 @@ def cpu_info():
 
 # ------------------------------------------------------------------------------------ clocks
 class ClockSampler:
-    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+    # the sample's own timestamp is used (lines reach the pipe in bursts, so arrival time is not sampling time)
+    FIELDS = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
               "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
               "clocks_event_reasons.sw_power_cap")
 
@@ -102,8 +103,16 @@ class ClockSampler:
             self.proc = None
 
     def _pump(self):
+        import datetime
+        skew = time.perf_counter() - time.time()          # wall clock -> perf_counter
         for line in self.proc.stdout:
-            self.lines.append((time.perf_counter(), line.strip()))
+            line = line.strip()
+            stamp, _, rest = line.partition(",")
+            try:
+                t = datetime.datetime.strptime(stamp.strip(), "%Y/%m/%d %H:%M:%S.%f").timestamp() + skew
+            except ValueError:
+                t = time.perf_counter()
+            self.lines.append((t, rest.strip()))
 
     def stop(self, t0, t1):
         if self.proc is None:
