@@ -457,3 +457,24 @@ def test_scene_stats_match_cv2_expressions():
                 assert got.avg_brightness == np.mean(gray)
                 assert got.green_ratio == np.sum(green > 0) / green.size
                 assert got.laplacian_var == pytest.approx(cv2.Laplacian(gray, cv2.CV_64F).var(), rel=1e-12, abs=1e-12)
+
+
+def test_hysteresis_long_weak_chains_are_schedule_independent():
+    """Low-contrast textured scenes make long weak chains that cross band and word boundaries: the hysteresis
+    kernel's walks / dirty flags / boundary rounds must give cv2's edge map on every run."""
+    rng = np.random.default_rng(77)
+    frames = []
+    for _ in range(3):
+        img = _random_scene(rng, 1080, 1920)
+        img = np.clip(img.astype(np.int16) + rng.integers(-14, 15, img.shape), 0, 255).astype(np.uint8)
+        frames.append(cv2.GaussianBlur(img, (0, 0), 1.5))
+    frames = np.stack(frames)
+    ref = Cv2LaneOracle()
+    want = [ref.edges(ref.blurred(f)) for f in frames]
+    det = LaneDetector(max_batch=3, max_segments=4096, debug=True)
+    for _ in range(3):
+        det.detect_batch(frames)
+        for i in range(3):
+            assert np.array_equal(det._ctx.tap(_native.TAP_EDGES, i), want[i]), i
+            assert det.last_records[i]["hysteresis_rounds"] >= 1
+    det.close()
