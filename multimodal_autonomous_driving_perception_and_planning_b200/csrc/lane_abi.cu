@@ -4,7 +4,10 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <condition_variable>
+#include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "lane_common.cuh"
@@ -16,8 +19,70 @@ void lane_upload_sample_rows(int H);
 static thread_local std::string g_create_error;
 void lane_set_global_error(const char *msg) { g_create_error = msg ? msg : ""; }
 
+// Host frames in ordinary (pageable) memory: cudaMemcpy from such memory runs at ~11 GB/s on this platform (the
+// driver stages it single-threaded).  The context stages them itself instead: a few worker threads copy 32 MB
+// pieces into a small ring of pinned buffers while the previous piece is on its way over PCIe.
+struct CopyPool {
+    std::vector<std::thread> th;
+    std::mutex m;
+    std::condition_variable cv_work, cv_done;
+    uint8_t *dst = nullptr;
+    const uint8_t *src = nullptr;
+    size_t bytes = 0;
+    unsigned long generation = 0;
+    int pending = 0;
+    bool stop = false;
+
+    explicit CopyPool(int n)
+    {
+        for (int t = 0; t < n; t++)
+            th.emplace_back([this, t, n] {
+                unsigned long seen = 0;
+                for (;;) {
+                    std::unique_lock<std::mutex> lk(m);
+                    cv_work.wait(lk, [&] { return stop || generation != seen; });
+                    if (stop) return;
+                    seen = generation;
+                    uint8_t *d = dst;
+                    const uint8_t *s0 = src;
+                    const size_t nb = bytes;
+                    lk.unlock();
+                    const size_t per = ((nb + n - 1) / n + 4095) & ~(size_t)4095, a = std::min(nb, per * t), b = std::min(nb, a + per);
+                    if (b > a) memcpy(d + a, s0 + a, b - a);
+                    lk.lock();
+                    if (--pending == 0) cv_done.notify_one();
+                }
+            });
+    }
+    void run(uint8_t *d, const uint8_t *s0, size_t nb)
+    {
+        std::unique_lock<std::mutex> lk(m);
+        dst = d; src = s0; bytes = nb;
+        pending = (int)th.size();
+        generation++;
+        cv_work.notify_all();
+        cv_done.wait(lk, [&] { return pending == 0; });
+    }
+    ~CopyPool()
+    {
+        {
+            std::lock_guard<std::mutex> lk(m);
+            stop = true;
+        }
+        cv_work.notify_all();
+        for (auto &t : th) t.join();
+    }
+};
+
+#define LANE_STAGE_SLOTS 3
+#define LANE_STAGE_BYTES ((size_t)32 << 20)
+
 struct lane_ctx {
     int device = 0;
+    CopyPool *pool = nullptr;                          // lazy: first batch of pageable host frames
+    uint8_t *h_stage[LANE_STAGE_SLOTS] = {};           // pinned staging ring
+    cudaEvent_t stage_ev[LANE_STAGE_SLOTS] = {};
+    bool stage_used[LANE_STAGE_SLOTS] = {};
     int max_batch = 0;
     LaneGeom g{};
     LaneHoughParams hp{50, 50, 150};
@@ -128,6 +193,11 @@ void free_all(lane_ctx *c)
     for (auto &e : c->copy_ev)
         if (e) cudaEventDestroy(e);
     if (c->start_ev) cudaEventDestroy(c->start_ev);
+    delete c->pool;
+    for (auto &p : c->h_stage)
+        if (p) cudaFreeHost(p);
+    for (auto &e : c->stage_ev)
+        if (e) cudaEventDestroy(e);
     if (c->copy_st) cudaStreamDestroy(c->copy_st);
     if (c->own_stream && c->st) cudaStreamDestroy(c->st);
 }
@@ -268,6 +338,21 @@ int enqueue(lane_ctx *c, const uint8_t *frames, bool on_device, int n, const int
             CU(cudaEventCreateWithFlags(&c->start_ev, cudaEventDisableTiming));
         }
         frames_dev = c->d_frames;
+        // pinned (or registered) host memory goes straight to the copy engine; ordinary memory through the staging ring
+        cudaPointerAttributes pa{};
+        bool pageable = cudaPointerGetAttributes(&pa, frames) != cudaSuccess || pa.type == cudaMemoryTypeUnregistered;
+        cudaGetLastError();
+        static const bool no_stage = getenv("LANE_B200_NO_STAGING") != nullptr;       // A/B knob
+        if (no_stage) pageable = false;
+        if (pageable && !c->pool) {
+            const unsigned hc = std::thread::hardware_concurrency();
+            c->pool = new CopyPool((int)std::max(1u, std::min(8u, hc ? hc / 2 : 4u)));
+            for (int i = 0; i < LANE_STAGE_SLOTS; i++) {
+                CU(cudaHostAlloc((void **)&c->h_stage[i], LANE_STAGE_BYTES, cudaHostAllocDefault));
+                CU(cudaEventCreateWithFlags(&c->stage_ev[i], cudaEventDisableTiming));
+            }
+        }
+        int piece = 0;
         // chunk so that a copy (~50 GB/s) and the compute of the previous chunk overlap; >= 4 chunks when possible
         const int chunk = std::max(1, std::min(64, (n + 3) / 4));
         CU(cudaEventRecord(c->start_ev, c->st));                 // the staging buffer is free once earlier work is done
@@ -275,8 +360,22 @@ int enqueue(lane_ctx *c, const uint8_t *frames, bool on_device, int n, const int
         int k = 0;
         for (int off = 0; off < n; off += chunk, k++) {
             const int m = std::min(chunk, n - off);
-            CU(cudaMemcpyAsync(c->d_frames + (size_t)off * bytes, frames + (size_t)off * bytes, bytes * m,
-                               cudaMemcpyHostToDevice, c->copy_st));
+            if (!pageable) {
+                CU(cudaMemcpyAsync(c->d_frames + (size_t)off * bytes, frames + (size_t)off * bytes, bytes * m,
+                                   cudaMemcpyHostToDevice, c->copy_st));
+            } else {
+                const size_t total = bytes * m;
+                for (size_t done = 0; done < total; done += LANE_STAGE_BYTES, piece++) {
+                    const int slot = piece % LANE_STAGE_SLOTS;
+                    const size_t nb = std::min(LANE_STAGE_BYTES, total - done);
+                    if (c->stage_used[slot]) CU(cudaEventSynchronize(c->stage_ev[slot]));   // its last DMA has left
+                    c->pool->run(c->h_stage[slot], frames + (size_t)off * bytes + done, nb);
+                    CU(cudaMemcpyAsync(c->d_frames + (size_t)off * bytes + done, c->h_stage[slot], nb, cudaMemcpyHostToDevice,
+                                       c->copy_st));
+                    CU(cudaEventRecord(c->stage_ev[slot], c->copy_st));
+                    c->stage_used[slot] = true;
+                }
+            }
             cudaEvent_t ev = c->copy_ev[k % LANE_COPY_EVENTS];
             CU(cudaEventRecord(ev, c->copy_st));
             CU(cudaStreamWaitEvent(c->st, ev, 0));

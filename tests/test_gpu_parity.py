@@ -478,3 +478,20 @@ def test_hysteresis_long_weak_chains_are_schedule_independent():
             assert np.array_equal(det._ctx.tap(_native.TAP_EDGES, i), want[i]), i
             assert det.last_records[i]["hysteresis_rounds"] >= 1
     det.close()
+
+
+def test_pageable_and_pinned_host_frames_give_identical_records():
+    """Ordinary numpy frames go through the context's pinned staging ring (32 MB pieces copied by worker threads);
+    pinned frames go straight to the copy engine.  Same records either way, call after call."""
+    import torch
+    from multimodal_autonomous_driving_perception_and_planning_b200 import multi_camera_batch
+    frames = np.concatenate([multi_camera_batch(1, 10, 1920, 1080)[0]] * 4)          # 249 MB: eight pieces, two chunks
+    pinned = torch.from_numpy(frames).pin_memory().numpy()
+    det = LaneDetector(max_batch=40)
+    det.detect_batch(pinned)
+    want = det.last_records.copy()
+    for _ in range(2):
+        det.reset()
+        det.detect_batch(frames)
+        assert det.last_records.tobytes() == want.tobytes()
+    det.close()
