@@ -343,7 +343,8 @@ int enqueue(lane_ctx *c, const uint8_t *frames, bool on_device, int n, const int
         bool pageable = cudaPointerGetAttributes(&pa, frames) != cudaSuccess || pa.type == cudaMemoryTypeUnregistered;
         cudaGetLastError();
         static const bool no_stage = getenv("LANE_B200_NO_STAGING") != nullptr;       // A/B knob
-        if (no_stage) pageable = false;
+        // small transfers (a single frame) are quicker through the driver's own path than through worker wake-ups
+        if (no_stage || bytes * (size_t)n < ((size_t)24 << 20)) pageable = false;
         if (pageable && !c->pool) {
             const unsigned hc = std::thread::hardware_concurrency();
             c->pool = new CopyPool((int)std::max(1u, std::min(8u, hc ? hc / 2 : 4u)));
