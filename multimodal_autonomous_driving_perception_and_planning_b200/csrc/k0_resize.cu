@@ -16,6 +16,7 @@
 #include <tuple>
 #include <vector>
 
+#include "host_stage.h"
 #include "lane_common.cuh"
 
 namespace {
@@ -156,7 +157,9 @@ extern "C" int lane_resize_batch(const uint8_t *src, int n, int src_h, int src_w
     uint8_t *tmp = nullptr;
     if (!on_device) {
         if ((e = cudaMalloc(&tmp, sbytes + dbytes))) return rfail(LANE_ERR_CUDA, "staging allocation", e);
-        if ((e = cudaMemcpyAsync(tmp, src, sbytes, cudaMemcpyHostToDevice, st))) { cudaFree(tmp); return rfail(LANE_ERR_CUDA, "H2D", e); }
+        HostStager *hs = lane_host_stager(device);
+        e = hs ? hs->h2d(tmp, src, sbytes, st) : cudaMemcpyAsync(tmp, src, sbytes, cudaMemcpyHostToDevice, st);
+        if (e) { cudaFree(tmp); return rfail(LANE_ERR_CUDA, "H2D", e); }
         s_dev = tmp;
         d_dev = tmp + sbytes;
     }

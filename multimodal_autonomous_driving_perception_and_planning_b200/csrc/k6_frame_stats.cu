@@ -25,6 +25,7 @@
 
 #include <vector>
 
+#include "host_stage.h"
 #include "lane_common.cuh"
 
 namespace {
@@ -322,7 +323,8 @@ extern "C" int lane_frame_stats(const uint8_t *frames, int on_device, int n, int
     if (!e) e = cudaMemsetAsync(d_acc, 0, (size_t)n * 4 * sizeof(unsigned long long), st);
     if (!e && !on_device) {
         uint8_t *df = scratch + ((512 * sizeof(int) + acc_bytes + 255) & ~(size_t)255);
-        e = cudaMemcpyAsync(df, frames, fbytes, cudaMemcpyHostToDevice, st);
+        HostStager *hs = lane_host_stager(device);
+        e = hs ? hs->h2d(df, frames, fbytes, st) : cudaMemcpyAsync(df, frames, fbytes, cudaMemcpyHostToDevice, st);
         d_frames = df;
     }
     if (e) { if (owned) cudaFree(scratch); return sfail(LANE_ERR_CUDA, "upload", e); }

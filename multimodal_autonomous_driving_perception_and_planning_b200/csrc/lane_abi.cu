@@ -19,60 +19,7 @@ void lane_upload_sample_rows(int H);
 static thread_local std::string g_create_error;
 void lane_set_global_error(const char *msg) { g_create_error = msg ? msg : ""; }
 
-// Host frames in ordinary (pageable) memory: cudaMemcpy from such memory runs at ~11 GB/s on this platform (the
-// driver stages it single-threaded).  The context stages them itself instead: a few worker threads copy 32 MB
-// pieces into a small ring of pinned buffers while the previous piece is on its way over PCIe.
-struct CopyPool {
-    std::vector<std::thread> th;
-    std::mutex m;
-    std::condition_variable cv_work, cv_done;
-    uint8_t *dst = nullptr;
-    const uint8_t *src = nullptr;
-    size_t bytes = 0;
-    unsigned long generation = 0;
-    int pending = 0;
-    bool stop = false;
-
-    explicit CopyPool(int n)
-    {
-        for (int t = 0; t < n; t++)
-            th.emplace_back([this, t, n] {
-                unsigned long seen = 0;
-                for (;;) {
-                    std::unique_lock<std::mutex> lk(m);
-                    cv_work.wait(lk, [&] { return stop || generation != seen; });
-                    if (stop) return;
-                    seen = generation;
-                    uint8_t *d = dst;
-                    const uint8_t *s0 = src;
-                    const size_t nb = bytes;
-                    lk.unlock();
-                    const size_t per = ((nb + n - 1) / n + 4095) & ~(size_t)4095, a = std::min(nb, per * t), b = std::min(nb, a + per);
-                    if (b > a) memcpy(d + a, s0 + a, b - a);
-                    lk.lock();
-                    if (--pending == 0) cv_done.notify_one();
-                }
-            });
-    }
-    void run(uint8_t *d, const uint8_t *s0, size_t nb)
-    {
-        std::unique_lock<std::mutex> lk(m);
-        dst = d; src = s0; bytes = nb;
-        pending = (int)th.size();
-        generation++;
-        cv_work.notify_all();
-        cv_done.wait(lk, [&] { return pending == 0; });
-    }
-    ~CopyPool()
-    {
-        {
-            std::lock_guard<std::mutex> lk(m);
-            stop = true;
-        }
-        cv_work.notify_all();
-        for (auto &t : th) t.join();
-    }
-};
+#include "host_stage.h"
 
 #define LANE_STAGE_SLOTS 3
 #define LANE_STAGE_BYTES ((size_t)32 << 20)
