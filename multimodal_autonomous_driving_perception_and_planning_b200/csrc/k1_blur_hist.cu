@@ -248,9 +248,11 @@ __global__ void __launch_bounds__(SWARPS * 32, MINB) k1_strip(const uint8_t *__r
                 if (y + RING < r1 + 2) issue_row(y + RING);
                 return;
             }
-            const int yy = fold101(y, H);
+            // BORDER_REFLECT_101 for a two-row halo (H >= 4 on this path): |y|, then mirrored at the bottom; 32-bit
+            // byte offset inside the frame
+            const int ya = abs(y), yy = min(ya, 2 * H - 2 - ya);
             if (in_img) {
-                const uint4 *p = reinterpret_cast<const uint4 *>(src + (size_t)yy * W * 3);
+                const uint4 *p = reinterpret_cast<const uint4 *>(src + (uint32_t)(yy * W) * 3u);
                 uint4 a = ldg_stream(p), b = ldg_stream(p + 1), c = ldg_stream(p + 2);
                 w[0] = a.x; w[1] = a.y; w[2] = a.z; w[3] = a.w; w[4] = b.x; w[5] = b.y; w[6] = b.z; w[7] = b.w;
                 w[8] = c.x; w[9] = c.y; w[10] = c.z; w[11] = c.w;
@@ -300,7 +302,7 @@ __global__ void __launch_bounds__(SWARPS * 32, MINB) k1_strip(const uint8_t *__r
             ov.z = __byte_perm(Hs[4], Hs[5], 0x7531);
             ov.w = __byte_perm(Hs[6], Hs[7], 0x7531);
             if (is_out) {
-                *reinterpret_cast<uint4 *>(dst + (size_t)yo * W) = ov;
+                *reinterpret_cast<uint4 *>(dst + (uint32_t)yo * (uint32_t)W) = ov;
                 const uint32_t ow[4] = {ov.x, ov.y, ov.z, ov.w};
 #pragma unroll
                 for (int q = 0; q < 4; q++) {
@@ -368,7 +370,7 @@ void launch_blur_hist(const uint8_t *frames, uint8_t *blur_out, uint32_t *hist, 
         return;
     }
     const bool aligned = (W % 16 == 0) && (((uintptr_t)frames | (uintptr_t)blur_out) % 16 == 0);
-    if (aligned && !force_tile) {
+    if (aligned && !force_tile && H >= 4 && (size_t)H * W * 3 < ((size_t)1 << 32)) {
         static int sms = 0;
         if (!sms) {
             int dev = 0;
