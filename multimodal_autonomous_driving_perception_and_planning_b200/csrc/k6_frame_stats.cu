@@ -190,9 +190,9 @@ __global__ void __launch_bounds__(K6_WARPS * 32, 5) k6_strip(const uint8_t *__re
 #pragma unroll
         for (int j = 0; j < 12; j++) w[j] = 0;
         auto load_row = [&](int y) {
-            const int yy = H == 1 ? 0 : (y < 0 ? -y : (y >= H ? 2 * H - 2 - y : y));       // BORDER_REFLECT_101
+            const int ya = abs(y), yy = min(ya, 2 * H - 2 - ya);       // BORDER_REFLECT_101, one-row halo, H >= 2
             if (in_img) {
-                const uint4 *p = reinterpret_cast<const uint4 *>(src + (size_t)yy * W * 3);
+                const uint4 *p = reinterpret_cast<const uint4 *>(src + (uint32_t)(yy * W) * 3u);
                 const uint4 a = k6_ldg(p), b = k6_ldg(p + 1), c = k6_ldg(p + 2);
                 w[0] = a.x; w[1] = a.y; w[2] = a.z; w[3] = a.w; w[4] = b.x; w[5] = b.y; w[6] = b.z; w[7] = b.w;
                 w[8] = c.x; w[9] = c.y; w[10] = c.z; w[11] = c.w;
@@ -209,7 +209,7 @@ __global__ void __launch_bounds__(K6_WARPS * 32, 5) k6_strip(const uint8_t *__re
                 ng = k6_not_green4(w[0], w[1], w[2], v_lo) | (k6_not_green4(w[3], w[4], w[5], v_lo) << 4) |
                      (k6_not_green4(w[6], w[7], w[8], v_lo) << 8) | (k6_not_green4(w[9], w[10], w[11], v_lo) << 12);
             }
-            const int yrow = H == 1 ? 0 : (y < 0 ? -y : (y >= H ? 2 * H - 2 - y : y));
+            const int yra = abs(y), yrow = min(yra, 2 * H - 2 - yra);
             if (y + 1 <= r1) load_row(y + 1);
             // horizontal part of this row: left + right + 1020 - 4 * centre
             uint32_t L7 = __shfl_up_sync(0xffffffffu, g[7], 1), R0 = __shfl_down_sync(0xffffffffu, g[0], 1);
@@ -331,7 +331,8 @@ extern "C" int lane_frame_stats(const uint8_t *frames, int on_device, int n, int
     dim3 grid((width + TC - 1) / TC, (height + TR - 1) / TR, n);
     if (grid.y > 65535) { if (owned) cudaFree(scratch); return sfail(LANE_ERR_UNSUPPORTED, "frame too tall", cudaSuccess); }
     static const bool force_tile = getenv("LANE_K6_TILE") != nullptr;
-    const bool strip = !force_tile && width % 16 == 0 && ((uintptr_t)d_frames % 16) == 0;
+    const bool strip = !force_tile && width % 16 == 0 && ((uintptr_t)d_frames % 16) == 0 && height >= 2 &&
+                       (size_t)height * width * 3 < ((size_t)1 << 32);
     if (strip) {
         int sms = 0;
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
