@@ -329,7 +329,7 @@ def main():
                              "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 (of fallback)",
                              # dram__bytes_read.sum + dram__bytes_write.sum of one k1_strip launch (256 x 1080p), from
                              # the ncu --set full capture summarised in profiles/r1_final_ncu_summary.md
-                             "traffic": (2.173e9 if (n == 256) else None), "traffic_source": "profiles/r1_final_ncu_summary.md",
+                             "traffic": (2.180e9 if (n == 256) else None), "traffic_source": "profiles/r1_final_ncu_summary.md",
                              "ms_per_launch": k1_ms,
                              "algorithmic_bytes_per_launch": n * ALGO_BYTES_PER_FRAME,
                              # SURVEY 8d also asks for the same 4 B/px over ALL edge kernels (BGR in -> edge map out):
