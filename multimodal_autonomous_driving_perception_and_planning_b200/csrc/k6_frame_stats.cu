@@ -147,16 +147,15 @@ __device__ __forceinline__ void k6_gray16(const uint32_t (&w)[12], uint32_t (&g)
     }
 }
 
-// sign bit set <=> pixel cannot be green: (G - R - 1) | (G - B) | (G - 40), four pixels per three words
-__device__ __forceinline__ uint32_t k6_not_green4(uint32_t w0, uint32_t w1, uint32_t w2, int v_lo)
+// sign bit set <=> pixel cannot be green: (G - R - 1) | (G - B), four pixels per three words (the V >= 40 test is left to
+// the exact path: dark greenish pixels are rare and it saves a dot product per pixel here)
+__device__ __forceinline__ uint32_t k6_not_green4(uint32_t w0, uint32_t w1, uint32_t w2)
 {
     // bytes: w0 = B0 G0 R0 B1 | w1 = G1 R1 B2 G2 | w2 = R2 B3 G3 R3 ; selector bytes are signed (+1 = 0x01, -1 = 0xFF)
-    const int a0 = k6_dp4a_us(w0, 0x00FF0100u, -1) | k6_dp4a_us(w0, 0x000001FFu, 0) | k6_dp4a_us(w0, 0x00000100u, -v_lo);
-    const int a1 = k6_dp4a_us(w1, 0x0000FF01u, -1) | k6_dp4a_us(w1, 0x00000001u, k6_dp4a_us(w0, 0xFF000000u, 0)) |
-                   k6_dp4a_us(w1, 0x00000001u, -v_lo);
-    const int a2 = k6_dp4a_us(w2, 0x000000FFu, k6_dp4a_us(w1, 0x01000000u, -1)) | k6_dp4a_us(w1, 0x01FF0000u, 0) |
-                   k6_dp4a_us(w1, 0x01000000u, -v_lo);
-    const int a3 = k6_dp4a_us(w2, 0xFF010000u, -1) | k6_dp4a_us(w2, 0x0001FF00u, 0) | k6_dp4a_us(w2, 0x00010000u, -v_lo);
+    const int a0 = k6_dp4a_us(w0, 0x00FF0100u, -1) | k6_dp4a_us(w0, 0x000001FFu, 0);
+    const int a1 = k6_dp4a_us(w1, 0x0000FF01u, -1) | k6_dp4a_us(w1, 0x00000001u, k6_dp4a_us(w0, 0xFF000000u, 0));
+    const int a2 = k6_dp4a_us(w2, 0x000000FFu, k6_dp4a_us(w1, 0x01000000u, -1)) | k6_dp4a_us(w1, 0x01FF0000u, 0);
+    const int a3 = k6_dp4a_us(w2, 0xFF010000u, -1) | k6_dp4a_us(w2, 0x0001FF00u, 0);
     return ((uint32_t)a0 >> 31) | (((uint32_t)a1 >> 31) << 1) | (((uint32_t)a2 >> 31) << 2) | (((uint32_t)a3 >> 31) << 3);
 }
 
@@ -206,8 +205,8 @@ __global__ void __launch_bounds__(K6_WARPS * 32, 5) k6_strip(const uint8_t *__re
             uint32_t ng = 0xFFFFu;                                   // "cannot be green" bits of this lane's 16 pixels
             const bool body_row = y >= r0 && y < r1;
             if (body_row && is_out) {
-                ng = k6_not_green4(w[0], w[1], w[2], v_lo) | (k6_not_green4(w[3], w[4], w[5], v_lo) << 4) |
-                     (k6_not_green4(w[6], w[7], w[8], v_lo) << 8) | (k6_not_green4(w[9], w[10], w[11], v_lo) << 12);
+                ng = k6_not_green4(w[0], w[1], w[2]) | (k6_not_green4(w[3], w[4], w[5]) << 4) |
+                     (k6_not_green4(w[6], w[7], w[8]) << 8) | (k6_not_green4(w[9], w[10], w[11]) << 12);
             }
             const int yra = abs(y), yrow = min(yra, 2 * H - 2 - yra);
             if (y + 1 <= r1) load_row(y + 1);
@@ -250,7 +249,7 @@ __global__ void __launch_bounds__(K6_WARPS * 32, 5) k6_strip(const uint8_t *__re
                 const int diff = gg - min(b, r);
                 const int s = (diff * __ldg(sdiv + gg) + (1 << 11)) >> 12;
                 const int h = ((b - r + 2 * diff) * __ldg(hdiv + diff) + (1 << 11)) >> 12;
-                green += (s >= s_lo && h >= h_lo && h <= h_hi) ? 1u : 0u;
+                green += (gg >= v_lo && s >= s_lo && h >= h_lo && h <= h_hi) ? 1u : 0u;
             }
         };
         for (int y = r0 - 1;;) {
