@@ -850,23 +850,68 @@ __global__ void __launch_bounds__(416, 2) k4_ppht_v3(const uint32_t *__restrict_
                         for (int base = 0;; base += gsteps) {
                             if (k < 2 && !s_wdone[k]) {
                                 unsigned hb[WPT], ibb[WPT];
+                                // all WPT mask words are requested before any is looked at (one L2 round trip, not WPT)
+                                int sh[WPT];
+                                bool ibv[WPT], roi[WPT];
+                                uint32_t mw[WPT];
 #pragma unroll
                                 for (int j = 0; j < WPT; j++) {
                                     int j1, i1;
                                     step_pixel(w, k, base + (wl * WPT + j) * 32 + lane, j1, i1);
-                                    const bool ib = j1 >= 0 && j1 < g.W && i1 >= 0 && i1 < g.H;
-                                    bool hit = false;
-                                    if (ib && i1 >= g.by0 && i1 < g.by1)
-                                        hit = ((__ldcg(&pm[(i1 - g.by0) * WW + (j1 >> 5)]) >> (j1 & 31)) & 1u) != 0;
-                                    ibb[j] = __ballot_sync(0xffffffffu, ib);
-                                    hb[j] = __ballot_sync(0xffffffffu, hit);
+                                    ibv[j] = j1 >= 0 && j1 < g.W && i1 >= 0 && i1 < g.H;
+                                    roi[j] = ibv[j] && i1 >= g.by0 && i1 < g.by1;
+                                    sh[j] = j1 & 31;
+                                    mw[j] = __ldcg(&pm[roi[j] ? (i1 - g.by0) * WW + (j1 >> 5) : 0]);
+                                }
+#pragma unroll
+                                for (int j = 0; j < WPT; j++) {
+                                    ibb[j] = __ballot_sync(0xffffffffu, ibv[j]);
+                                    hb[j] = __ballot_sync(0xffffffffu, roi[j] && ((mw[j] >> sh[j]) & 1u));
                                 }
                                 if (lane == 0)
 #pragma unroll
                                     for (int j = 0; j < WPT; j++) { s_whit[k][wl * WPT + j] = hb[j]; s_wib[k][wl * WPT + j] = ibb[j]; }
                             }
                             bar_v();
-                            if (tid < 2 && !s_wdone[tid] && (nvw >= 2 || tid == k)) {   // gap logic over this round's bit string
+                            const bool warp_gap = nvw >= 2 && hp.max_gap >= 31;       // a word per lane, see below
+                            if (warp_gap && wid < 2 && !s_wdone[wid]) {
+                                // cv2's gap logic over this round's bit string, a 32-step word per lane: with max_gap >= 31
+                                // only the distance from the last hit before a word to the word's first hit (and to the
+                                // word's end) can stop the walk, and "last hit so far" is a prefix maximum
+                                const int kk = wid, nq = half * WPT, NONE = -0x40000000;
+                                unsigned Hh = lane < nq ? s_whit[kk][lane] : 0u;
+                                const unsigned IB = lane < nq ? s_wib[kk][lane] : 0xFFFFFFFFu;
+                                const int limit = (~IB) ? __ffs(~IB) - 1 : 32;
+                                if (limit < 32) Hh &= (1u << limit) - 1u;
+                                const int b32 = base + 32 * lane;
+                                const int lastpos = Hh ? b32 + 31 - __clz(Hh) : NONE;
+                                int run = lastpos;
+                                for (int o2 = 1; o2 < 32; o2 <<= 1) {
+                                    const int t2 = __shfl_up_sync(0xffffffffu, run, o2);
+                                    if (lane >= o2) run = max(run, t2);
+                                }
+                                int last_in = __shfl_up_sync(0xffffffffu, run, 1);
+                                if (lane == 0) last_in = NONE;
+                                last_in = max(last_in, s_wlast[kk]);
+                                const bool c1 = Hh && (b32 + __ffs(Hh) - 1 - last_in > hp.max_gap + 1);
+                                const int last_out = (Hh && !c1) ? lastpos : last_in;
+                                const bool c2 = !c1 && (limit < 32 || b32 + 31 - last_out > hp.max_gap);
+                                const unsigned db = __ballot_sync(0xffffffffu, lane < nq && (c1 || c2));
+                                const int q = db ? __ffs(db) - 1 : nq - 1;
+                                const int last = __shfl_sync(0xffffffffu, (db && c1) ? last_in : last_out, q);
+                                if (lane == 0) {
+                                    s_wrounds[kk]++;
+                                    s_wlast[kk] = last;
+                                    if (db) {
+                                        s_wdone[kk] = 1;
+                                        int j1, i1;
+                                        step_pixel(w, kk, last, j1, i1);
+                                        s_end[kk][0] = j1; s_end[kk][1] = i1;
+                                        s_nsteps[kk] = last + 1;
+                                    }
+                                }
+                            }
+                            if (!warp_gap && tid < 2 && !s_wdone[tid] && (nvw >= 2 || tid == k)) {   // serial form (short max_gap)
                                 const int kk = tid;
                                 s_wrounds[kk]++;
                                 int last = s_wlast[kk];
