@@ -967,21 +967,24 @@ __global__ void __launch_bounds__(416, 2) k4_ppht_v3(const uint32_t *__restrict_
                         nl++;
                     }
                 }
-                for (int k = 0; k < 2; k++) {                         // pass 2: clear, and un-vote if good
-                    const int ns = s_nsteps[k];
+                {                                                     // pass 2: clear, and un-vote if good
+                    // both directions share the rounds: virtual step v < ns0 is step v of direction 0, the rest belong
+                    // to direction 1 (whose step 0 is the trigger pixel again and is left to direction 0)
+                    const int ns0 = s_nsteps[0], nst = ns0 + s_nsteps[1];
+                    const bool bits0 = s_wrounds[0] == 1, bits1 = s_wrounds[1] == 1;
                     const int per_round = min(4 * NVT, HITS_CAP);
-                    for (int base = 0; base < ns; base += per_round) {
+                    for (int base = 0; base < nst; base += per_round) {
                         if (tid == 0) s_nhits = 0;
                         bar_v();
                         // A walk that fit one pass-1 round left its hit bits in shared memory: they are exactly the set
                         // mask pixels along the line (the private mask has not changed since), so the mask is cleared
                         // with fire-and-forget atomics and nothing is read back.  Longer walks probe the mask again.
-                        const bool have_bits = s_wrounds[k] == 1;
-                        for (int s = base + tid; s < min(ns, base + per_round); s += NVT) {
+                        for (int v = base + tid; v < min(nst, base + per_round); v += NVT) {
+                            const int k = v >= ns0 ? 1 : 0, s = k ? v - ns0 : v;
+                            if (k == 1 && s == 0) continue;
                             int j1, i1;
-                            if (have_bits) {
-                                // step 0 is the trigger pixel itself in both directions: direction 0 has taken it
-                                if (((s_whit[k][s >> 5] >> (s & 31)) & 1u) && !(k == 1 && s == 0)) {
+                            if (k ? bits1 : bits0) {
+                                if ((s_whit[k][s >> 5] >> (s & 31)) & 1u) {
                                     step_pixel(w, k, s, j1, i1);
                                     atomicAnd(&pm[(i1 - g.by0) * WW + (j1 >> 5)], ~(1u << (j1 & 31)));
                                     const int h = atomicAdd(&s_nhits, 1);
