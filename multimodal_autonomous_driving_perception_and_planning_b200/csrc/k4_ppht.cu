@@ -551,7 +551,7 @@ __device__ __forceinline__ uint32_t cluster_reduce(XchgSlots *slots, unsigned &s
 
 constexpr int FLAG_CAP = 48;
 constexpr unsigned CBIAS = 0x4000u;
-constexpr int HITS_CAP = 256;
+constexpr int HITS_CAP = 512;        // cleared pixels of one un-vote round, packed (y << 16) | x
 constexpr int WPT = 4;             // pass-1 walk steps per thread per round
 
 __device__ __forceinline__ int scell_add(uint32_t *cells32, int cell, int delta)   // value BEFORE the add
@@ -580,7 +580,7 @@ __global__ void __launch_bounds__(416, 2) k4_ppht_v3(const uint32_t *__restrict_
     __shared__ uint32_t s_buf[2][BATCH3];
     __shared__ uint32_t s_rnd[BATCH3];
     __shared__ float s_fx[BATCH3], s_fy[BATCH3];     // batch points as float32, converted once
-    __shared__ float s_hx[HITS_CAP], s_hy[HITS_CAP];
+    __shared__ uint32_t s_hit[HITS_CAP];
     __shared__ XchgSlots s_slots;
     __shared__ int s_trig, s_nflag;
     __shared__ int s_flag_cell[FLAG_CAP], s_flag_slot[FLAG_CAP];
@@ -988,7 +988,7 @@ __global__ void __launch_bounds__(416, 2) k4_ppht_v3(const uint32_t *__restrict_
                                     step_pixel(w, k, s, j1, i1);
                                     atomicAnd(&pm[(i1 - g.by0) * WW + (j1 >> 5)], ~(1u << (j1 & 31)));
                                     const int h = atomicAdd(&s_nhits, 1);
-                                    s_hx[h] = (float)j1; s_hy[h] = (float)i1;
+                                    s_hit[h] = ((uint32_t)i1 << 16) | (uint32_t)j1;
                                 }
                                 continue;
                             }
@@ -997,15 +997,17 @@ __global__ void __launch_bounds__(416, 2) k4_ppht_v3(const uint32_t *__restrict_
                                 const uint32_t bit = 1u << (j1 & 31);
                                 if (atomicAnd(&pm[(i1 - g.by0) * WW + (j1 >> 5)], ~bit) & bit) {
                                     const int h = atomicAdd(&s_nhits, 1);
-                                    s_hx[h] = (float)j1; s_hy[h] = (float)i1;
+                                    s_hit[h] = ((uint32_t)i1 << 16) | (uint32_t)j1;
                                 }
                             }
                         }
                         bar_v();
                         if (s_good && active) {
                             const int nh = s_nhits;
-                            for (int h = sub; h < nh; h += tpa)
-                                scell_add(cells32, cell0 + rho_f(s_hx[h], s_hy[h], cs, sn), -1);
+                            for (int h = sub; h < nh; h += tpa) {
+                                const uint32_t p = s_hit[h];
+                                scell_add(cells32, cell0 + rho_f((float)(p & 0xFFFFu), (float)(p >> 16), cs, sn), -1);
+                            }
                         }
                         bar_v();
                     }
