@@ -225,19 +225,31 @@ def main():
     gatherer = RecordGatherer(n, dev) if world > 1 else None
 
     pending = [None]                                      # records of the previous step, not gathered yet
+    queued = [0]                                          # batches in flight on the context
 
-    def step():
-        # The step's kernels are enqueued first; the previous step's record gather (the path's only collective, NCCL
-        # over NVLink) is issued while they run, so its host-side cost is not GPU idle time.  flush() gathers the
-        # last step's records; K steps = K gathers inside the timed region.
-        ctx.enqueue(frames_dev.data_ptr(), n, None, 1, prev_fit, prev_valid, 0.7, 1 - 0.7)
+    def step(last=False):
+        # Streaming form of the C ABI: the next batch is enqueued before the previous one is collected, with the EMA
+        # state carried on the device (exactly the state chain of calling detect() frame after frame), so the GPU goes
+        # from one batch's last kernel to the next batch's first without waiting for the host.  All batches run in
+        # order on one stream; nothing overlaps.  The previous step's record gather (the path's only collective, NCCL
+        # over NVLink) is issued while the kernels run.  `last` ends a run of steps: K steps = K batches + K gathers.
+        if queued[0] == 0:
+            ctx.enqueue(frames_dev.data_ptr(), n, None, 1, prev_fit, prev_valid, 0.7, 1 - 0.7)   # explicit state
+            queued[0] += 1
+        if not last:
+            ctx.enqueue(frames_dev.data_ptr(), n, None, 1, None, None, 0.7, 1 - 0.7)            # queued behind it
+            queued[0] += 1
         if world > 1 and pending[0] is not None:
             gatherer.gather(pending[0], to_host=False)
         recs = ctx.collect(prev_fit, prev_valid)
+        queued[0] -= 1
         pending[0] = recs
         return recs
 
     def flush():
+        while queued[0]:
+            ctx.collect(prev_fit, prev_valid)
+            queued[0] -= 1
         if world > 1 and pending[0] is not None:
             gatherer.gather(pending[0], to_host=False)
             stream.wait_stream(torch.cuda.current_stream(dev))   # the timing event below fires after the gather
@@ -250,8 +262,9 @@ def main():
 
     sampler = ClockSampler(local) if rank == 0 else None
     t_load0 = time.perf_counter()
-    for _ in range(max(args.warmup, 3)):
-        recs = step()
+    nw = max(args.warmup, 3)
+    for i in range(nw):
+        recs = step(last=(i == nw - 1))
     flush()
     found = int(recs["side"]["valid"].sum())
 
@@ -263,8 +276,8 @@ def main():
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t0 = time.perf_counter()
     e0.record(stream)
-    for _ in range(args.steps):
-        step()
+    for i in range(args.steps):
+        step(last=(i == args.steps - 1))
         ms, ln = ctx.stage_ms()
         for k in stage_sum:
             stage_sum[k] += ms[k]

@@ -116,7 +116,13 @@ LANE_API int lane_detect_batch(lane_ctx *ctx, const uint8_t *frames, int frames_
                       lane_record *out);
 
 /* Asynchronous split of the above for pipelined callers: enqueue (device frames only; records
- * land in an internal pinned buffer), then collect.  The EMA state travels as above at collect. */
+ * land in an internal pinned buffer), then collect (waits for the OLDEST batch in flight and returns
+ * its records and the EMA state after it).
+ *   prev_fit / prev_valid given:  the batch starts from that state; one batch in flight at a time.
+ *   prev_fit = prev_valid = NULL: the batch continues from the state the previous batch left on the
+ *       device (the streaming case: the detector object's prev_*_fit simply stays on the GPU), and a
+ *       second batch may be queued behind the first -- enqueue, enqueue, collect, enqueue, collect, ...
+ *       -- so the device never waits for the host between batches.  Batches run in order on one stream. */
 LANE_API int lane_detect_enqueue(lane_ctx *ctx, const uint8_t *frames_dev, int n, const int32_t *stream_id,
                         int n_streams, const double *prev_fit, const uint8_t *prev_valid);
 LANE_API int lane_detect_collect(lane_ctx *ctx, double *prev_fit, uint8_t *prev_valid, lane_record *out);

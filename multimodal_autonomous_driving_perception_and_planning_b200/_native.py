@@ -153,6 +153,7 @@ class LaneContext:
         low, high = threshold_lut()
         self._check(L.lane_set_threshold_lut(self._h, _ptr(low), _ptr(high)))
         self._records = np.zeros(max_batch, RECORD_DTYPE)
+        self._inflight = []                       # sizes of the batches in flight, oldest first
 
     def _check(self, rc):
         if rc != 0:
@@ -205,16 +206,21 @@ class LaneContext:
         return self._records[:n].copy()
 
     def enqueue(self, frames_ptr: int, n: int, stream_id, n_streams, prev_fit, prev_valid, smoothing, one_minus):
+        """Asynchronous form for device-resident frames.  With ``prev_fit`` / ``prev_valid`` the batch starts from that
+        state (one batch in flight).  With both ``None`` it continues from the state the previous batch left on the
+        device, and a second batch may be queued behind the first (enqueue, enqueue, collect, enqueue, collect, ...):
+        the device then never waits for the host between batches."""
         L = lib()
         self._check(L.lane_set_smoothing(self._h, float(smoothing), float(one_minus)))
         sid = None if stream_id is None else np.ascontiguousarray(stream_id, dtype=np.int32)
         self._check(L.lane_detect_enqueue(self._h, C.c_void_p(frames_ptr), n, _ptr(sid), n_streams,
                                           _ptr(prev_fit), _ptr(prev_valid)))
-        self._n_inflight = n
+        self._inflight.append(n)
 
     def collect(self, prev_fit, prev_valid) -> np.ndarray:
+        """Waits for the oldest batch in flight; ``prev_fit`` / ``prev_valid`` receive the state after it."""
         self._check(lib().lane_detect_collect(self._h, _ptr(prev_fit), _ptr(prev_valid), _ptr(self._records)))
-        return self._records[:self._n_inflight].copy()
+        return self._records[:self._inflight.pop(0)].copy()
 
     def stage_ms(self):
         ms = np.zeros(NUM_STAGES, np.float32)

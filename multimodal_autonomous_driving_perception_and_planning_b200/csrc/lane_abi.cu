@@ -73,9 +73,7 @@ struct lane_ctx {
     double *d_prev_fit = nullptr;
     uint8_t *d_prev_valid = nullptr;
     int stream_cap = 0;
-    lane_record *d_records = nullptr, *h_records = nullptr;   // h_records pinned
-    double *h_prev_fit = nullptr;
-    uint8_t *h_prev_valid = nullptr;
+    lane_record *d_records = nullptr;
     int32_t *d_std_accum = nullptr;
     int2 *d_peaks = nullptr;
     int *d_n_peaks = nullptr;
@@ -83,14 +81,23 @@ struct lane_ctx {
     int force_tile = 0;               // LANE_B200_K1=tile forces the generic K1 kernel (A/B checks)
     int peaks_cap = 0;
 
-    // last call
+    // Up to two batches may be in flight on the context's stream (enqueue, enqueue, collect, enqueue, collect ...): the
+    // device never waits for the host between them.  Each has its own pinned result buffers and timing events.
+    struct slot_t {
+        lane_record *h_records = nullptr;            // pinned
+        double *h_prev_fit = nullptr;                // pinned: state in (explicit mode) and state out
+        uint8_t *h_prev_valid = nullptr;
+        cudaEvent_t ev[LANE_NUM_STAGES + 1] = {};
+        cudaEvent_t done = nullptr;
+        int n = 0, S = 0;
+        bool timed = false;
+        int32_t launches[LANE_NUM_STAGES] = {};
+    } slots[2];
+    int q_first = 0, q_count = 0, cur = 0;           // oldest batch in flight, batches in flight, slot being / last enqueued
+    bool state_on_device = false;                    // a batch has run: the EMA state of its streams is in d_prev_*
     const uint8_t *last_frames_dev = nullptr;
-    int last_n = 0, last_streams = 0;
-    bool in_flight = false;
-    cudaEvent_t ev[LANE_NUM_STAGES + 1] = {};
-    float stage_ms[LANE_NUM_STAGES] = {};
+    float stage_ms[LANE_NUM_STAGES] = {};            // of the batch collected last
     int32_t stage_launches[LANE_NUM_STAGES] = {};
-    bool timed = false;
 };
 
 namespace {
@@ -132,11 +139,14 @@ void free_all(lane_ctx *c)
     for (void *p : ptrs)
         if (p) cudaFree(p);
     free(c->h_roi);
-    if (c->h_records) cudaFreeHost(c->h_records);
-    if (c->h_prev_fit) cudaFreeHost(c->h_prev_fit);
-    if (c->h_prev_valid) cudaFreeHost(c->h_prev_valid);
-    for (auto &e : c->ev)
-        if (e) cudaEventDestroy(e);
+    for (auto &sl : c->slots) {
+        if (sl.h_records) cudaFreeHost(sl.h_records);
+        if (sl.h_prev_fit) cudaFreeHost(sl.h_prev_fit);
+        if (sl.h_prev_valid) cudaFreeHost(sl.h_prev_valid);
+        for (auto &e : sl.ev)
+            if (e) cudaEventDestroy(e);
+        if (sl.done) cudaEventDestroy(sl.done);
+    }
     for (auto &e : c->copy_ev)
         if (e) cudaEventDestroy(e);
     if (c->start_ev) cudaEventDestroy(c->start_ev);
@@ -154,13 +164,17 @@ int ensure_streams(lane_ctx *c, int S)
     if (S <= c->stream_cap) return LANE_OK;
     if (c->d_prev_fit) cudaFree(c->d_prev_fit);
     if (c->d_prev_valid) cudaFree(c->d_prev_valid);
-    if (c->h_prev_fit) cudaFreeHost(c->h_prev_fit);
-    if (c->h_prev_valid) cudaFreeHost(c->h_prev_valid);
-    c->d_prev_fit = nullptr; c->d_prev_valid = nullptr; c->h_prev_fit = nullptr; c->h_prev_valid = nullptr;
+    c->d_prev_fit = nullptr; c->d_prev_valid = nullptr;
     CU(dalloc(&c->d_prev_fit, (size_t)S * 6));
     CU(dalloc(&c->d_prev_valid, (size_t)S * 2));
-    CU(cudaMallocHost((void **)&c->h_prev_fit, sizeof(double) * S * 6));
-    CU(cudaMallocHost((void **)&c->h_prev_valid, (size_t)S * 2));
+    for (auto &sl : c->slots) {
+        if (sl.h_prev_fit) cudaFreeHost(sl.h_prev_fit);
+        if (sl.h_prev_valid) cudaFreeHost(sl.h_prev_valid);
+        sl.h_prev_fit = nullptr; sl.h_prev_valid = nullptr;
+        CU(cudaMallocHost((void **)&sl.h_prev_fit, sizeof(double) * S * 6));
+        CU(cudaMallocHost((void **)&sl.h_prev_valid, (size_t)S * 2));
+    }
+    c->state_on_device = false;
     c->stream_cap = S;
     return LANE_OK;
 }
@@ -184,7 +198,7 @@ int ensure_fallback(lane_ctx *c)
 
 int mark(lane_ctx *c, int i)
 {
-    if (c->profiling) CU(cudaEventRecord(c->ev[i], c->st));
+    if (c->profiling) CU(cudaEventRecord(c->slots[c->cur].ev[i], c->st));
     return LANE_OK;
 }
 
@@ -194,7 +208,7 @@ int run_stages(lane_ctx *c, const uint8_t *frames_dev, int off, int m, const int
     const LaneGeom &g = c->g;
     const int H = g.H, W = g.W;
     const size_t P = (size_t)H * W, WW = (W + 31) / 32, planes = (size_t)H * WW, o = (size_t)off;
-    int *L = c->stage_launches;
+    int *L = c->slots[c->cur].launches;
     int rc;
     const uint8_t *fr = frames_dev + o * P * 3;
     uint8_t *blur = c->d_blur + o * P;
@@ -264,13 +278,15 @@ int run_stages(lane_ctx *c, const uint8_t *frames_dev, int off, int m, const int
 int enqueue(lane_ctx *c, const uint8_t *frames, bool on_device, int n, const int32_t *stream_id, int S,
             const double *prev_fit, const uint8_t *prev_valid)
 {
-    int rc = ensure_streams(c, S);
-    if (rc) return rc;
+    int rc = LANE_OK;
+    lane_ctx::slot_t &sl = c->slots[c->cur];
     if (stream_id) CU(cudaMemcpyAsync(c->d_stream_id, stream_id, sizeof(int) * n, cudaMemcpyHostToDevice, c->st));
-    memcpy(c->h_prev_fit, prev_fit, sizeof(double) * S * 6);
-    memcpy(c->h_prev_valid, prev_valid, (size_t)S * 2);
-    CU(cudaMemcpyAsync(c->d_prev_fit, c->h_prev_fit, sizeof(double) * S * 6, cudaMemcpyHostToDevice, c->st));
-    CU(cudaMemcpyAsync(c->d_prev_valid, c->h_prev_valid, (size_t)S * 2, cudaMemcpyHostToDevice, c->st));
+    if (prev_fit) {                                  // explicit state: the caller's; otherwise what the last batch left on the device
+        memcpy(sl.h_prev_fit, prev_fit, sizeof(double) * S * 6);
+        memcpy(sl.h_prev_valid, prev_valid, (size_t)S * 2);
+        CU(cudaMemcpyAsync(c->d_prev_fit, sl.h_prev_fit, sizeof(double) * S * 6, cudaMemcpyHostToDevice, c->st));
+        CU(cudaMemcpyAsync(c->d_prev_valid, sl.h_prev_valid, (size_t)S * 2, cudaMemcpyHostToDevice, c->st));
+    }
     const int32_t *sid = stream_id ? c->d_stream_id : nullptr;
     const uint8_t *frames_dev = frames;
     if (on_device) {
@@ -332,16 +348,18 @@ int enqueue(lane_ctx *c, const uint8_t *frames, bool on_device, int n, const int
         }
     }
     rc = mark(c, LANE_STAGE_D2H); if (rc) return rc;
-    CU(cudaMemcpyAsync(c->h_records, c->d_records, sizeof(lane_record) * n, cudaMemcpyDeviceToHost, c->st));
-    CU(cudaMemcpyAsync(c->h_prev_fit, c->d_prev_fit, sizeof(double) * S * 6, cudaMemcpyDeviceToHost, c->st));
-    CU(cudaMemcpyAsync(c->h_prev_valid, c->d_prev_valid, (size_t)S * 2, cudaMemcpyDeviceToHost, c->st));
+    CU(cudaMemcpyAsync(sl.h_records, c->d_records, sizeof(lane_record) * n, cudaMemcpyDeviceToHost, c->st));
+    CU(cudaMemcpyAsync(sl.h_prev_fit, c->d_prev_fit, sizeof(double) * S * 6, cudaMemcpyDeviceToHost, c->st));
+    CU(cudaMemcpyAsync(sl.h_prev_valid, c->d_prev_valid, (size_t)S * 2, cudaMemcpyDeviceToHost, c->st));
     rc = mark(c, LANE_NUM_STAGES); if (rc) return rc;
     CU(cudaGetLastError());
     c->last_frames_dev = frames_dev;
-    c->last_n = n;
-    c->last_streams = S;
-    c->in_flight = true;
-    c->timed = c->profiling && on_device;
+    CU(cudaEventRecord(sl.done, c->st));
+    sl.n = n;
+    sl.S = S;
+    sl.timed = c->profiling && on_device;
+    c->state_on_device = true;
+    c->q_count++;
     return LANE_OK;
 }
 
@@ -349,9 +367,21 @@ int check_call(lane_ctx *c, const void *frames, int n, int S, const void *pf, co
 {
     if (!c) return LANE_ERR_INVALID;
     if (!frames || n <= 0 || n > c->max_batch) return fail(c, LANE_ERR_INVALID, "bad batch: n=%d (max_batch=%d)", n, c->max_batch);
-    if (S <= 0 || !pf || !pv) return fail(c, LANE_ERR_INVALID, "bad stream state: n_streams=%d", S);
+    if (S <= 0 || (!pf) != (!pv)) return fail(c, LANE_ERR_INVALID, "bad stream state: n_streams=%d", S);
     if (!c->have_roi || !c->have_lut) return fail(c, LANE_ERR_STATE, "lane_set_roi_mask and lane_set_threshold_lut must be called first");
-    if (c->in_flight) return fail(c, LANE_ERR_STATE, "a batch is already in flight; call lane_detect_collect");
+    if (pf) {          // explicit state is staged through host buffers: one batch at a time
+        if (c->q_count) return fail(c, LANE_ERR_STATE, "a batch is already in flight; call lane_detect_collect");
+    } else {           // state carried on the device: a second batch may queue behind the first
+        if (c->q_count >= 2) return fail(c, LANE_ERR_STATE, "two batches are already in flight; call lane_detect_collect");
+        if (!c->state_on_device || S > c->stream_cap)
+            return fail(c, LANE_ERR_STATE, "no state on the device for %d streams: pass prev_fit / prev_valid once", S);
+    }
+    {
+        int rc = c->q_count ? LANE_OK : ensure_streams(c, S);
+        if (rc) return rc;
+    }
+    c->cur = (c->q_first + c->q_count) & 1;
+    memset(c->slots[c->cur].launches, 0, sizeof(c->slots[c->cur].launches));
     return LANE_OK;
 }
 
@@ -401,7 +431,10 @@ int lane_ctx_create(int device, int height, int width, int max_batch, int max_se
         }                                                                                               \
     } while (0)
     CUB(cudaStreamCreateWithFlags(&ctx->st, cudaStreamNonBlocking));
-    for (auto &e : ctx->ev) CUB(cudaEventCreate(&e));
+    for (auto &sl : ctx->slots) {
+        for (auto &e : sl.ev) CUB(cudaEventCreate(&e));
+        CUB(cudaEventCreateWithFlags(&sl.done, cudaEventDisableTiming));
+    }
     CUB(dalloc(&ctx->d_blur, B * P));
     const size_t WW = (width + 31) / 32;
     CUB(dalloc(&ctx->d_roi_bits, (size_t)height * WW));
@@ -433,7 +466,7 @@ int lane_ctx_create(int device, int height, int width, int max_batch, int max_se
         e = getenv("LANE_B200_K2");
         ctx->force_generic_k2 = e && !strcmp(e, "generic");
     }
-    CUB(cudaMallocHost((void **)&ctx->h_records, sizeof(lane_record) * B));
+    for (auto &sl : ctx->slots) CUB(cudaMallocHost((void **)&sl.h_records, sizeof(lane_record) * B));
     CUB(cudaMemset(ctx->d_records, 0, sizeof(lane_record) * B));
     lane_upload_tables();
     lane_upload_sample_rows(height);
@@ -570,7 +603,7 @@ void *lane_ctx_stream(lane_ctx *c) { return c ? (void *)c->st : nullptr; }
 int lane_ctx_set_stream(lane_ctx *c, void *cuda_stream)
 {
     if (!c) return LANE_ERR_INVALID;
-    if (c->in_flight) return fail(c, LANE_ERR_STATE, "cannot switch streams with a batch in flight");
+    if (c->q_count) return fail(c, LANE_ERR_STATE, "cannot switch streams with a batch in flight");
     if (c->own_stream && c->st) { cudaStreamSynchronize(c->st); cudaStreamDestroy(c->st); }
     c->st = (cudaStream_t)cuda_stream;
     c->own_stream = false;
@@ -587,23 +620,25 @@ int lane_detect_enqueue(lane_ctx *c, const uint8_t *frames_dev, int n, const int
         for (int i = 0; i < n; i++)
             if (stream_id[i] < 0 || stream_id[i] >= n_streams)
                 return fail(c, LANE_ERR_INVALID, "stream_id[%d]=%d outside [0,%d)", i, stream_id[i], n_streams);
-    memset(c->stage_launches, 0, sizeof(c->stage_launches));
-    if (c->profiling) CU(cudaEventRecord(c->ev[LANE_STAGE_H2D], c->st));
+    if (c->profiling) CU(cudaEventRecord(c->slots[c->cur].ev[LANE_STAGE_H2D], c->st));
     return enqueue(c, frames_dev, true, n, stream_id, n_streams, prev_fit, prev_valid);
 }
 
 int lane_detect_collect(lane_ctx *c, double *prev_fit, uint8_t *prev_valid, lane_record *out)
 {
     if (!c || !out || !prev_fit || !prev_valid) return LANE_ERR_INVALID;
-    if (!c->in_flight) return fail(c, LANE_ERR_STATE, "no batch in flight");
+    if (!c->q_count) return fail(c, LANE_ERR_STATE, "no batch in flight");
     CU(cudaSetDevice(c->device));
-    c->in_flight = false;
-    CU(cudaStreamSynchronize(c->st));
-    memcpy(out, c->h_records, sizeof(lane_record) * c->last_n);
-    memcpy(prev_fit, c->h_prev_fit, sizeof(double) * c->last_streams * 6);
-    memcpy(prev_valid, c->h_prev_valid, (size_t)c->last_streams * 2);
-    if (c->timed)
-        for (int i = 0; i < LANE_NUM_STAGES; i++) CU(cudaEventElapsedTime(&c->stage_ms[i], c->ev[i], c->ev[i + 1]));
+    lane_ctx::slot_t &sl = c->slots[c->q_first];     // the oldest batch; a younger one keeps running
+    c->q_first ^= 1;
+    c->q_count--;
+    CU(cudaEventSynchronize(sl.done));
+    memcpy(out, sl.h_records, sizeof(lane_record) * sl.n);
+    memcpy(prev_fit, sl.h_prev_fit, sizeof(double) * sl.S * 6);
+    memcpy(prev_valid, sl.h_prev_valid, (size_t)sl.S * 2);
+    memcpy(c->stage_launches, sl.launches, sizeof(c->stage_launches));
+    if (sl.timed)
+        for (int i = 0; i < LANE_NUM_STAGES; i++) CU(cudaEventElapsedTime(&c->stage_ms[i], sl.ev[i], sl.ev[i + 1]));
     return LANE_OK;
 }
 
@@ -618,8 +653,7 @@ int lane_detect_batch(lane_ctx *c, const uint8_t *frames, int frames_on_device, 
         for (int i = 0; i < n; i++)
             if (stream_id[i] < 0 || stream_id[i] >= n_streams)
                 return fail(c, LANE_ERR_INVALID, "stream_id[%d]=%d outside [0,%d)", i, stream_id[i], n_streams);
-    memset(c->stage_launches, 0, sizeof(c->stage_launches));
-    if (c->profiling) CU(cudaEventRecord(c->ev[LANE_STAGE_H2D], c->st));
+    if (c->profiling) CU(cudaEventRecord(c->slots[c->cur].ev[LANE_STAGE_H2D], c->st));
     rc = enqueue(c, frames, frames_on_device != 0, n, stream_id, n_streams, prev_fit, prev_valid);
     if (rc) return rc;
     return lane_detect_collect(c, prev_fit, prev_valid, out);
@@ -636,8 +670,9 @@ int lane_get_stage_ms(lane_ctx *c, float ms[LANE_NUM_STAGES], int32_t launches[L
 int lane_debug_tap(lane_ctx *c, int what, int fi, void *host_out, size_t capacity, size_t *bytes_written)
 {
     if (!c || !host_out) return LANE_ERR_INVALID;
-    if (c->in_flight) return fail(c, LANE_ERR_STATE, "collect the batch before reading taps");
-    if (fi < 0 || fi >= c->last_n) return fail(c, LANE_ERR_INVALID, "frame_index %d outside last batch (%d)", fi, c->last_n);
+    if (c->q_count) return fail(c, LANE_ERR_STATE, "collect the batch before reading taps");
+    const int last_n = c->slots[c->cur].n;
+    if (fi < 0 || fi >= last_n) return fail(c, LANE_ERR_INVALID, "frame_index %d outside last batch (%d)", fi, last_n);
     CU(cudaSetDevice(c->device));
     const LaneGeom &g = c->g;
     const size_t P = (size_t)g.H * g.W;
@@ -682,7 +717,7 @@ int lane_debug_tap(lane_ctx *c, int what, int fi, void *host_out, size_t capacit
         src = c->d_gray_dbg; bytes = P; break;
     case LANE_TAP_POINTS: {
         if (!c->debug || !c->d_points_dbg) return fail(c, LANE_ERR_STATE, "LANE_TAP_POINTS needs lane_set_debug(ctx,1) before detect");
-        int np = c->h_records[fi].n_roi_points;
+        int np = c->slots[c->cur].h_records[fi].n_roi_points;
         std::vector<uint32_t> packed(np);
         CU(cudaMemcpy(packed.data(), c->d_points_dbg + (size_t)fi * g.max_points, sizeof(uint32_t) * np, cudaMemcpyDeviceToHost));
         bytes = sizeof(int32_t) * 2 * np;
@@ -694,7 +729,7 @@ int lane_debug_tap(lane_ctx *c, int what, int fi, void *host_out, size_t capacit
     }
     case LANE_TAP_SEGMENTS:
         src = c->d_lines + (size_t)fi * g.max_segments * 4;
-        bytes = sizeof(int32_t) * 4 * c->h_records[fi].n_segments; break;
+        bytes = sizeof(int32_t) * 4 * c->slots[c->cur].h_records[fi].n_segments; break;
     default: return fail(c, LANE_ERR_INVALID, "unknown tap %d", what);
     }
     if (bytes > capacity) return fail(c, LANE_ERR_INVALID, "tap needs %zu bytes, capacity %zu", bytes, capacity);
@@ -707,8 +742,9 @@ int lane_hough_accumulator(lane_ctx *c, int fi, int32_t *accum_host, int thresho
                            int max_peaks, int *n_peaks)
 {
     if (!c) return LANE_ERR_INVALID;
-    if (c->in_flight) return fail(c, LANE_ERR_STATE, "collect the batch first");
-    if (fi < 0 || fi >= c->last_n) return fail(c, LANE_ERR_INVALID, "frame_index %d outside last batch (%d)", fi, c->last_n);
+    if (c->q_count) return fail(c, LANE_ERR_STATE, "collect the batch first");
+    const int last_n = c->slots[c->cur].n;
+    if (fi < 0 || fi >= last_n) return fail(c, LANE_ERR_INVALID, "frame_index %d outside last batch (%d)", fi, last_n);
     if (!c->debug || !c->d_points_dbg) return fail(c, LANE_ERR_STATE, "lane_hough_accumulator needs lane_set_debug(ctx,1) before detect");
     CU(cudaSetDevice(c->device));
     const LaneGeom &g = c->g;

@@ -495,3 +495,40 @@ def test_pageable_and_pinned_host_frames_give_identical_records():
         det.detect_batch(frames)
         assert det.last_records.tobytes() == want.tobytes()
     det.close()
+
+
+def test_two_batches_in_flight_with_state_on_the_device():
+    """enqueue / enqueue / collect / ... with the EMA state carried on the device gives the records of calling
+    detect_batch batch after batch on one detector (the reference's frame-after-frame state chain)."""
+    import torch
+    from multimodal_autonomous_driving_perception_and_planning_b200 import multi_camera_batch
+    frames = multi_camera_batch(1, 24, 640, 480)[0]
+    chunks = [frames[i:i + 6] for i in range(0, 24, 6)]
+    det = LaneDetector(max_batch=6)
+    want = []
+    for ch in chunks:
+        det.detect_batch(ch)
+        want.append(det.last_records.copy())
+    want_state = (det.prev_left_fit.copy(), det.prev_right_fit.copy())
+    det.close()
+
+    det = LaneDetector(max_batch=6)
+    ctx = det._context(480, 640, 6)
+    dev = [torch.from_numpy(ch).cuda() for ch in chunks]
+    pf, pv = np.zeros((1, 2, 3)), np.zeros((1, 2), np.uint8)
+    ctx.enqueue(dev[0].data_ptr(), 6, None, 1, pf, pv, 0.7, 1 - 0.7)            # explicit (empty) state
+    got = []
+    for i in range(4):
+        if i + 1 < 4:
+            ctx.enqueue(dev[i + 1].data_ptr(), 6, None, 1, None, None, 0.7, 1 - 0.7)   # queued behind batch i
+        got.append(ctx.collect(pf, pv))
+    for a, b in zip(got, want):
+        assert a.tobytes() == b.tobytes()
+    assert np.array_equal(pf[0, 0], want_state[0]) and np.array_equal(pf[0, 1], want_state[1]) and pv.all()
+    with pytest.raises(_native.LaneError):                                    # a third batch does not fit the queue
+        ctx.enqueue(dev[0].data_ptr(), 6, None, 1, None, None, 0.7, 1 - 0.7)
+        ctx.enqueue(dev[1].data_ptr(), 6, None, 1, None, None, 0.7, 1 - 0.7)
+        ctx.enqueue(dev[2].data_ptr(), 6, None, 1, None, None, 0.7, 1 - 0.7)
+    while ctx._inflight:
+        ctx.collect(pf, pv)
+    det.close()
