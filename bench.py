@@ -169,7 +169,7 @@ def main():
         vals = []
         t0 = time.perf_counter()
         for _ in range(args.steps):
-            fps, cores, total, slowest = cpu_reference_fps(64)     # bounded: ~1 s of 16-core work per step
+            fps, cores, total, slowest = cpu_reference_fps(128)    # bounded: ~1.5 s of 16-core work per step
             vals.append((fps, total, slowest))
         fps = sum(v[1] for v in vals) / sum(v[2] for v in vals)
         sample = (f"{vals[0][1]} frames/step ({vals[0][1] // cores} per core) of the same 1080p generator streams, "
