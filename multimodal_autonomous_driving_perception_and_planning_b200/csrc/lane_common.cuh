@@ -8,6 +8,9 @@
 //   K3  k3_hough.cu       standard Hough accumulator + peaks (north-star add-on)
 //   K4  k4_ppht.cu        exact cv2.HoughLinesP (:94-101)
 //   K5  k5_fit.cu         side split (:105-134), polyfit + EMA + points (:136-176), offset (:253-272)
+// Adjacent rows:
+//   K0  k0_resize.cu      cv2.resize of VideoDataLoader.read_frame (data/loaders/video_loader.py:108,128)
+//   K6  k6_frame_stats.cu mean / Laplacian variance / HSV green ratio of SceneClassifier (src/tagging/scene_classifier.py)
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
