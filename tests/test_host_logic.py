@@ -72,3 +72,21 @@ def test_draw_lanes_fill_and_in_place_behaviour():
     assert tuple(out[80, 30]) == (255, 0, 0) and tuple(out[80, 90]) == (0, 0, 255)
     only_left = d.draw_lanes(frame, left, None)
     assert only_left is frame and tuple(frame[80, 30]) == (255, 0, 0)   # the reference draws in place here
+
+
+def test_frame_ingest_and_scene_stats_validate_inputs_before_touching_the_gpu():
+    import cv2
+    import pytest
+    from multimodal_autonomous_driving_perception_and_planning_b200 import FrameIngest
+    from multimodal_autonomous_driving_perception_and_planning_b200.perception.scene_stats import SceneStatsAnalyzer
+    frames = np.zeros((2, 8, 8, 3), np.uint8)
+    assert FrameIngest(None).resize_batch(frames) is frames                      # target_size=None: no resize, as the loader
+    assert FrameIngest((4, 4)).target_size == (4, 4)
+    with pytest.raises(cv2.error):
+        FrameIngest((4, 4)).resize_batch(frames.astype(np.float32))
+    with pytest.raises(cv2.error):
+        FrameIngest((4, 4)).resize_batch(np.zeros((2, 8, 8, 2), np.uint8))
+    with pytest.raises(ValueError):
+        SceneStatsAnalyzer().analyze_batch(np.zeros((8, 8, 3), np.uint8))
+    with pytest.raises(ValueError):
+        SceneStatsAnalyzer().analyze_batch(frames.astype(np.int16))
