@@ -64,11 +64,11 @@ typedef struct lane_record {
     int32_t n_segments;             /* segments HoughLinesP returned (:94-101) */
     int32_t hysteresis_rounds;      /* propagation rounds the frame needed (diagnostic) */
     int32_t flags;                  /* LANE_FLAG_* */
-    int32_t reserved;
+    int32_t n_segments_found;       /* segments HoughLinesP found; > n_segments iff LANE_FLAG_SEGMENTS_TRUNCATED */
 } lane_record;
 
 #define LANE_FLAG_SEGMENTS_TRUNCATED 1   /* more segments than max_segments: extra ones dropped */
-#define LANE_FLAG_POINTS_TRUNCATED 2     /* a side had more than LANE_MAX_SIDE_SEGMENTS segments */
+#define LANE_FLAG_POINTS_TRUNCATED 2     /* a side had more segments than its capacity (= max_segments) */
 
 typedef struct lane_ctx lane_ctx;
 
@@ -129,8 +129,20 @@ LANE_API int lane_detect_collect(lane_ctx *ctx, double *prev_fit, uint8_t *prev_
 
 /* The context's CUDA stream (cudaStream_t as void*), so callers can record events on it. */
 LANE_API void *lane_ctx_stream(lane_ctx *ctx);
+/* Device copy of the records lane_detect_collect / lane_detect_batch returned last (lane_record[n]).  It stays valid
+ * until the batch AFTER the next one is enqueued (two result slots alternate), so a multi-GPU caller can hand it to
+ * NCCL without a host round trip (the path's only collective is the gather of these records); the
+ * context's stream must be made to wait for that read before the slot's next enqueue. */
+LANE_API const lane_record *lane_ctx_records_device(lane_ctx *ctx);
 /* Use a caller-owned stream (cudaStream_t) instead of the context's own. */
 LANE_API int lane_ctx_set_stream(lane_ctx *ctx, void *cuda_stream);
+
+/* Which kernel family the last batch ran on (bit set = the fast path; a cleared bit means the launch was not possible
+ * for this geometry or was rejected by the device, and the generic kernels produced the same results more slowly). */
+#define LANE_PATH_FUSED_EDGE 1      /* one fused gray + blur + histogram + Sobel + NMS kernel (aligned widths) */
+#define LANE_PATH_CLUSTER_CANNY 2   /* hysteresis + ROI + point list in one thread-block cluster per frame */
+#define LANE_PATH_PPHT_DSMEM 4      /* HoughLinesP accumulator in distributed shared memory */
+LANE_API int lane_ctx_last_paths(lane_ctx *ctx);
 
 /* ---- measurement ---------------------------------------------------------------------- */
 #define LANE_STAGE_H2D 0

@@ -21,6 +21,8 @@ NUM_STAGES = 7
 STAGE_NAMES = ("h2d", "blur_hist", "canny", "compact", "ppht", "fit", "d2h")
 TAP_BLUR, TAP_HIST, TAP_CLASS, TAP_EDGES, TAP_POINTS, TAP_SEGMENTS, TAP_GRAY = 1, 2, 3, 4, 5, 6, 7
 FLAG_SEGMENTS_TRUNCATED, FLAG_POINTS_TRUNCATED = 1, 2
+PATH_FUSED_EDGE, PATH_CLUSTER_CANNY, PATH_PPHT_DSMEM = 1, 2, 4
+PATH_ALL_FAST = 7
 
 
 class LaneSide(C.Structure):
@@ -33,7 +35,7 @@ class LaneRecord(C.Structure):
     _fields_ = [("side", LaneSide * 2), ("offset", C.c_double), ("offset_valid", C.c_int32),
                 ("median_x2", C.c_int32), ("low", C.c_int32), ("high", C.c_int32), ("n_edges", C.c_int32),
                 ("n_roi_points", C.c_int32), ("n_segments", C.c_int32), ("hysteresis_rounds", C.c_int32),
-                ("flags", C.c_int32), ("reserved", C.c_int32)]
+                ("flags", C.c_int32), ("n_segments_found", C.c_int32)]
 
 
 # numpy view of lane_record (same layout) so batches decode without a Python loop per field
@@ -42,7 +44,7 @@ SIDE_DTYPE = np.dtype([("valid", "<i4"), ("n_lines", "<i4"), ("raw", "<f8", (3,)
 RECORD_DTYPE = np.dtype([("side", SIDE_DTYPE, (2,)), ("offset", "<f8"), ("offset_valid", "<i4"),
                          ("median_x2", "<i4"), ("low", "<i4"), ("high", "<i4"), ("n_edges", "<i4"),
                          ("n_roi_points", "<i4"), ("n_segments", "<i4"), ("hysteresis_rounds", "<i4"),
-                         ("flags", "<i4"), ("reserved", "<i4")], align=True)
+                         ("flags", "<i4"), ("n_segments_found", "<i4")], align=True)
 assert RECORD_DTYPE.itemsize == C.sizeof(LaneRecord), (RECORD_DTYPE.itemsize, C.sizeof(LaneRecord))
 
 
@@ -84,6 +86,8 @@ _PROTOS = {
     "lane_detect_collect": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "lane_ctx_stream": (C.c_void_p, [C.c_void_p]),
     "lane_ctx_set_stream": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "lane_ctx_records_device": (C.c_void_p, [C.c_void_p]),
+    "lane_ctx_last_paths": (C.c_int, [C.c_void_p]),
     "lane_set_profiling": (C.c_int, [C.c_void_p, C.c_int]),
     "lane_get_stage_ms": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "lane_debug_tap": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]),
@@ -152,6 +156,7 @@ class LaneContext:
         self._check(L.lane_set_roi_mask(self._h, _ptr(mask)))
         low, high = threshold_lut()
         self._check(L.lane_set_threshold_lut(self._h, _ptr(low), _ptr(high)))
+        self.settings = {"hough": (50, 50, 150), "lut": (low, high), "blur": True}   # what copy_settings_to replays
         self._records = np.zeros(max_batch, RECORD_DTYPE)
         self._inflight = []                       # sizes of the batches in flight, oldest first
 
@@ -174,10 +179,12 @@ class LaneContext:
     def set_hough_params(self, threshold=50, min_line_length=50, max_line_gap=150):
         self._check(lib().lane_set_hough_params(self._h, int(threshold), int(round(min_line_length)),
                                                 int(round(max_line_gap))))
+        self.settings["hough"] = (int(threshold), int(round(min_line_length)), int(round(max_line_gap)))
 
     def set_preprocess(self, gaussian_blur: bool):
         """False: skip the 5x5 blur, Canny runs on the plain grayscale plane (scene_classifier.py:145-146)."""
         self._check(lib().lane_set_preprocess(self._h, int(gaussian_blur)))
+        self.settings["blur"] = bool(gaussian_blur)
 
     def set_threshold_lut(self, low511: np.ndarray, high511: np.ndarray):
         low = np.ascontiguousarray(low511, dtype=np.uint8)
@@ -185,12 +192,27 @@ class LaneContext:
         if low.shape != (511,) or high.shape != (511,):
             raise ValueError("threshold LUTs must have 511 entries (one per 2*median)")
         self._check(lib().lane_set_threshold_lut(self._h, _ptr(low), _ptr(high)))
+        self.settings["lut"] = (low, high)
+
+    def copy_settings_to(self, other: "LaneContext"):
+        """Replay this context's Hough literals, threshold LUT and preprocess mode on another context."""
+        other.set_hough_params(*self.settings["hough"])
+        other.set_threshold_lut(*self.settings["lut"])
+        other.set_preprocess(self.settings["blur"])
 
     def set_profiling(self, on: bool):
         self._check(lib().lane_set_profiling(self._h, int(on)))
 
     def stream(self) -> int:
         return int(lib().lane_ctx_stream(self._h) or 0)
+
+    def last_paths(self) -> int:
+        """PATH_* bits of the kernels the last batch ran on (PATH_ALL_FAST when nothing fell back)."""
+        return int(lib().lane_ctx_last_paths(self._h))
+
+    def records_device_ptr(self) -> int:
+        """Device address of the records of the batch enqueued last (see lane_ctx_records_device)."""
+        return int(lib().lane_ctx_records_device(self._h) or 0)
 
     # ---- hot path
     def detect(self, frames, n: int, on_device: bool, stream_id, n_streams: int, prev_fit: np.ndarray,

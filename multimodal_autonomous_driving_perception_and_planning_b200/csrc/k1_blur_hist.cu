@@ -371,12 +371,7 @@ void launch_blur_hist(const uint8_t *frames, uint8_t *blur_out, uint32_t *hist, 
     }
     const bool aligned = (W % 16 == 0) && (((uintptr_t)frames | (uintptr_t)blur_out) % 16 == 0);
     if (aligned && !force_tile && H >= 4 && (size_t)H * W * 3 < ((size_t)1 << 32)) {
-        static int sms = 0;
-        if (!sms) {
-            int dev = 0;
-            cudaGetDevice(&dev);
-            cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        }
+        const int sms = lane_sm_count();
         // band height: 102 rows (3.9 % halo rows) when there is plenty of work, thinner when a small batch would
         // otherwise leave most of the sms*5*SWARPS warps without a task; the last sixteenth of the frames is cut into
         // bands a third as high to shorten the end-of-kernel tail
@@ -397,10 +392,10 @@ void launch_blur_hist(const uint8_t *frames, uint8_t *blur_out, uint32_t *hist, 
         static const bool use_ldg = !(getenv("LANE_B200_K1") && !strcmp(getenv("LANE_B200_K1"), "tma"));
         const size_t smem_ldg = SWARPS * 256 * 32;
         const size_t smem_tma = smem_ldg + SWARPS * RING * ROW_BYTES + SWARPS * RING * 8;
-        static bool configured = false;
-        if (!configured) {
+        static bool configured[LANE_MAX_DEVICES];
+        if (!configured[lane_cur_device()]) {
             cudaFuncSetAttribute(k1_strip<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tma);
-            configured = true;
+            configured[lane_cur_device()] = true;
         }
         static const int minb = getenv("LANE_K1_MINB") ? atoi(getenv("LANE_K1_MINB")) : 5;
         if (use_ldg && minb == 5) {

@@ -690,15 +690,12 @@ bool launch_canny_cluster(const uint8_t *blur, const uint32_t *hist, const uint8
         if (smem <= 200 * 1024 || G >= 16) break;
     }
     if (smem > 220 * 1024) return false;
-    static bool configured = false;
-    static int sms = 0;
-    if (!configured) {
+    static bool configured[LANE_MAX_DEVICES];
+    const int sms = lane_sm_count();
+    if (!configured[lane_cur_device()]) {
         cudaFuncSetAttribute(k2_canny_cluster, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
         cudaFuncSetAttribute(k2_canny_cluster, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        configured = true;
+        configured[lane_cur_device()] = true;
     }
     cudaMemsetAsync(task_counter, 0, sizeof(int), st);
     {

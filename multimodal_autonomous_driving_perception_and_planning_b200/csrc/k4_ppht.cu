@@ -1052,11 +1052,11 @@ bool launch_ppht_v3(const uint32_t *points, const int *n_points, const uint32_t 
     tpa = tpa < 1 ? 1 : (tpa > 8 ? 8 : tpa);
     const int nvw = (angles * tpa + 31) / 32;
     const size_t smem = (((size_t)cells_max * 2 + 15) & ~(size_t)15) + sizeof(uint32_t) * LIST_CAP3;
-    static bool configured = false;
-    if (!configured) {
+    static bool configured[LANE_MAX_DEVICES];
+    if (!configured[lane_cur_device()]) {
         cudaFuncSetAttribute(k4_ppht_v3, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
         cudaFuncSetAttribute(k4_ppht_v3, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
-        configured = true;
+        configured[lane_cur_device()] = true;
     }
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(n * G);

@@ -11,25 +11,9 @@
 //           truncated toward zero like astype(int32).
 #include "lane_common.cuh"
 
-__constant__ double c_sample_y[LANE_NUM_POINTS];
-
-void lane_upload_sample_rows(int H)
-{
-    // np.linspace(H * 0.6, H, 50): step = (stop - start) / 49; y = arange(50) * step + start; y[-1] = stop
-    double ys[LANE_NUM_POINTS];
-    const double start = (double)H * 0.6, stop = (double)H;
-    const double step = (stop - start) / (double)(LANE_NUM_POINTS - 1);
-    for (int i = 0; i < LANE_NUM_POINTS; i++) {
-        volatile double t = (double)i * step;   // keep the two roundings separate
-        ys[i] = t + start;
-    }
-    ys[LANE_NUM_POINTS - 1] = stop;
-    cudaMemcpyToSymbol(c_sample_y, ys, sizeof(ys));
-}
-
 namespace {
 
-constexpr int MAXP = 2 * LANE_MAX_SIDE_SEGMENTS;   // points per side
+constexpr int MAXP = 2 * LANE_MAX_SIDE_SEGMENTS;   // points per side held in shared memory
 
 __device__ __forceinline__ double warp_sum(double v)
 {
@@ -51,9 +35,13 @@ __device__ __forceinline__ void axpy(double *y, const double *x, double alpha, i
 }
 
 // one warp per (frame, side)
+// A side can receive every segment of the frame, so its capacity is max_segments: the five work columns live in
+// shared memory up to LANE_MAX_SIDE_SEGMENTS segments (the default context) and in a per-(frame, side) global
+// scratch for contexts created with a larger max_segments (dense frames; cv2.HoughLinesP itself has no cap).
 __global__ void __launch_bounds__(64) k5_fit(const int32_t *__restrict__ lines_all, const int *__restrict__ n_lines,
                                              double *__restrict__ raw, int *__restrict__ side_n,
-                                             int *__restrict__ side_flags, int W, int max_segments)
+                                             int *__restrict__ side_flags, double *__restrict__ big, int W,
+                                             int max_segments)
 {
     __shared__ double sA[2][4][MAXP];      // columns a0 a1 a2 and rhs, per side
     __shared__ double sy[2][MAXP];
@@ -63,6 +51,12 @@ __global__ void __launch_bounds__(64) k5_fit(const int32_t *__restrict__ lines_a
     int flags = 0;
     if (L > max_segments) { L = max_segments; flags |= LANE_FLAG_SEGMENTS_TRUNCATED; }
     double *a0 = sA[side][0], *a1 = sA[side][1], *a2 = sA[side][2], *bx = sA[side][3], *ys = sy[side];
+    const int side_cap = big ? max_segments : LANE_MAX_SIDE_SEGMENTS;
+    if (big) {
+        const size_t col = 2 * (size_t)max_segments;
+        double *b = big + ((size_t)f * 2 + side) * 5 * col;
+        a0 = b; a1 = b + col; a2 = b + 2 * col; bx = b + 3 * col; ys = b + 4 * col;
+    }
     const double cx = (double)W / 2.0;
 
     // ---- split (order preserved): both endpoints of every accepted segment become fit points
@@ -83,7 +77,7 @@ __global__ void __launch_bounds__(64) k5_fit(const int32_t *__restrict__ lines_a
         }
         unsigned bal = __ballot_sync(0xffffffffu, take);
         int pos = cnt + __popc(bal & ((1u << lane) - 1u));
-        if (take && pos < LANE_MAX_SIDE_SEGMENTS) {
+        if (take && pos < side_cap) {
             ys[2 * pos] = (double)y1; bx[2 * pos] = (double)x1;
             ys[2 * pos + 1] = (double)y2; bx[2 * pos + 1] = (double)x2;
         }
@@ -91,10 +85,10 @@ __global__ void __launch_bounds__(64) k5_fit(const int32_t *__restrict__ lines_a
     }
     __syncwarp();
     if (lane == 0) side_n[2 * f + side] = cnt;
-    if (cnt > LANE_MAX_SIDE_SEGMENTS) flags |= LANE_FLAG_POINTS_TRUNCATED;
+    if (cnt > side_cap) flags |= LANE_FLAG_POINTS_TRUNCATED;
     if (lane == 0 && flags) atomicOr(&side_flags[f], flags);
     if (cnt == 0) return;
-    const int n = 2 * min(cnt, LANE_MAX_SIDE_SEGMENTS);
+    const int n = 2 * min(cnt, side_cap);
 
     // ---- distinct-y census and column norms
     double ymin = 1e300, ymax = -1e300, s4 = 0.0, s2 = 0.0;
@@ -249,7 +243,8 @@ __device__ __forceinline__ int trunc_i32(double v)
 __global__ void __launch_bounds__(128) k5_points(lane_record *__restrict__ rec, const int4 *__restrict__ thr,
                                                  const int *__restrict__ n_edges, const int *__restrict__ n_points,
                                                  const int *__restrict__ n_lines, const int *__restrict__ rounds,
-                                                 const int *__restrict__ side_flags, int W, int max_segments)
+                                                 const int *__restrict__ side_flags, int W, int max_segments,
+                                                 double y_start, double y_step, double y_stop)
 {
     const int f = blockIdx.x, tid = threadIdx.x;
     lane_record *r = &rec[f];
@@ -257,7 +252,8 @@ __global__ void __launch_bounds__(128) k5_points(lane_record *__restrict__ rec, 
     if (i < LANE_NUM_POINTS) {
         lane_side *o = &r->side[side];
         if (o->valid) {
-            double y = c_sample_y[i];
+            // np.linspace(0.6 H, H, 50): y = arange(50) * step + start (two roundings), last sample = stop exactly
+            double y = i == LANE_NUM_POINTS - 1 ? y_stop : __dadd_rn(__dmul_rn((double)i, y_step), y_start);
             double x = __dadd_rn(__dmul_rn(o->coeffs[0], y), o->coeffs[1]);
             x = __dadd_rn(__dmul_rn(x, y), o->coeffs[2]);
             o->points[i][0] = trunc_i32(x);
@@ -287,9 +283,9 @@ __global__ void __launch_bounds__(128) k5_points(lane_record *__restrict__ rec, 
         r->n_roi_points = n_points[f];
         int nl = n_lines[f];
         r->n_segments = nl < max_segments ? nl : max_segments;
+        r->n_segments_found = nl;
         r->hysteresis_rounds = rounds[f];
         r->flags = side_flags[f];
-        r->reserved = 0;
     }
 }
 
@@ -301,10 +297,13 @@ void launch_fit(const int32_t *lines, const int *n_lines, LaneFitScratch fs, con
                 lane_record *records, LaneGeom g, int n, cudaStream_t st, int *launches)
 {
     cudaMemsetAsync(fs.side_flags, 0, sizeof(int) * n, st);
-    k5_fit<<<n, 64, 0, st>>>(lines, n_lines, fs.raw, fs.side_n, fs.side_flags, g.W, g.max_segments);
+    k5_fit<<<n, 64, 0, st>>>(lines, n_lines, fs.raw, fs.side_n, fs.side_flags, fs.big, g.W, g.max_segments);
     k5_ema<<<n_streams, 256, 0, st>>>(fs.raw, fs.side_n, stream_id, prev_fit, prev_valid, smooth, one_minus_smooth,
                                       records, n);
+    // np.linspace(H * 0.6, H, 50): step = (stop - start) / 49, evaluated per context (not a process-wide constant)
+    const double y_start = (double)g.H * 0.6, y_stop = (double)g.H;
+    const double y_step = (y_stop - y_start) / (double)(LANE_NUM_POINTS - 1);
     k5_points<<<n, 128, 0, st>>>(records, thr, n_edges, n_points, n_lines, rounds, fs.side_flags, g.W,
-                                 g.max_segments);
+                                 g.max_segments, y_start, y_step, y_stop);
     *launches += 3;
 }

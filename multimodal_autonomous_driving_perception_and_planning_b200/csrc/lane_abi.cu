@@ -12,8 +12,6 @@
 
 #include "lane_common.cuh"
 
-void lane_upload_sample_rows(int H);
-
 #define LANE_COPY_EVENTS 8
 
 static thread_local std::string g_create_error;
@@ -52,6 +50,7 @@ struct lane_ctx {
     uint8_t *d_cls = nullptr, *d_cls_dbg = nullptr, *d_roi = nullptr, *d_pmask = nullptr;
     uint8_t *h_roi = nullptr;
     bool fallback_ready = false, last_cluster = false;
+    int last_paths = 0;               // LANE_PATH_* of the chunk that ran last
     int force_generic_k2 = 0;         // LANE_B200_K2=generic forces the byte-map kernels (A/B checks)
     uint8_t *d_gray_dbg = nullptr;
     uint32_t *d_hist = nullptr, *d_points = nullptr, *d_points_dbg = nullptr;
@@ -73,7 +72,6 @@ struct lane_ctx {
     double *d_prev_fit = nullptr;
     uint8_t *d_prev_valid = nullptr;
     int stream_cap = 0;
-    lane_record *d_records = nullptr;
     int32_t *d_std_accum = nullptr;
     int2 *d_peaks = nullptr;
     int *d_n_peaks = nullptr;
@@ -85,6 +83,7 @@ struct lane_ctx {
     // device never waits for the host between them.  Each has its own pinned result buffers and timing events.
     struct slot_t {
         lane_record *h_records = nullptr;            // pinned
+        lane_record *d_records = nullptr;            // device copy, alive until this slot is enqueued again
         double *h_prev_fit = nullptr;                // pinned: state in (explicit mode) and state out
         uint8_t *h_prev_valid = nullptr;
         cudaEvent_t ev[LANE_NUM_STAGES + 1] = {};
@@ -93,6 +92,7 @@ struct lane_ctx {
         bool timed = false;
         int32_t launches[LANE_NUM_STAGES] = {};
     } slots[2];
+    int last_collected = 0;                          // slot of the batch lane_detect_collect returned last
     int q_first = 0, q_count = 0, cur = 0;           // oldest batch in flight, batches in flight, slot being / last enqueued
     bool state_on_device = false;                    // a batch has run: the EMA state of its streams is in d_prev_*
     const uint8_t *last_frames_dev = nullptr;
@@ -133,9 +133,9 @@ void free_all(lane_ctx *c)
     void *ptrs[] = {c->d_frames, c->d_blur, c->d_cls, c->d_cls_dbg, c->d_roi, c->d_pmask, c->d_gray_dbg, c->d_hist,
                     c->d_roi_bits, c->d_pmask_bits, c->d_edge_bits, c->d_dbg_c, c->d_dbg_s, c->d_accum16, c->d_win, c->d_win3, c->d_pmask_work,
                     c->d_points, c->d_points_dbg, c->d_lut, c->d_thr, c->d_seedsA, c->d_seedsB, c->d_seed_count,
-                    c->d_n_edges, c->d_n_points, c->d_rounds, c->d_n_lines, c->d_accum, c->d_lines, c->fit.raw,
+                    c->d_n_edges, c->d_n_points, c->d_rounds, c->d_n_lines, c->d_accum, c->d_lines, c->fit.raw, c->fit.big,
                     c->fit.side_n, c->fit.side_flags, c->d_stream_id, c->d_prev_fit, c->d_prev_valid,
-                    c->d_records, c->d_std_accum, c->d_peaks, c->d_n_peaks, c->d_task_counter};
+                    c->slots[0].d_records, c->slots[1].d_records, c->d_std_accum, c->d_peaks, c->d_n_peaks, c->d_task_counter};
     for (void *p : ptrs)
         if (p) cudaFree(p);
     free(c->h_roi);
@@ -246,6 +246,7 @@ int run_stages(lane_ctx *c, const uint8_t *frames_dev, int off, int m, const int
         launch_bytes_to_bits(cls, edge_bits, m, H, W, W, c->st, &L[LANE_STAGE_COMPACT]);
         launch_mask_rows(edge_bits, c->d_roi_bits, pmask_bits, g, m, c->st, &L[LANE_STAGE_COMPACT]);
     }
+    c->last_paths = (c->last_paths & LANE_PATH_FUSED_EDGE) | (c->last_cluster ? LANE_PATH_CLUSTER_CANNY : 0);
     if (c->debug)
         CU(cudaMemcpyAsync(c->d_points_dbg + o * g.max_points, points, sizeof(uint32_t) * (size_t)m * g.max_points,
                            cudaMemcpyDeviceToDevice, c->st));
@@ -263,12 +264,14 @@ int run_stages(lane_ctx *c, const uint8_t *frames_dev, int off, int m, const int
                                  c->d_win3, c->cells_max3, c->G3, lines, n_lines, g, c->hp, m, c->st, &L[LANE_STAGE_PPHT]);
         launch_ppht_v2(points, n_points, pmask_bits, c->d_accum16 + o * (c->cells_per_frame / 2), c->d_win,
                        c->cells_per_frame, lines, n_lines, g, c->hp, m, c->st, &L[LANE_STAGE_PPHT], v3 ? 1 : 0);
+        if (v3) c->last_paths |= LANE_PATH_PPHT_DSMEM;
     }
 
     if (timed) { rc = mark(c, LANE_STAGE_FIT); if (rc) return rc; }
-    LaneFitScratch fs{c->fit.raw + o * 6, c->fit.side_n + o * 2, c->fit.side_flags + o};
+    LaneFitScratch fs{c->fit.raw + o * 6, c->fit.side_n + o * 2, c->fit.side_flags + o,
+                      c->fit.big ? c->fit.big + o * 2 * 5 * 2 * (size_t)g.max_segments : nullptr};
     launch_fit(lines, n_lines, fs, stream_id_dev ? stream_id_dev + o : nullptr, S, c->d_prev_fit, c->d_prev_valid, c->smooth,
-               c->one_minus_smooth, thr, n_edges, n_points, rounds, c->d_records + o, g, m, c->st, &L[LANE_STAGE_FIT]);
+               c->one_minus_smooth, thr, n_edges, n_points, rounds, c->slots[c->cur].d_records + o, g, m, c->st, &L[LANE_STAGE_FIT]);
     return LANE_OK;
 }
 
@@ -348,7 +351,7 @@ int enqueue(lane_ctx *c, const uint8_t *frames, bool on_device, int n, const int
         }
     }
     rc = mark(c, LANE_STAGE_D2H); if (rc) return rc;
-    CU(cudaMemcpyAsync(sl.h_records, c->d_records, sizeof(lane_record) * n, cudaMemcpyDeviceToHost, c->st));
+    CU(cudaMemcpyAsync(sl.h_records, sl.d_records, sizeof(lane_record) * n, cudaMemcpyDeviceToHost, c->st));
     CU(cudaMemcpyAsync(sl.h_prev_fit, c->d_prev_fit, sizeof(double) * S * 6, cudaMemcpyDeviceToHost, c->st));
     CU(cudaMemcpyAsync(sl.h_prev_valid, c->d_prev_valid, (size_t)S * 2, cudaMemcpyDeviceToHost, c->st));
     rc = mark(c, LANE_NUM_STAGES); if (rc) return rc;
@@ -454,8 +457,13 @@ int lane_ctx_create(int device, int height, int width, int max_batch, int max_se
     CUB(dalloc(&ctx->fit.raw, B * 6));
     CUB(dalloc(&ctx->fit.side_n, B * 2));
     CUB(dalloc(&ctx->fit.side_flags, B));
+    if (g.max_segments > LANE_MAX_SIDE_SEGMENTS)      // a side can hold every segment: work columns in global memory
+        CUB(dalloc(&ctx->fit.big, B * 2 * 5 * 2 * (size_t)g.max_segments));
     CUB(dalloc(&ctx->d_stream_id, B));
-    CUB(dalloc(&ctx->d_records, B));
+    for (auto &sl : ctx->slots) {
+        CUB(dalloc(&sl.d_records, B));
+        CUB(cudaMemset(sl.d_records, 0, sizeof(lane_record) * B));
+    }
     CUB(dalloc(&ctx->d_task_counter, 4));
     {
         const char *e = getenv("LANE_B200_K1");
@@ -467,9 +475,7 @@ int lane_ctx_create(int device, int height, int width, int max_batch, int max_se
         ctx->force_generic_k2 = e && !strcmp(e, "generic");
     }
     for (auto &sl : ctx->slots) CUB(cudaMallocHost((void **)&sl.h_records, sizeof(lane_record) * B));
-    CUB(cudaMemset(ctx->d_records, 0, sizeof(lane_record) * B));
     lane_upload_tables();
-    lane_upload_sample_rows(height);
     CUB(cudaGetLastError());
     CUB(cudaDeviceSynchronize());
 #undef CUB
@@ -600,6 +606,10 @@ int lane_set_profiling(lane_ctx *c, int enabled)
 
 void *lane_ctx_stream(lane_ctx *c) { return c ? (void *)c->st : nullptr; }
 
+int lane_ctx_last_paths(lane_ctx *c) { return c ? c->last_paths : 0; }
+
+const lane_record *lane_ctx_records_device(lane_ctx *c) { return c ? c->slots[c->last_collected].d_records : nullptr; }
+
 int lane_ctx_set_stream(lane_ctx *c, void *cuda_stream)
 {
     if (!c) return LANE_ERR_INVALID;
@@ -630,6 +640,7 @@ int lane_detect_collect(lane_ctx *c, double *prev_fit, uint8_t *prev_valid, lane
     if (!c->q_count) return fail(c, LANE_ERR_STATE, "no batch in flight");
     CU(cudaSetDevice(c->device));
     lane_ctx::slot_t &sl = c->slots[c->q_first];     // the oldest batch; a younger one keeps running
+    c->last_collected = c->q_first;
     c->q_first ^= 1;
     c->q_count--;
     CU(cudaEventSynchronize(sl.done));

@@ -18,7 +18,7 @@
 #include "../../include/lane_b200.h"
 
 #define LANE_NUM_ANGLES 180
-#define LANE_MAX_SIDE_SEGMENTS 256   // per side; more sets LANE_FLAG_POINTS_TRUNCATED
+#define LANE_MAX_SIDE_SEGMENTS 256   // per side in shared memory; contexts with a larger max_segments use global scratch
 
 struct LaneGeom {
     int H, W;
@@ -32,6 +32,23 @@ struct LaneGeom {
 struct LaneHoughParams {
     int threshold, min_len, max_gap;
 };
+
+// Function attributes (dynamic shared memory limit, non-portable cluster size) and the SM count are per DEVICE, and one
+// process may drive several GPUs: "done once" flags are therefore arrays indexed by the current device.
+#define LANE_MAX_DEVICES 64
+static inline int lane_cur_device()
+{
+    int d = 0;
+    cudaGetDevice(&d);
+    return d & (LANE_MAX_DEVICES - 1);
+}
+static inline int lane_sm_count()
+{
+    static int sms[LANE_MAX_DEVICES];
+    const int d = lane_cur_device();
+    if (!sms[d]) cudaDeviceGetAttribute(&sms[d], cudaDevAttrMultiProcessorCount, d);
+    return sms[d];
+}
 
 // message returned by lane_last_error(NULL): context creation and the context-free entry points
 void lane_set_global_error(const char *msg);
@@ -98,6 +115,7 @@ struct LaneFitScratch {
     double *raw;        // [n][2][3]
     int *side_n;        // [n][2] segments per side (0 => None)
     int *side_flags;    // [n]
+    double *big;        // [n][2][5][2 * max_segments] work columns when max_segments > LANE_MAX_SIDE_SEGMENTS, else null
 };
 void launch_fit(const int32_t *lines, const int *n_lines, LaneFitScratch fs, const int *stream_id, int n_streams,
                 double *prev_fit, uint8_t *prev_valid, double smooth, double one_minus_smooth,

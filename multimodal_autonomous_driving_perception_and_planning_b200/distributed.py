@@ -65,31 +65,65 @@ def merge_stream_major(per_rank: Sequence[np.ndarray], n_streams: int, frames_pe
     return out
 
 
+class _DeviceBytes:
+    """Zero-copy view of raw device memory for ``torch.as_tensor`` (``__cuda_array_interface__``)."""
+
+    def __init__(self, ptr: int, nbytes: int):
+        self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (int(ptr), False), "version": 2}
+
+
 class RecordGatherer:
     """Fixed-size gather for steady-state serving: every rank contributes exactly ``n`` records per
-    call, buffers are allocated once (pinned staging + device payload), one collective per call."""
+    call, buffers are allocated once, one collective per call.
+
+    ``gather(local)`` takes the host records (staged through one of two pinned buffers; the copy of call k
+    is fenced by an event before buffer k % 2 is rewritten by call k + 2).  ``gather_device(ptr)`` takes the
+    device copy the native context keeps (``LaneContext.records_device_ptr()``): the records go from the
+    context's buffer straight into the collective, with no host round trip.  On the destination rank both return
+    the per-rank device buffers (``to_host=False``) or decoded ``RECORD_DTYPE`` arrays."""
 
     def __init__(self, n: int, device, dst: int = 0, group=None):
         import torch
         import torch.distributed as dist
         self.n, self.dst, self.group, self.device = n, dst, group, device
         self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
-        nbytes = n * RECORD_DTYPE.itemsize
-        self.stage = torch.empty(nbytes, dtype=torch.uint8).pin_memory() if device.type == "cuda" \
-            else torch.empty(nbytes, dtype=torch.uint8)
-        self.payload = torch.empty(nbytes, dtype=torch.uint8, device=device)
+        self.nbytes = nbytes = n * RECORD_DTYPE.itemsize
+        cuda = device.type == "cuda"
+        self.stage = [torch.empty(nbytes, dtype=torch.uint8).pin_memory() if cuda else torch.empty(nbytes, dtype=torch.uint8)
+                      for _ in range(2)]
+        self.payload = [torch.empty(nbytes, dtype=torch.uint8, device=device) for _ in range(2)]
+        self.copied = [None, None]                   # CUDA event after the H2D copy out of stage[i]
+        self.calls = 0
         self.bufs = [torch.empty(nbytes, dtype=torch.uint8, device=device) for _ in range(self.world)] \
             if self.rank == dst else None
 
-    def gather(self, local: np.ndarray, to_host: bool = True):
+    def _finish(self, payload, to_host):
         import torch.distributed as dist
-        if local.shape[0] != self.n or local.dtype != RECORD_DTYPE:
-            raise ValueError("RecordGatherer.gather expects exactly n RECORD_DTYPE records")
-        self.stage.numpy()[:] = np.ascontiguousarray(local).view(np.uint8).reshape(-1)
-        self.payload.copy_(self.stage, non_blocking=True)
-        dist.gather(self.payload, self.bufs, dst=self.dst, group=self.group)
+        dist.gather(payload, self.bufs, dst=self.dst, group=self.group)
         if self.rank != self.dst:
             return None
         if not to_host:
             return self.bufs
         return [b.cpu().numpy().view(RECORD_DTYPE).copy() for b in self.bufs]
+
+    def gather(self, local: np.ndarray, to_host: bool = True):
+        if local.shape[0] != self.n or local.dtype != RECORD_DTYPE:
+            raise ValueError("RecordGatherer.gather expects exactly n RECORD_DTYPE records")
+        k = self.calls & 1
+        self.calls += 1
+        if self.copied[k] is not None:
+            self.copied[k].synchronize()             # the DMA that last read this staging buffer has finished
+        self.stage[k].numpy()[:] = np.ascontiguousarray(local).view(np.uint8).reshape(-1)
+        self.payload[k].copy_(self.stage[k], non_blocking=True)
+        if self.device.type == "cuda":
+            import torch
+            self.copied[k] = torch.cuda.Event()
+            self.copied[k].record(torch.cuda.current_stream(self.device))
+        return self._finish(self.payload[k], to_host)
+
+    def gather_device(self, records_ptr: int, to_host: bool = False):
+        """``records_ptr``: device address of ``n`` packed ``lane_record``s on ``self.device``; the caller orders
+        the producing stream before torch's current stream (and the buffer's reuse after the returned work)."""
+        import torch
+        src = torch.as_tensor(_DeviceBytes(records_ptr, self.nbytes), device=self.device)
+        return self._finish(src, to_host)

@@ -56,6 +56,9 @@ class LaneDetector:
         self._debug = bool(debug)
         self._ctx: Optional[_native.LaneContext] = None
         self._ctx_key = None
+        self._dense_ctx: Optional[_native.LaneContext] = None   # larger max_segments, for frames the default truncated
+        self._dense_key = None
+        self.dense_reruns = 0       # chunks re-run because HoughLinesP found more segments than max_segments
         self._stream_fit = None     # float64 [S,2,3] for detect_streams
         self._stream_valid = None   # uint8  [S,2]
         self.last_records = None    # RECORD_DTYPE array of the last call (diagnostics)
@@ -73,7 +76,14 @@ class LaneDetector:
         cv2.fillPoly(mask, vertices, 255)
         return mask
 
-    def _device_index(self) -> int:
+    def _device_index(self, frames=None) -> int:
+        """GPU the context lives on: the device of a CUDA tensor input, else ``device=``, else torch's current one."""
+        if frames is not None and _is_torch_cuda(frames):
+            idx = frames.device.index
+            idx = 0 if idx is None else int(idx)
+            if self._device is not None and int(self._device) != idx:
+                raise ValueError(f"frames are on cuda:{idx} but this LaneDetector was created with device={self._device}")
+            return idx
         if self._device is not None:
             return int(self._device)
         try:
@@ -84,9 +94,9 @@ class LaneDetector:
             pass
         return 0
 
-    def _context(self, h: int, w: int, n: int) -> _native.LaneContext:
+    def _context(self, h: int, w: int, n: int, frames=None) -> _native.LaneContext:
         roi_key = None if self.roi_vertices is None else np.asarray(self.roi_vertices).tobytes()
-        key = (h, w, roi_key, self._device_index())
+        key = (h, w, roi_key, self._device_index(frames))
         if self._ctx is None or self._ctx_key != key or self._ctx.max_batch < min(n, self._max_batch):
             if self._ctx is not None:
                 self._ctx.close()
@@ -130,7 +140,7 @@ class LaneDetector:
     def _run(self, frames, stream_id, n_streams, prev_fit, prev_valid) -> np.ndarray:
         """Chunked native calls over frames [N,H,W,3] (numpy or CUDA torch); state arrays updated in place."""
         n, h, w = int(frames.shape[0]), int(frames.shape[1]), int(frames.shape[2])
-        ctx = self._context(h, w, n)
+        ctx = self._context(h, w, n, frames)
         s, oms = self.smoothing_factor, 1 - self.smoothing_factor
         chunks = []
         on_device = _is_torch_cuda(frames)
@@ -140,17 +150,43 @@ class LaneDetector:
             torch.cuda.current_stream(frames.device).synchronize()
         else:
             frames = np.ascontiguousarray(frames)
+
+        def call(c, a, b):
+            sid = None if stream_id is None else stream_id[a:b]
+            src = frames.data_ptr() + a * h * w * 3 if on_device else frames[a:b]
+            return c.detect(src, b - a, on_device, sid, n_streams, prev_fit, prev_valid, s, oms)
+
         for a in range(0, n, ctx.max_batch):
             b = min(a + ctx.max_batch, n)
-            sid = None if stream_id is None else stream_id[a:b]
-            if on_device:
-                ptr = frames.data_ptr() + a * h * w * 3
-                chunks.append(ctx.detect(ptr, b - a, True, sid, n_streams, prev_fit, prev_valid, s, oms))
-            else:
-                chunks.append(ctx.detect(frames[a:b], b - a, False, sid, n_streams, prev_fit, prev_valid, s, oms))
+            fit0, valid0 = prev_fit.copy(), prev_valid.copy()
+            recs = call(ctx, a, b)
+            if recs["flags"].any():
+                # cv2.HoughLinesP has no cap on the number of segments: a frame that found more than max_segments would
+                # otherwise be fitted on a truncated list.  Re-run the chunk, from the state it started with, on a context
+                # sized for what was found (the reference result, just slower), never return a truncated fit silently.
+                prev_fit[...], prev_valid[...] = fit0, valid0
+                dense = self._dense_context(h, w, int(recs["n_segments_found"].max()), ctx.device)
+                recs = np.concatenate([call(dense, i, min(i + dense.max_batch, b)) for i in range(a, b, dense.max_batch)])
+                if recs["flags"].any():
+                    raise _native.LaneError(-5, "segment list still truncated after the dense re-run")
+                self.dense_reruns += 1
+            chunks.append(recs)
         recs = chunks[0] if len(chunks) == 1 else np.concatenate(chunks)
         self.last_records = recs
         return recs
+
+    def _dense_context(self, h: int, w: int, need: int, device: int) -> _native.LaneContext:
+        cap = 1 << max(int(need) - 1, 1).bit_length()
+        roi_key = None if self.roi_vertices is None else np.asarray(self.roi_vertices).tobytes()
+        key = (h, w, roi_key, device)
+        if self._dense_ctx is None or self._dense_key != key or self._dense_ctx.max_segments < need:
+            if self._dense_ctx is not None:
+                self._dense_ctx.close()
+            self._dense_ctx = _native.LaneContext(h, w, 8, self._get_roi_mask((h, w)), device=device, max_segments=cap,
+                                                  debug=self._debug)
+            self._dense_key = key
+        self._ctx.copy_settings_to(self._dense_ctx)
+        return self._dense_ctx
 
     def _state_arrays(self):
         fit = np.zeros((1, 2, 3), np.float64)
@@ -247,6 +283,8 @@ class LaneDetector:
         self._stream_valid = None
 
     def close(self):
-        if self._ctx is not None:
-            self._ctx.close()
-            self._ctx = None
+        for name in ("_ctx", "_dense_ctx"):
+            c = getattr(self, name)
+            if c is not None:
+                c.close()
+                setattr(self, name, None)

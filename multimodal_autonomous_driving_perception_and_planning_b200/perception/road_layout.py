@@ -66,7 +66,14 @@ class RoadLayoutAnalyzer:
         frames = np.ascontiguousarray(frames)
         for a in range(0, n, ctx.max_batch):
             b = min(a + ctx.max_batch, n)
-            ctx.detect(frames[a:b], b - a, False, None, 1, pf, pv, 0.7, 1 - 0.7)
+            recs = ctx.detect(frames[a:b], b - a, False, None, 1, pf, pv, 0.7, 1 - 0.7)
+            if recs["flags"].any():
+                # cv2.HoughLinesP has no segment cap: grow the context to what was found and redo this chunk
+                self._max_segments = 1 << int(recs["n_segments_found"].max()).bit_length()
+                self._ctx.close()
+                self._ctx = None
+                ctx = self._context(h, w, n)
+                recs = ctx.detect(frames[a:b], b - a, False, None, 1, pf, pv, 0.7, 1 - 0.7)
             for i in range(b - a):
                 edges = ctx.tap(_native.TAP_EDGES, i)
                 center = edges[h // 3:2 * h // 3, w // 3:2 * w // 3]
