@@ -36,7 +36,19 @@ constexpr int SPX = 16;
 constexpr int STRIP_OUT = 30 * SPX;
 
 struct K2Args {
-    const uint32_t *c_bits, *s_bits;   // [n][H][WW] candidate / strong planes from k2a_sobel_nms
+    const uint32_t *c_bits, *s_bits;   // [n][H][WW] candidate / strong planes from k2a_sobel_nms (unfused path)
+    // fused path (k1_fused.cu): NMS survivors K [n][H][WW] + their magnitudes V [n][H][W]; the thresholds are formed
+    // here from the histogram, and the candidate / strong planes only ever exist in shared memory
+    const uint32_t *k_bits;
+    const uint8_t *v_plane;            // null => unfused path
+    const uint32_t *hist;              // [n][256]
+    const uint8_t *lut_low, *lut_high;
+    int4 *thr;                         // [n] (median_x2, low, high, pre)
+    const int *pre;                    // [n] magnitude floor k1_fused used
+    int *pre_redo;                     // [n] floor for the redo pass (= the true low)
+    int *redo_list, *redo_count;       // frames whose floor was above the true low
+    const int *frame_list, *n_list;    // redo pass: the frames to process (null = all)
+    uint32_t *dbg_c, *dbg_s;           // [n][H][WW] candidate / strong planes before hysteresis (verification taps) or null
     const uint32_t *roi_bits;      // [H][WW]
     int *n_edges, *rounds, *n_points;
     uint32_t *points;              // [n][max_points]
@@ -386,9 +398,37 @@ __global__ void __launch_bounds__(K2T, 3) k2_canny_cluster(K2Args A)
 #endif
     cg::cluster_group cluster = cg::this_cluster();
     const int G = (int)cluster.num_blocks(), rank = (int)cluster.block_rank();
-    const int f = blockIdx.x / G;
+    int f = blockIdx.x / G;
+    if (A.frame_list) {                          // redo pass: only the listed frames (the whole cluster leaves together)
+        if (f >= *A.n_list) return;
+        f = A.frame_list[f];
+    }
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int H = A.H, WW = A.WW, R = A.R;
+    const bool fused = A.v_plane != nullptr;
+    __shared__ int s_low, s_high;
+    if (fused) {
+        // thresholds of the frame from its histogram (np.median + the host LUT).  Every CTA of the cluster reads the same
+        // final values, so they all take the same decision below.
+        if (wid == 0) {
+            const int m2 = median_x2_warp(A.hist + f * 256, (long long)H * A.W, lane);
+            int low = A.lut_low[m2], high = A.lut_high[m2];
+            if (low > high) { int t = low; low = high; high = t; }
+            if (lane == 0) {
+                s_low = low; s_high = high;
+                if (rank == 0) A.thr[f] = make_int4(m2, low, high, A.pre[f]);
+            }
+        }
+        __syncthreads();
+        if (!A.frame_list && s_low < A.pre[f]) {
+            // the sampled floor was above the true low: K misses candidates.  List the frame for the redo pass.
+            if (rank == 0 && tid == 0) {
+                A.pre_redo[f] = s_low;
+                A.redo_list[atomicAdd(A.redo_count, 1)] = f;
+            }
+            return;
+        }
+    }
     const int b0 = rank * R, b1 = min(b0 + R, H), Rv = max(b1 - b0, 0);
     uint32_t *C = smem;                         // [R][WW]
     uint32_t *S = smem + (size_t)R * WW;        // [R+2][WW], row 0 / Rv+1 = neighbour bands
@@ -400,7 +440,8 @@ __global__ void __launch_bounds__(K2T, 3) k2_canny_cluster(K2Args A)
     // ---- phase 1 ran in k2a_sobel_nms: load this band's candidate / strong planes.  A band is one contiguous
     // run of Rv*WW words in each plane, so two bulk copies (TMA, completion on an mbarrier) bring it in.
     {
-        const uint32_t *cg = A.c_bits + ((size_t)f * H + b0) * WW, *sg = A.s_bits + ((size_t)f * H + b0) * WW;
+        const uint32_t *cg = (fused ? A.k_bits : A.c_bits) + ((size_t)f * H + b0) * WW;
+        const uint32_t *sg = fused ? nullptr : A.s_bits + ((size_t)f * H + b0) * WW;
         const bool bulk = (WW % 4 == 0) && Rv > 0;
         if (bulk) {
             const uint32_t bar = smem_u32(&s_bar);
@@ -411,16 +452,49 @@ __global__ void __launch_bounds__(K2T, 3) k2_canny_cluster(K2Args A)
             __syncthreads();
             if (tid == 0) {
                 const uint32_t bytes = (uint32_t)Rv * WW * 4u;
-                mbar_expect_tx(bar, 2 * bytes);
+                mbar_expect_tx(bar, fused ? bytes : 2 * bytes);
                 bulk_g2s(smem_u32(C), cg, bytes, bar);
-                bulk_g2s(smem_u32(S + WW), sg, bytes, bar);
+                if (!fused) bulk_g2s(smem_u32(S + WW), sg, bytes, bar);
             }
         } else {
-            for (int i = tid; i < Rv * WW; i += K2T) { C[i] = cg[i]; S[WW + i] = sg[i]; }
+            for (int i = tid; i < Rv * WW; i += K2T) { C[i] = cg[i]; if (!fused) S[WW + i] = sg[i]; }
         }
         for (int i = tid; i < WW; i += K2T) { S[i] = 0; S[(size_t)(Rv + 1) * WW + i] = 0; }
         for (int i = tid; i < (Rv * WW + 3) / 4; i += K2T) reinterpret_cast<volatile uint32_t *>(D)[i] = 0;
         if (bulk) mbar_wait(smem_u32(&s_bar), 0);
+        if (fused) {
+            // K / V -> candidate and strong words: a survivor is a candidate iff m > low and strong iff m > high, and
+            // V = min(m, 256) - 1, so both are byte compares V >= t.  Only words with survivors touch V (32 bytes each).
+            if (!bulk) __syncthreads();
+            const uint32_t lo4 = (uint32_t)s_low * 0x01010101u, hi4 = (uint32_t)s_high * 0x01010101u;
+            const uint8_t *vb = A.v_plane + ((size_t)f * H + b0) * A.W;
+            auto ge_bits = [](const uint4 &a, const uint4 &b, uint32_t t4) {
+                const uint32_t wds[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+                uint32_t m = 0;
+#pragma unroll
+                for (int q = 0; q < 8; q++)     // per byte 0/1, gathered into a nibble by one multiply
+                    m |= ((((__vcmpgeu4(wds[q], t4) & 0x01010101u) * 0x01020408u) >> 24) & 0xFu) << (4 * q);
+                return m;
+            };
+            for (int i = tid; i < Rv * WW; i += K2T) {
+                const uint32_t k = C[i];
+                uint32_t cw = 0, sw = 0;
+                if (k) {
+                    const int r = i / WW, w = i - r * WW;
+                    const uint4 *vp = reinterpret_cast<const uint4 *>(vb + (size_t)r * A.W + w * 32);
+                    const uint4 a = __ldg(vp);
+                    const uint4 b = (w * 32 + 16 < A.W) ? __ldg(vp + 1) : make_uint4(0, 0, 0, 0);
+                    cw = k & ge_bits(a, b, lo4);
+                    sw = k & ge_bits(a, b, hi4);
+                    C[i] = cw;
+                }
+                S[WW + i] = sw;
+                if (A.dbg_c) {
+                    A.dbg_c[((size_t)f * H + b0) * WW + i] = cw;
+                    A.dbg_s[((size_t)f * H + b0) * WW + i] = sw;
+                }
+            }
+        }
     }
     __syncthreads();
     K2TICK(tL);
@@ -670,15 +744,11 @@ __global__ void k_mask_rows(const uint32_t *__restrict__ edge_bits, const uint32
 
 }  // namespace
 
-// Returns false when this frame geometry cannot take the cluster path (caller falls back to the
-// generic byte-map kernels).
-bool launch_canny_cluster(const uint8_t *blur, const uint32_t *hist, const uint8_t *lut_low, const uint8_t *lut_high,
-                          const uint32_t *roi_bits, int4 *thr, int *n_edges, int *rounds, uint32_t *points,
-                          int *n_points, uint32_t *pmask_bits, uint32_t *edge_bits, uint32_t *c_bits, uint32_t *s_bits,
-                          int *task_counter, LaneGeom g, int n, cudaStream_t st, int *launches)
+// Cluster geometry of K2b for a frame size: G CTAs per frame, R rows per band, dynamic shared memory; false when the
+// frame does not fit (caller falls back to the generic byte-map kernels).
+static bool k2b_plan(int H, int W, int *G_out, int *R_out, size_t *smem_out)
 {
-    const int H = g.H, W = g.W, WW = (W + 31) / 32;
-    if (W % 16 != 0 || ((uintptr_t)blur % 16) != 0) return false;
+    const int WW = (W + 31) / 32;
     int G = 1;
     const int rows_per_band = getenv("LANE_K2_ROWS") ? atoi(getenv("LANE_K2_ROWS")) : 160;   // tuning knob
     while (G < 16 && H > rows_per_band * G) G *= 2;
@@ -691,12 +761,43 @@ bool launch_canny_cluster(const uint8_t *blur, const uint32_t *hist, const uint8
     }
     if (smem > 220 * 1024) return false;
     static bool configured[LANE_MAX_DEVICES];
-    const int sms = lane_sm_count();
     if (!configured[lane_cur_device()]) {
         cudaFuncSetAttribute(k2_canny_cluster, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
         cudaFuncSetAttribute(k2_canny_cluster, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
         configured[lane_cur_device()] = true;
     }
+    *G_out = G; *R_out = R; *smem_out = smem;
+    return true;
+}
+
+static cudaError_t k2b_launch(const K2Args &A, int G, size_t smem, int n, cudaStream_t st)
+{
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(n * G);
+    cfg.blockDim = dim3(K2T);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = G; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, k2_canny_cluster, A);
+}
+
+// Unfused form: K2a (Sobel + NMS + thresholds from the blurred plane) then K2b.  Returns false when this frame geometry
+// cannot take the cluster path (caller falls back to the generic byte-map kernels).
+bool launch_canny_cluster(const uint8_t *blur, const uint32_t *hist, const uint8_t *lut_low, const uint8_t *lut_high,
+                          const uint32_t *roi_bits, int4 *thr, int *n_edges, int *rounds, uint32_t *points,
+                          int *n_points, uint32_t *pmask_bits, uint32_t *edge_bits, uint32_t *c_bits, uint32_t *s_bits,
+                          int *task_counter, LaneGeom g, int n, cudaStream_t st, int *launches)
+{
+    const int H = g.H, W = g.W, WW = (W + 31) / 32;
+    if (W % 16 != 0 || ((uintptr_t)blur % 16) != 0) return false;
+    int G = 1, R = 0;
+    size_t smem = 0;
+    if (!k2b_plan(H, W, &G, &R, &smem)) return false;
+    const int sms = lane_sm_count();
     cudaMemsetAsync(task_counter, 0, sizeof(int), st);
     {
         static const int band_env = getenv("LANE_K2A_BAND") ? atoi(getenv("LANE_K2A_BAND")) : 0;
@@ -718,26 +819,48 @@ bool launch_canny_cluster(const uint8_t *blur, const uint32_t *hist, const uint8
             k2a_sobel_nms<5><<<sms * 5, K2A_WARPS * 32, 0, st>>>(blur, hist, lut_low, lut_high, thr, c_bits, s_bits, task_counter,
                                                                  n, H, W, band_rows, tail_frames, tail_rows);
     }
-    K2Args A;
+    K2Args A{};
     A.c_bits = c_bits; A.s_bits = s_bits; A.roi_bits = roi_bits;
     A.n_edges = n_edges; A.rounds = rounds; A.n_points = n_points; A.points = points;
     A.pmask_bits = pmask_bits; A.edge_bits = edge_bits;
     A.H = H; A.W = W; A.WW = WW; A.R = R; A.g = g;
     cudaMemsetAsync(n_edges, 0, sizeof(int) * n, st);
     cudaMemsetAsync(n_points, 0, sizeof(int) * n, st);
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(n * G);
-    cfg.blockDim = dim3(K2T);
-    cfg.dynamicSmemBytes = smem;
-    cfg.stream = st;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = G; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    cudaError_t e = cudaLaunchKernelEx(&cfg, k2_canny_cluster, A);
+    cudaError_t e = k2b_launch(A, G, smem, n, st);
     if (e != cudaSuccess) { cudaGetLastError(); return false; }
     *launches += 2;
+    return true;
+}
+
+// Fused form, first pass: K2b straight from the K / V planes of k1_fused.  Frames whose magnitude floor turned out to be
+// above their true low are listed in redo_list (and skipped); launch_canny_cluster_redo finishes them after
+// launch_fused_edge_redo has rebuilt their planes.
+bool launch_canny_cluster_fused(const uint32_t *k_bits, const uint8_t *v_plane, const uint32_t *hist, const uint8_t *lut_low,
+                                const uint8_t *lut_high, const uint32_t *roi_bits, int4 *thr, const int *pre, int *pre_redo,
+                                int *redo_list, int *redo_count, const int *frame_list, int *n_edges, int *rounds,
+                                uint32_t *points, int *n_points, uint32_t *pmask_bits, uint32_t *edge_bits, uint32_t *dbg_c,
+                                uint32_t *dbg_s, LaneGeom g, int n, cudaStream_t st, int *launches)
+{
+    const int H = g.H, W = g.W, WW = (W + 31) / 32;
+    int G = 1, R = 0;
+    size_t smem = 0;
+    if (!k2b_plan(H, W, &G, &R, &smem)) return false;
+    K2Args A{};
+    A.k_bits = k_bits; A.v_plane = v_plane; A.hist = hist; A.lut_low = lut_low; A.lut_high = lut_high; A.thr = thr;
+    A.pre = frame_list ? pre_redo : pre; A.pre_redo = pre_redo; A.redo_list = redo_list; A.redo_count = redo_count;
+    A.frame_list = frame_list; A.n_list = frame_list ? redo_count : nullptr;
+    A.dbg_c = dbg_c; A.dbg_s = dbg_s; A.roi_bits = roi_bits;
+    A.n_edges = n_edges; A.rounds = rounds; A.n_points = n_points; A.points = points;
+    A.pmask_bits = pmask_bits; A.edge_bits = edge_bits;
+    A.H = H; A.W = W; A.WW = WW; A.R = R; A.g = g;
+    if (!frame_list) {
+        cudaMemsetAsync(n_edges, 0, sizeof(int) * n, st);
+        cudaMemsetAsync(n_points, 0, sizeof(int) * n, st);
+        cudaMemsetAsync(redo_count, 0, sizeof(int), st);
+    }
+    cudaError_t e = k2b_launch(A, G, smem, n, st);
+    if (e != cudaSuccess) { cudaGetLastError(); return false; }
+    *launches += 1;
     return true;
 }
 

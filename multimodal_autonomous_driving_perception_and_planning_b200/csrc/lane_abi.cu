@@ -41,7 +41,11 @@ struct lane_ctx {
 
     // device buffers
     uint8_t *d_frames = nullptr;      // staging for host frames (lazy)
-    uint8_t *d_blur = nullptr;
+    uint8_t *d_blur = nullptr;        // blurred plane: unfused path and verification taps only (lazy)
+    uint32_t *d_kbits = nullptr;      // [B][H][WW] NMS survivors of the fused edge kernel
+    uint8_t *d_vplane = nullptr;      // [B][H][W]  their magnitudes (sparse: only survivors' bytes are ever written / read)
+    int *d_pre = nullptr;             // [B] magnitude floor per frame | [B] floor of the redo pass | [B] redo list | count
+    int force_unfused = 0;            // LANE_B200_K1=unfused pins the round-1 K1 + K2a kernels (A/B checks)
     uint32_t *d_roi_bits = nullptr;   // [H][WW] bit-plane of the ROI mask
     uint32_t *d_pmask_bits = nullptr; // [B][bh][WW] ROI-masked edges (the HoughLinesP mask)
     uint32_t *d_edge_bits = nullptr;  // [B][H][WW] Canny map
@@ -130,7 +134,7 @@ cudaError_t dalloc(T **p, size_t count)
 void free_all(lane_ctx *c)
 {
     cudaSetDevice(c->device);
-    void *ptrs[] = {c->d_frames, c->d_blur, c->d_cls, c->d_cls_dbg, c->d_roi, c->d_pmask, c->d_gray_dbg, c->d_hist,
+    void *ptrs[] = {c->d_frames, c->d_blur, c->d_kbits, c->d_vplane, c->d_pre, c->d_cls, c->d_cls_dbg, c->d_roi, c->d_pmask, c->d_gray_dbg, c->d_hist,
                     c->d_roi_bits, c->d_pmask_bits, c->d_edge_bits, c->d_dbg_c, c->d_dbg_s, c->d_accum16, c->d_win, c->d_win3, c->d_pmask_work,
                     c->d_points, c->d_points_dbg, c->d_lut, c->d_thr, c->d_seedsA, c->d_seedsB, c->d_seed_count,
                     c->d_n_edges, c->d_n_points, c->d_rounds, c->d_n_lines, c->d_accum, c->d_lines, c->fit.raw, c->fit.big,
@@ -179,6 +183,12 @@ int ensure_streams(lane_ctx *c, int S)
     return LANE_OK;
 }
 
+int ensure_blur(lane_ctx *c)
+{
+    if (!c->d_blur) CU(dalloc(&c->d_blur, (size_t)c->max_batch * c->g.H * c->g.W));
+    return LANE_OK;
+}
+
 // Byte-map buffers of the generic-width path, allocated the first time that path runs.
 int ensure_fallback(lane_ctx *c)
 {
@@ -193,6 +203,17 @@ int ensure_fallback(lane_ctx *c)
     CU(dalloc(&c->d_seed_count, B));
     CU(cudaMemcpyAsync(c->d_roi, c->h_roi, P, cudaMemcpyHostToDevice, c->st));
     c->fallback_ready = true;
+    return LANE_OK;
+}
+
+// LANE_B200_SYNC_DEBUG=1: synchronise after every stage and name the one that faulted (debugging aid)
+int stage_check(lane_ctx *c, const char *what)
+{
+    static const bool on = getenv("LANE_B200_SYNC_DEBUG") != nullptr;
+    if (!on) return LANE_OK;
+    cudaError_t e = cudaStreamSynchronize(c->st);
+    if (e == cudaSuccess) e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(c, LANE_ERR_CUDA, "stage %s failed: %s", what, cudaGetErrorString(e));
     return LANE_OK;
 }
 
@@ -211,7 +232,6 @@ int run_stages(lane_ctx *c, const uint8_t *frames_dev, int off, int m, const int
     int *L = c->slots[c->cur].launches;
     int rc;
     const uint8_t *fr = frames_dev + o * P * 3;
-    uint8_t *blur = c->d_blur + o * P;
     uint32_t *hist = c->d_hist + o * 256;
     int4 *thr = c->d_thr + o;
     int *n_edges = c->d_n_edges + o, *n_points = c->d_n_points + o, *rounds = c->d_rounds + o, *n_lines = c->d_n_lines + o;
@@ -221,19 +241,58 @@ int run_stages(lane_ctx *c, const uint8_t *frames_dev, int off, int m, const int
     int32_t *lines = c->d_lines + o * g.max_segments * 4;
 
     if (timed) { rc = mark(c, LANE_STAGE_BLUR_HIST); if (rc) return rc; }
-    launch_blur_hist(fr, blur, hist, m, H, W, c->st, &L[LANE_STAGE_BLUR_HIST], c->d_task_counter, c->force_tile,
-                     c->blur);
-
-    if (timed) { rc = mark(c, LANE_STAGE_CANNY); if (rc) return rc; }
-    c->last_cluster = !c->force_generic_k2 &&
-        launch_canny_cluster(blur, hist, c->d_lut, c->d_lut + 511, c->d_roi_bits, thr, n_edges, rounds, points, n_points,
-                             pmask_bits, edge_bits, cb, sb, c->d_task_counter, g, m, c->st, &L[LANE_STAGE_CANNY]);
+    // Fused edge path (aligned widths, Gaussian blur on): one kernel from BGR frames to NMS survivors, then the
+    // cluster kernel; the blurred plane is only written for the verification taps.
+    bool fused = false;
+    c->last_cluster = false;
+    if (!c->force_unfused && !c->force_tile && !c->force_generic_k2 && c->blur && lane_fused_edge_supported(H, W, fr)) {
+        if (!c->d_kbits) {
+            CU(dalloc(&c->d_kbits, (size_t)c->max_batch * planes));
+            CU(dalloc(&c->d_vplane, (size_t)c->max_batch * P));
+            CU(dalloc(&c->d_pre, (size_t)c->max_batch * 3 + 4));
+        }
+        if (c->debug) { rc = ensure_blur(c); if (rc) return rc; }
+        const size_t B = (size_t)c->max_batch;
+        int *pre = c->d_pre + o, *pre_redo = c->d_pre + B + o, *redo_list = c->d_pre + 2 * B + o, *redo_count = c->d_pre + 3 * B;
+        uint32_t *kb = c->d_kbits + o * planes;
+        uint8_t *vp = c->d_vplane + o * P, *bd = c->debug ? c->d_blur + o * P : nullptr;
+        uint32_t *dc = c->debug ? cb : nullptr, *ds = c->debug ? sb : nullptr;
+        int *LK = &L[LANE_STAGE_BLUR_HIST], *LC = &L[LANE_STAGE_CANNY];
+        if (launch_fused_edge(fr, c->d_lut, hist, pre, kb, vp, bd, c->d_task_counter, m, H, W, c->st, LK)) {
+            rc = stage_check(c, "k1_fused"); if (rc) return rc;
+            if (timed) { rc = mark(c, LANE_STAGE_CANNY); if (rc) return rc; }
+            fused = launch_canny_cluster_fused(kb, vp, hist, c->d_lut, c->d_lut + 511, c->d_roi_bits, thr, pre, pre_redo,
+                                               redo_list, redo_count, nullptr, n_edges, rounds, points, n_points, pmask_bits,
+                                               edge_bits, dc, ds, g, m, c->st, LC) &&
+                    // frames whose sampled floor was above their true low (normally none): rebuild K / V with the exact
+                    // floor and finish them; both kernels return at once when the list is empty
+                    launch_fused_edge_redo(fr, redo_list, redo_count, pre_redo, kb, vp, bd, c->d_task_counter, m, H, W, c->st, LC) &&
+                    launch_canny_cluster_fused(kb, vp, hist, c->d_lut, c->d_lut + 511, c->d_roi_bits, thr, pre, pre_redo,
+                                               redo_list, redo_count, redo_list, n_edges, rounds, points, n_points,
+                                               pmask_bits, edge_bits, dc, ds, g, m, c->st, LC);
+        }
+        if (!fused) fprintf(stderr, "lane_b200: fused edge path rejected by device %d, using the unfused kernels\n", c->device);
+        c->last_cluster = fused;
+        rc = stage_check(c, "k2_canny_cluster (fused input)"); if (rc) return rc;
+    }
+    c->last_paths = fused ? LANE_PATH_FUSED_EDGE : 0;
+    if (!fused) {
+        rc = ensure_blur(c); if (rc) return rc;
+        uint8_t *blur = c->d_blur + o * P;
+        if (timed) { rc = mark(c, LANE_STAGE_BLUR_HIST); if (rc) return rc; }
+        launch_blur_hist(fr, blur, hist, m, H, W, c->st, &L[LANE_STAGE_BLUR_HIST], c->d_task_counter, c->force_tile,
+                         c->blur);
+        if (timed) { rc = mark(c, LANE_STAGE_CANNY); if (rc) return rc; }
+        c->last_cluster = !c->force_generic_k2 &&
+            launch_canny_cluster(blur, hist, c->d_lut, c->d_lut + 511, c->d_roi_bits, thr, n_edges, rounds, points, n_points,
+                                 pmask_bits, edge_bits, cb, sb, c->d_task_counter, g, m, c->st, &L[LANE_STAGE_CANNY]);
+    }
     if (c->last_cluster) {
         if (timed) { rc = mark(c, LANE_STAGE_COMPACT); if (rc) return rc; }
     } else {
         // generic widths / unaligned planes: byte-map kernels, then the same bit-plane outputs
         rc = ensure_fallback(c); if (rc) return rc;
-        uint8_t *cls = c->d_cls + o * P;
+        uint8_t *cls = c->d_cls + o * P, *blur = c->d_blur + o * P;
         int *seedsA = c->d_seedsA + o * c->seed_cap, *seedsB = c->d_seedsB + o * c->seed_cap, *seed_count = c->d_seed_count + o;
         launch_thresholds(hist, c->d_lut, c->d_lut + 511, thr, m, H, W, c->st, &L[LANE_STAGE_CANNY]);
         launch_sobel_nms(blur, thr, cls, seedsA, seed_count, c->seed_cap, m, H, W, c->st, &L[LANE_STAGE_CANNY]);
@@ -246,11 +305,12 @@ int run_stages(lane_ctx *c, const uint8_t *frames_dev, int off, int m, const int
         launch_bytes_to_bits(cls, edge_bits, m, H, W, W, c->st, &L[LANE_STAGE_COMPACT]);
         launch_mask_rows(edge_bits, c->d_roi_bits, pmask_bits, g, m, c->st, &L[LANE_STAGE_COMPACT]);
     }
-    c->last_paths = (c->last_paths & LANE_PATH_FUSED_EDGE) | (c->last_cluster ? LANE_PATH_CLUSTER_CANNY : 0);
+    c->last_paths |= c->last_cluster ? LANE_PATH_CLUSTER_CANNY : 0;
     if (c->debug)
         CU(cudaMemcpyAsync(c->d_points_dbg + o * g.max_points, points, sizeof(uint32_t) * (size_t)m * g.max_points,
                            cudaMemcpyDeviceToDevice, c->st));
 
+    rc = stage_check(c, "canny / compaction"); if (rc) return rc;
     if (timed) { rc = mark(c, LANE_STAGE_PPHT); if (rc) return rc; }
     if (c->ppht_v1) {
         if (!c->d_accum) CU(dalloc(&c->d_accum, (size_t)c->max_batch * LANE_NUM_ANGLES * g.numrho));
@@ -267,12 +327,13 @@ int run_stages(lane_ctx *c, const uint8_t *frames_dev, int off, int m, const int
         if (v3) c->last_paths |= LANE_PATH_PPHT_DSMEM;
     }
 
+    rc = stage_check(c, "ppht"); if (rc) return rc;
     if (timed) { rc = mark(c, LANE_STAGE_FIT); if (rc) return rc; }
     LaneFitScratch fs{c->fit.raw + o * 6, c->fit.side_n + o * 2, c->fit.side_flags + o,
                       c->fit.big ? c->fit.big + o * 2 * 5 * 2 * (size_t)g.max_segments : nullptr};
     launch_fit(lines, n_lines, fs, stream_id_dev ? stream_id_dev + o : nullptr, S, c->d_prev_fit, c->d_prev_valid, c->smooth,
                c->one_minus_smooth, thr, n_edges, n_points, rounds, c->slots[c->cur].d_records + o, g, m, c->st, &L[LANE_STAGE_FIT]);
-    return LANE_OK;
+    return stage_check(c, "fit");
 }
 
 // Enqueue the whole batch.  Device-resident frames run as one chunk.  Host frames are cut into chunks that are
@@ -438,7 +499,6 @@ int lane_ctx_create(int device, int height, int width, int max_batch, int max_se
         for (auto &e : sl.ev) CUB(cudaEventCreate(&e));
         CUB(cudaEventCreateWithFlags(&sl.done, cudaEventDisableTiming));
     }
-    CUB(dalloc(&ctx->d_blur, B * P));
     const size_t WW = (width + 31) / 32;
     CUB(dalloc(&ctx->d_roi_bits, (size_t)height * WW));
     CUB(dalloc(&ctx->d_edge_bits, B * height * WW));
@@ -468,6 +528,7 @@ int lane_ctx_create(int device, int height, int width, int max_batch, int max_se
     {
         const char *e = getenv("LANE_B200_K1");
         ctx->force_tile = e && !strcmp(e, "tile");
+        ctx->force_unfused = e && (!strcmp(e, "unfused") || !strcmp(e, "tma"));
         e = getenv("LANE_B200_K4");
         ctx->ppht_v1 = e && !strcmp(e, "v1");
         ctx->ppht_v2 = e && !strcmp(e, "v2");
@@ -691,7 +752,9 @@ int lane_debug_tap(lane_ctx *c, int what, int fi, void *host_out, size_t capacit
     size_t bytes = 0;
     std::vector<int32_t> tmp;
     switch (what) {
-    case LANE_TAP_BLUR: src = c->d_blur + fi * P; bytes = P; break;
+    case LANE_TAP_BLUR:
+        if (!c->d_blur) return fail(c, LANE_ERR_STATE, "LANE_TAP_BLUR needs lane_set_debug(ctx,1) before detect");
+        src = c->d_blur + fi * P; bytes = P; break;
     case LANE_TAP_HIST: src = c->d_hist + fi * 256; bytes = 256 * sizeof(uint32_t); break;
     case LANE_TAP_EDGES:
     case LANE_TAP_CLASS: {

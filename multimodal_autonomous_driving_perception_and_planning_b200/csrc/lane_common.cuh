@@ -56,6 +56,14 @@ void lane_set_global_error(const char *msg);
 // ---- K1 ---------------------------------------------------------------------------------
 void launch_blur_hist(const uint8_t *frames, uint8_t *blur, uint32_t *hist, int n, int H, int W,
                       cudaStream_t st, int *launches, int *task_counter, int force_tile, int gaussian_blur);
+// fused edge kernel (k1_fused.cu): probe + gray + blur + histogram + Sobel + NMS -> K bit-plane, V byte plane
+bool lane_fused_edge_supported(int H, int W, const void *frames);
+bool launch_fused_edge(const uint8_t *frames, const uint8_t *lut_low, uint32_t *hist, int *pre, uint32_t *k_bits,
+                       uint8_t *v_plane, uint8_t *blur_dbg, int *task_counter, int n, int H, int W, cudaStream_t st,
+                       int *launches);
+bool launch_fused_edge_redo(const uint8_t *frames, const int *frame_list, const int *n_list, const int *pre,
+                            uint32_t *k_bits, uint8_t *v_plane, uint8_t *blur_dbg, int *task_counter, int n, int H, int W,
+                            cudaStream_t st, int *launches);
 void launch_gray_debug(const uint8_t *frame, uint8_t *gray, int H, int W, cudaStream_t st);
 
 // ---- K2 ---------------------------------------------------------------------------------
@@ -79,6 +87,11 @@ bool launch_canny_cluster(const uint8_t *blur, const uint32_t *hist, const uint8
                           const uint32_t *roi_bits, int4 *thr, int *n_edges, int *rounds, uint32_t *points,
                           int *n_points, uint32_t *pmask_bits, uint32_t *edge_bits, uint32_t *c_bits, uint32_t *s_bits,
                           int *task_counter, LaneGeom g, int n, cudaStream_t st, int *launches);
+bool launch_canny_cluster_fused(const uint32_t *k_bits, const uint8_t *v_plane, const uint32_t *hist, const uint8_t *lut_low,
+                                const uint8_t *lut_high, const uint32_t *roi_bits, int4 *thr, const int *pre, int *pre_redo,
+                                int *redo_list, int *redo_count, const int *frame_list, int *n_edges, int *rounds,
+                                uint32_t *points, int *n_points, uint32_t *pmask_bits, uint32_t *edge_bits, uint32_t *dbg_c,
+                                uint32_t *dbg_s, LaneGeom g, int n, cudaStream_t st, int *launches);
 void launch_bytes_to_bits(const uint8_t *bytes, uint32_t *bits, int n, int rows, int W, int row_stride,
                           cudaStream_t st, int *launches);
 void launch_mask_rows(const uint32_t *edge_bits, const uint32_t *roi_bits, uint32_t *pmask_bits, LaneGeom g, int n,
