@@ -115,6 +115,13 @@ LANE_API int lane_detect_batch(lane_ctx *ctx, const uint8_t *frames, int frames_
                       const int32_t *stream_id, int n_streams, double *prev_fit, uint8_t *prev_valid,
                       lane_record *out);
 
+/* Same as lane_detect_batch for frames still in the decoder's NV12 layout (uint8 [n][height*3/2][width]): only
+ * 1.5 B/px cross PCIe, the NV12 -> BGR conversion of lane_nv12_to_bgr_batch runs on the device chunk by chunk behind
+ * the copies, and the records equal those of lane_detect_batch on the converted frames. */
+LANE_API int lane_detect_batch_nv12(lane_ctx *ctx, const uint8_t *frames_nv12, int frames_on_device, int n,
+                           const int32_t *stream_id, int n_streams, double *prev_fit, uint8_t *prev_valid,
+                           lane_record *out);
+
 /* Asynchronous split of the above for pipelined callers: enqueue (device frames only; records
  * land in an internal pinned buffer), then collect (waits for the OLDEST batch in flight and returns
  * its records and the EMA state after it).
@@ -177,6 +184,18 @@ LANE_API int lane_debug_tap(lane_ctx *ctx, int what, int frame_index, void *host
 LANE_API int lane_hough_accumulator(lane_ctx *ctx, int frame_index, int32_t *accum_host, int threshold,
                            int32_t *peaks_host, int max_peaks, int *n_peaks);
 
+/* The same for EVERY frame of the last batch in one call, without debug mode (north-star kernel #3: "Hough voting with
+ * warp-aggregated shared-memory accumulators per theta band, followed by peak extraction"): votes come from the ROI rows
+ * of the frames' Canny bit-planes, peaks are extracted and ordered on the device.
+ *   peaks_host    int32 [n][max_peaks][3]  (rho_index, angle_index, votes) per frame in cv2.HoughLines order
+ *                 (votes descending, ties by ascending accumulator index); only the first min(n_peaks, max_peaks) rows
+ *                 of a frame are written (if more were found, which ones are kept is unspecified)
+ *   n_peaks_host  int32 [n]                peaks found per frame
+ *   accum_host    optional int32 [n][182][2*(W+H)+3]  the padded accumulators (verification: 4.4 MB per 1080p frame)
+ *   device_ms     optional: device time of the voting + peak kernels for the whole batch */
+LANE_API int lane_hough_lines_batch(lane_ctx *ctx, int threshold, int max_peaks, int32_t *peaks_host,
+                           int32_t *n_peaks_host, int32_t *accum_host, float *device_ms);
+
 /* ---- frame ingest (the step before the path) -------------------------------------------
  * Replaces the pixel work of VideoDataLoader.read_frame / read_frame_at
  * (/root/reference/data/loaders/video_loader.py:96-131): `frame = cv2.resize(frame, self.target_size)` (:108, :128),
@@ -188,6 +207,14 @@ LANE_API int lane_hough_accumulator(lane_ctx *ctx, int frame_index, int32_t *acc
  * call copies in, resizes, copies out and synchronises.  Needs no context; errors via lane_last_error(NULL). */
 LANE_API int lane_resize_batch(const uint8_t *src, int n, int src_h, int src_w, int channels, uint8_t *dst, int dst_h,
                                int dst_w, int on_device, int device, void *cuda_stream);
+
+/* NV12 -> BGR for a batch of decoded frames, bit-exact against cv2.cvtColor(nv12, cv2.COLOR_YUV2BGR_NV12): what a
+ * hardware decoder hands out (Y plane + interleaved half-resolution UV plane, 1.5 B/px) becomes the BGR frame
+ * VideoDataLoader.read_frame returns (/root/reference/data/loaders/video_loader.py:103-110).
+ * src: uint8 [n][height*3/2][width], dst: uint8 [n][height][width][3]; width and height even.  on_device / device /
+ * cuda_stream as for lane_resize_batch.  Needs no context; errors via lane_last_error(NULL). */
+LANE_API int lane_nv12_to_bgr_batch(const uint8_t *src, int n, int height, int width, uint8_t *dst, int on_device,
+                                    int device, void *cuda_stream);
 
 /* ---- scene statistics (second half) -----------------------------------------------------
  * Integer sums behind SceneClassifier's image cues (/root/reference/src/tagging/scene_classifier.py):

@@ -82,6 +82,9 @@ _PROTOS = {
     "lane_set_preprocess": (C.c_int, [C.c_void_p, C.c_int]),
     "lane_detect_batch": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p,
                                     C.c_void_p, C.c_void_p]),
+    "lane_detect_batch_nv12": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p,
+                                         C.c_void_p, C.c_void_p]),
+    "lane_nv12_to_bgr_batch": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
     "lane_detect_enqueue": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
     "lane_detect_collect": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "lane_ctx_stream": (C.c_void_p, [C.c_void_p]),
@@ -91,6 +94,8 @@ _PROTOS = {
     "lane_set_profiling": (C.c_int, [C.c_void_p, C.c_int]),
     "lane_get_stage_ms": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "lane_debug_tap": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]),
+    "lane_hough_lines_batch": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
+                                         C.POINTER(C.c_float)]),
     "lane_hough_accumulator": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int,
                                          C.POINTER(C.c_int)]),
 }
@@ -216,15 +221,17 @@ class LaneContext:
 
     # ---- hot path
     def detect(self, frames, n: int, on_device: bool, stream_id, n_streams: int, prev_fit: np.ndarray,
-               prev_valid: np.ndarray, smoothing: float, one_minus: float) -> np.ndarray:
-        """frames: int device pointer (on_device) or C-contiguous uint8 ndarray.  prev_fit float64[S,2,3] and
-        prev_valid uint8[S,2] are updated in place.  Returns a RECORD_DTYPE array of n records (a copy)."""
+               prev_valid: np.ndarray, smoothing: float, one_minus: float, nv12: bool = False) -> np.ndarray:
+        """frames: int device pointer (on_device) or C-contiguous uint8 ndarray -- BGR [n,H,W,3], or with ``nv12`` the
+        decoder layout [n,H*3/2,W].  prev_fit float64[S,2,3] and prev_valid uint8[S,2] are updated in place.
+        Returns a RECORD_DTYPE array of n records (a copy)."""
         L = lib()
         self._check(L.lane_set_smoothing(self._h, float(smoothing), float(one_minus)))
         fp = C.c_void_p(frames) if on_device else _ptr(frames)
         sid = None if stream_id is None else np.ascontiguousarray(stream_id, dtype=np.int32)
-        self._check(L.lane_detect_batch(self._h, fp, int(on_device), n, _ptr(sid), n_streams, _ptr(prev_fit),
-                                        _ptr(prev_valid), _ptr(self._records)))
+        fn = L.lane_detect_batch_nv12 if nv12 else L.lane_detect_batch
+        self._check(fn(self._h, fp, int(on_device), n, _ptr(sid), n_streams, _ptr(prev_fit), _ptr(prev_valid),
+                       _ptr(self._records)))
         return self._records[:n].copy()
 
     def enqueue(self, frames_ptr: int, n: int, stream_id, n_streams, prev_fit, prev_valid, smoothing, one_minus):
@@ -269,6 +276,20 @@ class LaneContext:
             rows = written.value // (out.shape[1] * 4)
             return out[:rows].copy()
         return out
+
+    def hough_lines_batch(self, n: int, threshold: int = 50, max_peaks: int = 256, with_accum: bool = False):
+        """Standard Hough transform (what ``cv2.HoughLines(masked, 1, pi/180, threshold)`` computes) of all ``n`` frames
+        of the last batch.  Returns ``(peaks, counts, accum, ms)``: ``peaks[i]`` = int32 rows (rho_index, angle_index,
+        votes) of frame i in cv2 order, ``counts[i]`` = peaks found, ``accum`` = int32 [n, 182, 2(W+H)+3] or None,
+        ``ms`` = device time of the batch."""
+        numrho = 2 * (self.width + self.height) + 1
+        peaks = np.zeros((n, max_peaks, 3), np.int32)
+        counts = np.zeros(n, np.int32)
+        acc = np.empty((n, 182, numrho + 2), np.int32) if with_accum else None
+        ms = C.c_float(0)
+        self._check(lib().lane_hough_lines_batch(self._h, int(threshold), int(max_peaks), _ptr(peaks), _ptr(counts),
+                                                 _ptr(acc), C.byref(ms)))
+        return [peaks[i, :min(int(counts[i]), max_peaks)].copy() for i in range(n)], counts, acc, float(ms.value)
 
     def hough_accumulator(self, frame_index: int, threshold: int = 0, max_peaks: int = 0):
         """Standard-Hough accumulator int32[182][2(W+H)+3] of the ROI-masked edges of one frame of the

@@ -48,19 +48,17 @@ namespace {
 constexpr int SPX = 16;                 // pixels per lane
 constexpr int STRIP_OUT = 30 * SPX;     // 480 output pixels per warp (lanes 0 and 31 are halo providers)
 constexpr int FWARPS = 4;               // warps per CTA
-constexpr int FLUSH_ROWS = 15;          // 15 rows x 16 px = 240 < 256 increments per byte counter
 constexpr int RS = 512 + 16;            // M ring row stride in u16 (8 px of padding either side)
 
 // per-warp shared memory (bytes)
-constexpr int SM_CNT = 0;                          // [256][32] u8   private histogram counters
-constexpr int SM_TOT = SM_CNT + 256 * 32;          // [256] u32      per-task totals
-constexpr int SM_M = SM_TOT + 256 * 4;             // [3][RS] u16    magnitude ring
+constexpr int SM_TAB = 0;                          // [256] u32      histogram of the task (shared-memory atomics)
+constexpr int SM_M = SM_TAB + 256 * 4;             // [3][RS] u16    magnitude ring
 constexpr int SM_DX = SM_M + 3 * RS * 2;           // [2][512] u16   dx of rows s, s-1 (f16 sign-magnitude)
 constexpr int SM_DY = SM_DX + 2 * 512 * 2;         // [2][512] u16
 constexpr int SM_Q = SM_DY + 2 * 512 * 2;          // [512] u16      candidate queue of one row
 constexpr int SM_KB = SM_Q + 512 * 2;              // [16] u32       K bits of one row (word w = px 32w .. 32w+31 of the strip)
-constexpr int SM_QN = SM_KB + 16 * 4;              // u32 [2]        queue length, alternating by row parity
-constexpr int SM_WARP = SM_QN + 16;                // 17584
+constexpr int SM_QN = SM_KB + 16 * 4;              // u32            running count of queued candidates (never reset)
+constexpr int SM_WARP = SM_QN + 16;                // 9392
 static_assert(SM_WARP % 16 == 0, "per-warp block must keep 16-byte alignment");
 
 __device__ __forceinline__ uint32_t dp2a_lo(uint32_t a, uint32_t b, uint32_t c)
@@ -125,6 +123,74 @@ __device__ __forceinline__ void gray16(const uint32_t (&w)[12], uint32_t (&g)[8]
     }
 }
 
+// NMS of one row for the candidates queued by the warp (called only for rows that have candidates).
+// Both loops have WARP-UNIFORM trip counts taken from redux instructions (max / sum of the lanes' candidate counts), with
+// the per-lane work predicated inside.  That is deliberate: with per-lane trip counts (or a count read back from shared
+// memory) ptxas can no longer prove that the warp is converged in the rest of the row step, guards every shuffle there
+// with a BRA.DIV fallback path and pays ~60 register moves per row to keep the fallback's register layout.
+// Returns (K word of this lane's slot in the row's bit string, new queue base).
+__device__ __noinline__ uint2 nms_row(uint32_t cand, uint32_t qbase, uint8_t *ws, int sa, int sb, int sc, int parity,
+                                      uint8_t *vrow)
+{
+    const int lane = threadIdx.x & 31;
+    uint16_t *Mring = reinterpret_cast<uint16_t *>(ws + SM_M) + 8;
+    const uint16_t *dxp = reinterpret_cast<uint16_t *>(ws + SM_DX) + parity * 512;
+    const uint16_t *dyp = reinterpret_cast<uint16_t *>(ws + SM_DY) + parity * 512;
+    uint16_t *queue = reinterpret_cast<uint16_t *>(ws + SM_Q);
+    uint32_t *kbits = reinterpret_cast<uint32_t *>(ws + SM_KB);
+    uint32_t *qn = reinterpret_cast<uint32_t *>(ws + SM_QN);
+    // spread the row's candidates over the lanes
+    const uint32_t cnt0 = (uint32_t)__popc(cand);
+    {
+        const uint32_t cnt = cnt0;
+        uint32_t at = 0;
+        if (cand) at = atomicAdd(qn, cnt) - qbase;
+        const uint32_t xb = SPX * lane;
+        const uint32_t most = __reduce_max_sync(0xffffffffu, cnt);      // warp-uniform trip count
+        for (uint32_t k = 0; k < most; k++) {
+            if (cand) {
+                const int p = __ffs(cand) - 1;
+                cand &= cand - 1;
+                queue[at++] = (uint16_t)(xb + p);
+            }
+        }
+    }
+    __syncwarp();                                          // queue, M row s and dx/dy rows are visible to every lane
+    // the counter only ever grows (no reset, hence no reset race): this row's entries are [qbase, *qn)
+    const uint32_t total = __reduce_add_sync(0xffffffffu, cnt0), qend = qbase + total;
+    const uint16_t *Ma = Mring + sa, *Mb = Mring + sb, *Mc = Mring + sc;
+    for (uint32_t base = 0; base < total; base += 32) {
+        const uint32_t i = base + lane;
+        if (i >= total) continue;
+        const uint32_t x = queue[i];
+        const int m = Mb[x];
+        const uint32_t xr = dxp[x], yr = dyp[x];
+        const int a = (int)(xr & 0x7FFFu), b = (int)(yr & 0x7FFFu);
+        const int tg22x = a * 13573, ay = b << 15;
+        const uint16_t *p1, *p2;
+        int ge;                                            // second comparison is >= for the axis-aligned sectors
+        if (ay < tg22x) { p1 = Mb + x - 1; p2 = Mb + x + 1; ge = 1; }                    // horizontal gradient
+        else if (ay > tg22x + (a << 16)) { p1 = Ma + x; p2 = Mc + x; ge = 1; }             // vertical
+        else {                                             // diagonal: along (+1,+1) when the signs agree
+            const int d = ((xr ^ yr) & 0x8000u) ? 1 : -1;
+            p1 = Ma + x + d; p2 = Mc + x - d; ge = 0;
+        }
+        const int n1 = *p1, n2 = *p2;
+        if (m > n1 && m + ge > n2) {
+            const uint32_t xs = x - SPX;                   // pixel inside the strip's 480 outputs
+            atomicOr(&kbits[xs >> 5], 1u << (xs & 31));
+            vrow[xs] = (uint8_t)(min(m, 256) - 1);
+        }
+    }
+    __syncwarp();                                          // all survivors are in kbits; ring slot sa is free again
+    uint32_t kw = 0;
+    if (lane < 16) {
+        kw = kbits[lane];
+        kbits[lane] = 0;
+    }
+    return make_uint2(kw, qend);
+}
+
 struct FusedArgs {
     const uint8_t *frames;         // [n][H][W][3]
     const int *frame_list;         // redo pass: indices of the frames to process (null = 0..n-1)
@@ -139,13 +205,13 @@ struct FusedArgs {
     int band_rows, tail_frames, tail_rows;
 };
 
-__global__ void __launch_bounds__(FWARPS * 32, 3) k1_fused(FusedArgs A)
+template <int MINB>
+__global__ void __launch_bounds__(FWARPS * 32, MINB) k1_fused(FusedArgs A)
 {
     extern __shared__ __align__(128) uint8_t fsm[];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     uint8_t *ws = fsm + wid * SM_WARP;
-    uint8_t *wh = ws + SM_CNT;
-    uint32_t *tot = reinterpret_cast<uint32_t *>(ws + SM_TOT);
+    uint32_t *tab = reinterpret_cast<uint32_t *>(ws + SM_TAB);
     uint16_t *Mring = reinterpret_cast<uint16_t *>(ws + SM_M) + 8;     // + slot * RS
     uint16_t *DXr = reinterpret_cast<uint16_t *>(ws + SM_DX), *DYr = reinterpret_cast<uint16_t *>(ws + SM_DY);
     uint16_t *queue = reinterpret_cast<uint16_t *>(ws + SM_Q);
@@ -155,20 +221,19 @@ __global__ void __launch_bounds__(FWARPS * 32, 3) k1_fused(FusedArgs A)
     const bool redo = A.frame_list != nullptr;
     const int n_frames = redo ? *A.n_list : A.n_frames;
     const int tail_frames = redo ? 0 : A.tail_frames;
-    {   // zero this warp's private counters, K bits and queue length
-        uint4 *z = reinterpret_cast<uint4 *>(wh);
-        for (int i = lane; i < 256 * 32 / 16; i += 32) z[i] = make_uint4(0, 0, 0, 0);
+    {   // zero this warp's K bits and queue length
         if (lane < 16) kbits[lane] = 0;
-        if (lane == 0) { qn[0] = 0; qn[1] = 0; }
+        if (lane == 0) *qn = 0;
     }
     __syncwarp();
+    uint32_t qbase = 0;                                   // value of *qn when the current row's queue starts (warp-uniform)
     const int n_strips = (W + STRIP_OUT - 1) / STRIP_OUT;
     const int n_bands = (H + A.band_rows - 1) / A.band_rows, n_bands_t = (H + A.tail_rows - 1) / A.tail_rows;
     const int n_main = (n_frames - tail_frames) * n_bands * n_strips;
     const int n_tasks = n_main + tail_frames * n_bands_t * n_strips;
     const size_t frame_px = (size_t)H * W;
     const uint32_t xb = SPX * lane;                       // first pixel of this lane in strip coordinates
-    const uint32_t hbase = smem_u32(wh) + lane;           // this lane's column of the private counters
+    const uint32_t hbase = smem_u32(tab);
 
     for (;;) {
         int task = 0;
@@ -188,9 +253,10 @@ __global__ void __launch_bounds__(FWARPS * 32, 3) k1_fused(FusedArgs A)
         const bool left_edge = xl == 0, right_edge = xl + SPX == W;
         const uint8_t *src = A.frames + f * frame_px * 3 + (size_t)max(xl, 0) * 3;
         uint8_t *bdst = A.blur_dbg ? A.blur_dbg + f * frame_px + max(xl, 0) : nullptr;
-        uint8_t *vdst = A.v_plane + f * frame_px + strip * STRIP_OUT;           // + n * W + (x - 16)
+        const bool dbg_store = bdst != nullptr && is_out;
+        uint8_t *vrow = A.v_plane + f * frame_px + (size_t)q0 * W + strip * STRIP_OUT;      // row n of V: + (x - 16)
         const int word0 = strip * (STRIP_OUT / 32);
-        uint32_t *kdst = A.k_bits + (size_t)f * H * WW + word0 + lane;         // + n * WW   (lanes 0..14)
+        uint32_t *krow = A.k_bits + ((size_t)f * H + q0) * WW + word0 + lane;                // row n of K (lanes 0..14)
         const bool k_writer = lane < STRIP_OUT / 32 && word0 + lane < WW;
         const uint32_t pre = (uint32_t)A.pre[f];
         const uint32_t pre2 = pre | (pre << 16);
@@ -207,7 +273,7 @@ __global__ void __launch_bounds__(FWARPS * 32, 3) k1_fused(FusedArgs A)
         }
         if (!redo) {
 #pragma unroll
-            for (int b = 0; b < 8; b++) tot[b * 32 + lane] = 0;
+            for (int b = 0; b < 8; b++) tab[b * 32 + lane] = 0;
         }
         if (!in_img) {                                    // the magnitude plane has a zero border beyond the image
 #pragma unroll
@@ -216,27 +282,8 @@ __global__ void __launch_bounds__(FWARPS * 32, 3) k1_fused(FusedArgs A)
                 z[0] = make_uint4(0, 0, 0, 0); z[1] = make_uint4(0, 0, 0, 0);
             }
         }
-        if (lane == 0) { qn[0] = 0; qn[1] = 0; }          // a band of odd height leaves its last count behind
-        int since_flush = 0;
         uint32_t cand_prev = 0;                           // candidates of the row whose NMS runs next
         int sa = 0, sb = RS, sc = 2 * RS;                 // ring slots of M rows s-2, s-1, s
-
-        auto flush = [&]() {
-            __syncwarp();
-#pragma unroll
-            for (int b = 0; b < 8; b++) {
-                uint4 *row = reinterpret_cast<uint4 *>(wh + (b * 32 + lane) * 32);
-                uint4 a = row[0], c = row[1];
-                uint32_t s = 0;
-                s = __dp4a(a.x, 0x01010101u, s); s = __dp4a(a.y, 0x01010101u, s);
-                s = __dp4a(a.z, 0x01010101u, s); s = __dp4a(a.w, 0x01010101u, s);
-                s = __dp4a(c.x, 0x01010101u, s); s = __dp4a(c.y, 0x01010101u, s);
-                s = __dp4a(c.z, 0x01010101u, s); s = __dp4a(c.w, 0x01010101u, s);
-                tot[b * 32 + lane] += s;
-                row[0] = make_uint4(0, 0, 0, 0); row[1] = make_uint4(0, 0, 0, 0);
-            }
-            __syncwarp();
-        };
 
         uint32_t w[12];
         auto load_row = [&](int y) {
@@ -254,6 +301,21 @@ __global__ void __launch_bounds__(FWARPS * 32, 3) k1_fused(FusedArgs A)
         const int y_first = q0 - 4, y_last = q1 + 3;      // gray rows this band reads
         load_row(y_first);
 
+        // pipeline fill: the first four gray rows only feed the vertical filter
+        auto fill_step = [&](auto slot, int y) {
+            constexpr int c = decltype(slot)::value, o = c ^ 1;
+            gray16(w, sg[c]);
+            load_row(y + 1);
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                s1[c][j] = h2add(sg[c][j], sg[o][j]);
+                s2[c][j] = h2add(s1[c][j], s1[o][j]);
+                s3[c][j] = h2add(s2[c][j], s2[o][j]);
+            }
+        };
+        // One row of the steady state.  No persistent array is assigned under a condition here (the frame borders are
+        // patched in shared memory by a rare branch below): every conditional assignment to the column state costs a
+        // block of register moves per row once the compiler has to merge the two versions.
         auto row_step = [&](auto slot, int y) {
             constexpr int c = decltype(slot)::value, o = c ^ 1;
             gray16(w, sg[c]);
@@ -266,7 +328,6 @@ __global__ void __launch_bounds__(FWARPS * 32, 3) k1_fused(FusedArgs A)
                 s3[c][j] = h2add(s2[c][j], s2[o][j]);
                 V[j] = s3[c][j] + s3[o][j];
             }
-            if (y < q0) return;                           // pipeline fill
             const int r = y - 2;                          // V is the column sum of blurred row r
             // ---- horizontal [1 4 6 4 1]
             uint32_t Bp[8];                               // blurred row r as zero-interleaved pairs (f16x2 integers)
@@ -293,158 +354,136 @@ __global__ void __launch_bounds__(FWARPS * 32, 3) k1_fused(FusedArgs A)
                     ov.y = __byte_perm(Hs[2], Hs[3], 0x7531);
                     ov.z = __byte_perm(Hs[4], Hs[5], 0x7531);
                     ov.w = __byte_perm(Hs[6], Hs[7], 0x7531);
-                    if (bdst && is_out) *reinterpret_cast<uint4 *>(bdst + (uint32_t)r * (uint32_t)W) = ov;
+                    if (dbg_store) *reinterpret_cast<uint4 *>(bdst + (uint32_t)r * (uint32_t)W) = ov;
                     if (!redo) {
-                        // lanes whose sixteen pixels are equal (flat sky / asphalt) update one counter by 16
+                        // Histogram of the task in a per-warp table of 32-bit counters, updated with shared-memory
+                        // atomics (fire and forget; 1 KB per warp instead of 8 KB of per-lane byte counters, which is what
+                        // lets 16 warps share an SM).  A lane whose sixteen pixels are equal (flat sky / asphalt) adds 16
+                        // once; when the whole 480-px row of the strip is one value, one lane adds it all.
                         const bool flat = ov.x == ov.y && ov.z == ov.w && ov.x == ov.z && ov.x == __byte_perm(ov.x, 0, 0);
-                        if (__all_sync(0xffffffffu, flat || !is_out)) {
-                            if (is_out) {
-                                const uint32_t addr = __dp4a(ov.x, 0x20u, hbase);
-                                uint32_t t;
-                                asm volatile("ld.shared.u8 %0, [%1];" : "=r"(t) : "r"(addr));
-                                t += 16;
-                                asm volatile("st.shared.u8 [%0], %1;" ::"r"(addr), "r"(t) : "memory");
-                            }
+                        const uint32_t v0 = __shfl_sync(0xffffffffu, ov.x, 1);
+                        const unsigned out_lanes = __ballot_sync(0xffffffffu, is_out);
+                        if (__all_sync(0xffffffffu, !is_out || (flat && ov.x == v0))) {
+                            if (lane == 1) atomicAdd(&tab[v0 & 0xFFu], 16u * (uint32_t)__popc(out_lanes));
+                        } else if (__all_sync(0xffffffffu, flat || !is_out)) {
+                            if (is_out) atomicAdd(&tab[ov.x & 0xFFu], 16u);
                         } else if (is_out) {
                             const uint32_t ow[4] = {ov.x, ov.y, ov.z, ov.w};
 #pragma unroll
                             for (int q = 0; q < 4; q++) {
 #pragma unroll
                                 for (int k = 0; k < 4; k++) {
-                                    // counter address = base + 32 * byte k of the word, in one dot-product instruction
-                                    const uint32_t addr = __dp4a(ow[q], 0x20u << (8 * k), hbase);
-                                    uint32_t t;
-                                    asm volatile("ld.shared.u8 %0, [%1];" : "=r"(t) : "r"(addr));
-                                    t += 1;
-                                    asm volatile("st.shared.u8 [%0], %1;" ::"r"(addr), "r"(t) : "memory");
+                                    // counter address = base + 4 * byte k of the word, in one dot-product instruction
+                                    const uint32_t addr = __dp4a(ow[q], 0x4u << (8 * k), hbase);
+                                    asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(addr), "r"(1u) : "memory");
                                 }
                             }
                         }
-                        if (++since_flush == FLUSH_ROWS) { flush(); since_flush = 0; }
                     }
                 }
             }
-            // ---- Sobel, arrival of blurred row r: forms the gradient of row s = r - 1.
-            // BORDER_REPLICATE of the blurred plane: rows above the frame repeat row 0, rows below repeat row H-1.
+            // ---- Sobel, arrival of blurred row r: forms the gradient of row s = r - 1
             const int s = r - 1;
-            uint32_t h2n[8];
-            if (r < H) {
+            uint32_t dx[8], dy[8], Mw[8], cand_new;
+            {
                 uint32_t BL = __shfl_up_sync(0xffffffffu, Bp[7], 1), BR = __shfl_down_sync(0xffffffffu, Bp[0], 1);
-                if (left_edge) BL = __byte_perm(Bp[0], 0, 0x1010);       // x=-1 := x=0
+                if (left_edge) BL = __byte_perm(Bp[0], 0, 0x1010);       // x=-1 := x=0 (BORDER_REPLICATE)
                 if (right_edge) BR = __byte_perm(Bp[7], 0, 0x3232);      // x=W := x=W-1
                 uint32_t Bo[9];                                            // odd-aligned pairs (B(2j-1), B(2j))
                 Bo[0] = __byte_perm(BL, Bp[0], 0x5432);
 #pragma unroll
                 for (int j = 1; j < 8; j++) Bo[j] = __byte_perm(Bp[j - 1], Bp[j], 0x5432);
                 Bo[8] = __byte_perm(Bp[7], BR, 0x5432);
+                uint32_t acc = 0;
 #pragma unroll
                 for (int j = 0; j < 8; j++) {
                     h1s[c][j] = h2sub(Bo[j + 1], Bo[j]);                   // B(x+1) - B(x-1)
-                    h2n[j] = h2fma2(Bp[j], h2add(Bo[j], Bo[j + 1]));       // B(x-1) + 2 B(x) + B(x+1)
-                }
-            } else {                                       // warp-uniform: below the frame, repeat row H-1
-#pragma unroll
-                for (int j = 0; j < 8; j++) { h1s[c][j] = h1s[o][j]; h2n[j] = h2s[o][j]; }
-            }
-            if (r == 0) {                                  // warp-uniform: above the frame, row -1 := row 0
-#pragma unroll
-                for (int j = 0; j < 8; j++) { h1s[o][j] = h1s[c][j]; h2s[o][j] = h2n[j]; }
-            }
-            const bool row_ok = s >= 0 && s < H;          // outside the frame the magnitude is zero
-            uint32_t cand_new;
-            {
-                uint32_t dx[8], dy[8], Mw[8], acc = 0;
-#pragma unroll
-                for (int j = 0; j < 8; j++) {
+                    const uint32_t h2old = h2s[c][j];                      // h2 of row r - 2
+                    h2s[c][j] = h2fma2(Bp[j], h2add(Bo[j], Bo[j + 1]));    // B(x-1) + 2 B(x) + B(x+1)
                     T1s[c][j] = h2add(h1s[o][j], h1s[c][j]);
-                    dx[j] = h2add(T1s[o][j], T1s[c][j]);                  // h1(s-1) + 2 h1(s) + h1(s+1)
-                    dy[j] = h2sub(h2n[j], h2s[c][j]);                     // h2(s+1) - h2(s-1)
-                    h2s[c][j] = h2n[j];
+                    dx[j] = h2add(T1s[o][j], T1s[c][j]);                   // h1(s-1) + 2 h1(s) + h1(s+1)
+                    dy[j] = h2sub(h2s[c][j], h2old);                       // h2(s+1) - h2(s-1)
                     Mw[j] = h2abs_sum(dx[j], dy[j]);
                     const uint32_t gt = __hgt2_mask(*reinterpret_cast<const __half2 *>(&Mw[j]),
                                                     *reinterpret_cast<const __half2 *>(&pre2));   // 0xFFFF per half: M > pre
                     acc |= gt & ((1u << (2 * j)) | (1u << (2 * j + 17)));
                 }
                 cand_new = (acc | (acc >> 16)) & own_mask;
-                if (!row_ok) {                              // warp-uniform
-                    cand_new = 0;
+            }
+            uint4 *mrow = reinterpret_cast<uint4 *>(Mring + sc + xb);
+            uint4 *xrow = reinterpret_cast<uint4 *>(DXr + (s & 1) * 512 + xb);
+            uint4 *yrow = reinterpret_cast<uint4 *>(DYr + (s & 1) * 512 + xb);
+            if (s <= 0 || s >= H - 1) {
+                // Frame borders (warp-uniform, two rows per frame).  The blurred plane is extended by BORDER_REPLICATE
+                // (row -1 := row 0, row H := row H-1) while the rows the filter state saw there came from the reflected
+                // gray rows, and the magnitude is zero outside the frame: redo this row's gradient from the state.
+                uint32_t acc = 0;
 #pragma unroll
-                    for (int j = 0; j < 8; j++) Mw[j] = 0;
+                for (int j = 0; j < 8; j++) {
+                    uint32_t ex, ey;
+                    if (s == 0) {                          // h1(-1) = h1(0), h2(-1) = h2(0)
+                        ex = h2add(T1s[c][j], h2add(h1s[o][j], h1s[o][j]));
+                        ey = h2sub(h2s[c][j], h2s[o][j]);
+                    } else {                               // s == H-1: h1(H) = h1(H-1), h2(H) = h2(H-1); h2(H-2) = h2new - dy
+                        ex = h2add(T1s[o][j], h2add(h1s[o][j], h1s[o][j]));
+                        ey = h2sub(h2s[o][j], h2sub(h2s[c][j], dy[j]));
+                    }
+                    uint32_t em = h2abs_sum(ex, ey);
+                    if (s < 0 || s >= H) { ex = 0; ey = 0; em = 0; }
+                    const uint32_t gt = __hgt2_mask(*reinterpret_cast<const __half2 *>(&em),
+                                                    *reinterpret_cast<const __half2 *>(&pre2));
+                    acc |= gt & ((1u << (2 * j)) | (1u << (2 * j + 17)));
+                    dx[j] = ex; dy[j] = ey; Mw[j] = em;
                 }
+                cand_new = (acc | (acc >> 16)) & own_mask;
                 if (in_img) {
-                    uint4 *mrow = reinterpret_cast<uint4 *>(Mring + sc + xb);
                     mrow[0] = make_uint4(Mw[0], Mw[1], Mw[2], Mw[3]); mrow[1] = make_uint4(Mw[4], Mw[5], Mw[6], Mw[7]);
                 }
-                uint4 *xrow = reinterpret_cast<uint4 *>(DXr + (s & 1) * 512 + xb);
                 xrow[0] = make_uint4(dx[0], dx[1], dx[2], dx[3]); xrow[1] = make_uint4(dx[4], dx[5], dx[6], dx[7]);
-                uint4 *yrow = reinterpret_cast<uint4 *>(DYr + (s & 1) * 512 + xb);
                 yrow[0] = make_uint4(dy[0], dy[1], dy[2], dy[3]); yrow[1] = make_uint4(dy[4], dy[5], dy[6], dy[7]);
+            } else {
+                if (in_img) {
+                    mrow[0] = make_uint4(Mw[0], Mw[1], Mw[2], Mw[3]); mrow[1] = make_uint4(Mw[4], Mw[5], Mw[6], Mw[7]);
+                }
+                if (cand_new) {                            // only candidates' gradients are ever read back
+                    xrow[0] = make_uint4(dx[0], dx[1], dx[2], dx[3]); xrow[1] = make_uint4(dx[4], dx[5], dx[6], dx[7]);
+                    yrow[0] = make_uint4(dy[0], dy[1], dy[2], dy[3]); yrow[1] = make_uint4(dy[4], dy[5], dy[6], dy[7]);
+                }
             }
             // ---- NMS of row n = s - 1 (M rows n-1, n, n+1 in ring slots sa, sb, sc)
             const int n = s - 1;
             if (n >= q0) {
-                // spread the row's candidates over the lanes
-                uint32_t rem = cand_prev;
-                if (rem) {
-                    uint32_t at = atomicAdd(&qn[c], (uint32_t)__popc(rem));
-                    do {
-                        const int p = __ffs(rem) - 1;
-                        rem &= rem - 1;
-                        queue[at++] = (uint16_t)(xb + p);
-                    } while (rem);
+                uint32_t kw = 0;
+                if (__any_sync(0xffffffffu, cand_prev != 0)) {
+                    const uint2 res = nms_row(cand_prev, qbase, ws, sa, sb, sc, n & 1, vrow);
+                    kw = res.x; qbase = res.y;
                 }
-                __syncwarp();                              // queue, M row s and dx/dy rows are visible to every lane
-                const uint32_t total = *reinterpret_cast<volatile uint32_t *>(&qn[c]);
-                if (lane == 0) qn[o] = 0;                  // the other parity's counter: last read a row ago, next used a row ahead
-                const uint16_t *Ma = Mring + sa, *Mb = Mring + sb, *Mc = Mring + sc;
-                const uint16_t *dxp = DXr + (n & 1) * 512, *dyp = DYr + (n & 1) * 512;
-                for (uint32_t i = lane; i < total; i += 32) {
-                    const uint32_t x = queue[i];
-                    const int m = Mb[x];
-                    const uint32_t xr = dxp[x], yr = dyp[x];
-                    const int a = (int)(xr & 0x7FFFu), b = (int)(yr & 0x7FFFu);
-                    const int tg22x = a * 13573, ay = b << 15;
-                    const uint16_t *p1, *p2;
-                    int ge;                                // second comparison is >= for the axis-aligned sectors
-                    if (ay < tg22x) { p1 = Mb + x - 1; p2 = Mb + x + 1; ge = 1; }                    // horizontal gradient
-                    else if (ay > tg22x + (a << 16)) { p1 = Ma + x; p2 = Mc + x; ge = 1; }             // vertical
-                    else {                                 // diagonal: along (+1,+1) when the signs agree
-                        const int d = ((xr ^ yr) & 0x8000u) ? 1 : -1;
-                        p1 = Ma + x + d; p2 = Mc + x - d; ge = 0;
-                    }
-                    const int n1 = *p1, n2 = *p2;
-                    if (m > n1 && m + ge > n2) {
-                        const uint32_t xs = x - SPX;       // pixel inside the strip's 480 outputs
-                        atomicOr(&kbits[xs >> 5], 1u << (xs & 31));
-                        vdst[(uint32_t)n * (uint32_t)W + xs] = (uint8_t)(min(m, 256) - 1);
-                    }
-                }
-                __syncwarp();                              // all survivors are in kbits; ring slot sa is free again
-                if (lane < 16) {
-                    const uint32_t kw = kbits[lane];
-                    if (k_writer) kdst[(uint32_t)n * (uint32_t)WW] = kw;
-                    kbits[lane] = 0;
-                }
-            } else {
-                __syncwarp();
+                if (k_writer) *krow = kw;
+                krow += WW; vrow += W;
             }
             cand_prev = cand_new;
             const int t = sa; sa = sb; sb = sc; sc = t;
         };
-        for (int y = y_first;;) {
-            row_step(std::integral_constant<int, 0>{}, y);
-            if (++y > y_last) break;
-            row_step(std::integral_constant<int, 1>{}, y);
-            if (++y > y_last) break;
+        {
+            int y = y_first;
+            fill_step(std::integral_constant<int, 0>{}, y++);
+            fill_step(std::integral_constant<int, 1>{}, y++);
+            fill_step(std::integral_constant<int, 0>{}, y++);
+            fill_step(std::integral_constant<int, 1>{}, y++);
+            for (;;) {
+                row_step(std::integral_constant<int, 0>{}, y);
+                if (++y > y_last) break;
+                row_step(std::integral_constant<int, 1>{}, y);
+                if (++y > y_last) break;
+            }
         }
         __syncwarp();
         if (!redo) {
-            flush();
-            since_flush = 0;
 #pragma unroll
             for (int b = 0; b < 8; b++)
-                if (const uint32_t t = tot[b * 32 + lane]) atomicAdd(&A.hist[f * 256 + b * 32 + lane], t);
+                if (const uint32_t t = tab[b * 32 + lane]) atomicAdd(&A.hist[f * 256 + b * 32 + lane], t);
         }
+        __syncwarp();                                     // the table is zeroed again at the start of the next task
     }
 }
 
@@ -491,10 +530,18 @@ bool lane_fused_edge_supported(int H, int W, const void *frames)
     return (W % 16 == 0) && H >= 16 && ((uintptr_t)frames % 16 == 0) && (size_t)H * W * 3 < ((size_t)1 << 32);
 }
 
+static int fused_minb()
+{
+    // CTAs (of four warps) per SM: 4 = 128 registers per thread, 3 = 168 (LANE_K1F_MINB, A/B knob)
+    // measured on B200, 256 x 1080p: 3 -> 0.74 ms, 4 -> 0.88 ms (the 160 bytes of spills cost more than four more warps hide)
+    static const int minb = getenv("LANE_K1F_MINB") ? atoi(getenv("LANE_K1F_MINB")) : 3;
+    return minb == 4 ? 4 : 3;
+}
+
 static void fused_config(int n, int H, int W, int *band_rows, int *tail_frames, int *tail_rows)
 {
     const int sms = lane_sm_count();
-    const int n_strips = (W + STRIP_OUT - 1) / STRIP_OUT, warps = sms * 3 * FWARPS;
+    const int n_strips = (W + STRIP_OUT - 1) / STRIP_OUT, warps = sms * fused_minb() * FWARPS;
     static const int band_env = getenv("LANE_K1F_BAND") ? atoi(getenv("LANE_K1F_BAND")) : 0;
     static const int tail_env = getenv("LANE_K1F_TAIL") ? atoi(getenv("LANE_K1F_TAIL")) : -1;
     // every band re-reads 8 halo rows: 135-row bands cost 5.9 %; small batches get thinner bands so that every
@@ -514,14 +561,16 @@ static bool fused_launch(FusedArgs A, cudaStream_t st)
 {
     static bool configured[LANE_MAX_DEVICES];
     if (!configured[lane_cur_device()]) {
-        if (cudaFuncSetAttribute(k1_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, FWARPS * SM_WARP) != cudaSuccess) {
+        if (cudaFuncSetAttribute(k1_fused<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, FWARPS * SM_WARP) != cudaSuccess ||
+            cudaFuncSetAttribute(k1_fused<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, FWARPS * SM_WARP) != cudaSuccess) {
             cudaGetLastError();
             return false;
         }
         configured[lane_cur_device()] = true;
     }
     cudaMemsetAsync(A.task_counter, 0, sizeof(int), st);
-    k1_fused<<<lane_sm_count() * 3, FWARPS * 32, FWARPS * SM_WARP, st>>>(A);
+    if (fused_minb() == 3) k1_fused<3><<<lane_sm_count() * 3, FWARPS * 32, FWARPS * SM_WARP, st>>>(A);
+    else k1_fused<4><<<lane_sm_count() * 4, FWARPS * 32, FWARPS * SM_WARP, st>>>(A);
     return cudaPeekAtLastError() == cudaSuccess;
 }
 

@@ -36,19 +36,9 @@ constexpr int SPX = 16;
 constexpr int STRIP_OUT = 30 * SPX;
 
 struct K2Args {
-    const uint32_t *c_bits, *s_bits;   // [n][H][WW] candidate / strong planes from k2a_sobel_nms (unfused path)
-    // fused path (k1_fused.cu): NMS survivors K [n][H][WW] + their magnitudes V [n][H][W]; the thresholds are formed
-    // here from the histogram, and the candidate / strong planes only ever exist in shared memory
-    const uint32_t *k_bits;
-    const uint8_t *v_plane;            // null => unfused path
-    const uint32_t *hist;              // [n][256]
-    const uint8_t *lut_low, *lut_high;
-    int4 *thr;                         // [n] (median_x2, low, high, pre)
-    const int *pre;                    // [n] magnitude floor k1_fused used
-    int *pre_redo;                     // [n] floor for the redo pass (= the true low)
-    int *redo_list, *redo_count;       // frames whose floor was above the true low
+    const uint32_t *c_bits, *s_bits;   // [n][H][WW] candidate / strong planes (from k2a_sobel_nms or k2t_threshold)
+    const int *skip_flag;              // [n] or null: frames waiting for the redo pass (fused path) are skipped
     const int *frame_list, *n_list;    // redo pass: the frames to process (null = all)
-    uint32_t *dbg_c, *dbg_s;           // [n][H][WW] candidate / strong planes before hysteresis (verification taps) or null
     const uint32_t *roi_bits;      // [H][WW]
     int *n_edges, *rounds, *n_points;
     uint32_t *points;              // [n][max_points]
@@ -387,6 +377,89 @@ __device__ __forceinline__ void chase_column(uint32_t cA, uint32_t sA, uint32_t 
     }
 }
 
+// ---- K2t: thresholds + candidate / strong planes from the fused edge kernel's output -----------------------------
+// k1_fused leaves, per frame, the NMS survivors K (bit-plane) and their magnitudes V = min(m, 256) - 1 (byte plane, only
+// survivors' bytes valid) plus the histogram.  Here the median and the two Canny thresholds are formed (np.median + the
+// host LUT, lane_detector.py:79-81) and every survivor is classified: candidate iff m > low, strong iff m > high, i.e.
+// V >= low / V >= high.  One thread per 32-px word, 32 bytes of V fetched only for words that have survivors; massively
+// parallel, so the dependent V fetch costs nothing here (inside the hysteresis cluster it sat on the critical path).
+// A frame whose true low is below the floor `pre` k1_fused used (the sampled estimate was too high) is flagged and
+// listed for the redo pass instead.
+struct K2tArgs {
+    const uint32_t *k_bits;            // [n][H][WW]
+    const uint8_t *v_plane;            // [n][H][W]
+    const uint32_t *hist;              // [n][256]
+    const uint8_t *lut_low, *lut_high;
+    int4 *thr;                         // [n] (median_x2, low, high, floor used)
+    const int *pre;                    // [n] floor k1_fused used for this pass
+    int *pre_redo;                     // [n] floor for the redo pass (= the true low)
+    int *redo_list, *redo_count, *redo_flag;
+    const int *frame_list, *n_list;    // redo pass: frames to process (null = all)
+    uint32_t *c_bits, *s_bits;         // [n][H][WW]
+    int H, W, WW, words_per_cta;
+};
+
+__global__ void __launch_bounds__(256) k2t_threshold(K2tArgs A)
+{
+    __shared__ int s_low, s_high;
+    int f = blockIdx.y;
+    if (A.frame_list) {
+        if (f >= *A.n_list) return;
+        f = A.frame_list[f];
+    }
+    const int tid = threadIdx.x, lane = tid & 31;
+    if (tid < 32) {
+        const int m2 = median_x2_warp(A.hist + f * 256, (long long)A.H * A.W, lane);
+        int low = A.lut_low[m2], high = A.lut_high[m2];
+        if (low > high) { int t = low; low = high; high = t; }
+        if (lane == 0) {
+            s_low = low; s_high = high;
+            if (blockIdx.x == 0) {
+                const int pre = A.pre[f];
+                A.thr[f] = make_int4(m2, low, high, pre);
+                if (!A.frame_list) {
+                    const int redo = low < pre;
+                    A.redo_flag[f] = redo;
+                    if (redo) {
+                        A.pre_redo[f] = low;
+                        A.redo_list[atomicAdd(A.redo_count, 1)] = f;
+                    }
+                }
+            }
+        }
+    }
+    __syncthreads();
+    if (!A.frame_list && s_low < A.pre[f]) return;          // this frame's planes are rebuilt in the redo pass
+    const uint32_t lo4 = (uint32_t)s_low * 0x01010101u, hi4 = (uint32_t)s_high * 0x01010101u;
+    const int n_words = A.H * A.WW;
+    const uint32_t *kb = A.k_bits + (size_t)f * n_words;
+    uint32_t *cb = A.c_bits + (size_t)f * n_words, *sb = A.s_bits + (size_t)f * n_words;
+    const uint8_t *vb = A.v_plane + (size_t)f * A.H * A.W;
+    auto ge_bits = [](const uint4 &a, const uint4 &b, uint32_t t4) {
+        const uint32_t wds[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+        uint32_t m = 0;
+#pragma unroll
+        for (int q = 0; q < 8; q++)     // per byte 0/1 (V >= t), gathered into a nibble by one multiply
+            m |= ((((__vcmpgeu4(wds[q], t4) & 0x01010101u) * 0x01020408u) >> 24) & 0xFu) << (4 * q);
+        return m;
+    };
+    const int w0 = blockIdx.x * A.words_per_cta, w1 = min(w0 + A.words_per_cta, n_words);
+    for (int i = w0 + tid; i < w1; i += 256) {
+        const uint32_t k = kb[i];
+        uint32_t cw = 0, sw = 0;
+        if (k) {
+            const int r = i / A.WW, w = i - r * A.WW;
+            const uint4 *vp = reinterpret_cast<const uint4 *>(vb + (size_t)r * A.W + w * 32);
+            const uint4 a = __ldg(vp);
+            const uint4 b = (w * 32 + 16 < A.W) ? __ldg(vp + 1) : make_uint4(0, 0, 0, 0);
+            cw = k & ge_bits(a, b, lo4);
+            sw = k & ge_bits(a, b, hi4);
+        }
+        cb[i] = cw;
+        sb[i] = sw;
+    }
+}
+
 __global__ void __launch_bounds__(K2T, 3) k2_canny_cluster(K2Args A)
 {
     extern __shared__ __align__(128) uint32_t smem[];
@@ -405,30 +478,7 @@ __global__ void __launch_bounds__(K2T, 3) k2_canny_cluster(K2Args A)
     }
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int H = A.H, WW = A.WW, R = A.R;
-    const bool fused = A.v_plane != nullptr;
-    __shared__ int s_low, s_high;
-    if (fused) {
-        // thresholds of the frame from its histogram (np.median + the host LUT).  Every CTA of the cluster reads the same
-        // final values, so they all take the same decision below.
-        if (wid == 0) {
-            const int m2 = median_x2_warp(A.hist + f * 256, (long long)H * A.W, lane);
-            int low = A.lut_low[m2], high = A.lut_high[m2];
-            if (low > high) { int t = low; low = high; high = t; }
-            if (lane == 0) {
-                s_low = low; s_high = high;
-                if (rank == 0) A.thr[f] = make_int4(m2, low, high, A.pre[f]);
-            }
-        }
-        __syncthreads();
-        if (!A.frame_list && s_low < A.pre[f]) {
-            // the sampled floor was above the true low: K misses candidates.  List the frame for the redo pass.
-            if (rank == 0 && tid == 0) {
-                A.pre_redo[f] = s_low;
-                A.redo_list[atomicAdd(A.redo_count, 1)] = f;
-            }
-            return;
-        }
-    }
+    if (A.skip_flag && !A.frame_list && A.skip_flag[f]) return;      // cluster-uniform: every CTA reads the same flag
     const int b0 = rank * R, b1 = min(b0 + R, H), Rv = max(b1 - b0, 0);
     uint32_t *C = smem;                         // [R][WW]
     uint32_t *S = smem + (size_t)R * WW;        // [R+2][WW], row 0 / Rv+1 = neighbour bands
@@ -440,8 +490,7 @@ __global__ void __launch_bounds__(K2T, 3) k2_canny_cluster(K2Args A)
     // ---- phase 1 ran in k2a_sobel_nms: load this band's candidate / strong planes.  A band is one contiguous
     // run of Rv*WW words in each plane, so two bulk copies (TMA, completion on an mbarrier) bring it in.
     {
-        const uint32_t *cg = (fused ? A.k_bits : A.c_bits) + ((size_t)f * H + b0) * WW;
-        const uint32_t *sg = fused ? nullptr : A.s_bits + ((size_t)f * H + b0) * WW;
+        const uint32_t *cg = A.c_bits + ((size_t)f * H + b0) * WW, *sg = A.s_bits + ((size_t)f * H + b0) * WW;
         const bool bulk = (WW % 4 == 0) && Rv > 0;
         if (bulk) {
             const uint32_t bar = smem_u32(&s_bar);
@@ -452,49 +501,16 @@ __global__ void __launch_bounds__(K2T, 3) k2_canny_cluster(K2Args A)
             __syncthreads();
             if (tid == 0) {
                 const uint32_t bytes = (uint32_t)Rv * WW * 4u;
-                mbar_expect_tx(bar, fused ? bytes : 2 * bytes);
+                mbar_expect_tx(bar, 2 * bytes);
                 bulk_g2s(smem_u32(C), cg, bytes, bar);
-                if (!fused) bulk_g2s(smem_u32(S + WW), sg, bytes, bar);
+                bulk_g2s(smem_u32(S + WW), sg, bytes, bar);
             }
         } else {
-            for (int i = tid; i < Rv * WW; i += K2T) { C[i] = cg[i]; if (!fused) S[WW + i] = sg[i]; }
+            for (int i = tid; i < Rv * WW; i += K2T) { C[i] = cg[i]; S[WW + i] = sg[i]; }
         }
         for (int i = tid; i < WW; i += K2T) { S[i] = 0; S[(size_t)(Rv + 1) * WW + i] = 0; }
         for (int i = tid; i < (Rv * WW + 3) / 4; i += K2T) reinterpret_cast<volatile uint32_t *>(D)[i] = 0;
         if (bulk) mbar_wait(smem_u32(&s_bar), 0);
-        if (fused) {
-            // K / V -> candidate and strong words: a survivor is a candidate iff m > low and strong iff m > high, and
-            // V = min(m, 256) - 1, so both are byte compares V >= t.  Only words with survivors touch V (32 bytes each).
-            if (!bulk) __syncthreads();
-            const uint32_t lo4 = (uint32_t)s_low * 0x01010101u, hi4 = (uint32_t)s_high * 0x01010101u;
-            const uint8_t *vb = A.v_plane + ((size_t)f * H + b0) * A.W;
-            auto ge_bits = [](const uint4 &a, const uint4 &b, uint32_t t4) {
-                const uint32_t wds[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
-                uint32_t m = 0;
-#pragma unroll
-                for (int q = 0; q < 8; q++)     // per byte 0/1, gathered into a nibble by one multiply
-                    m |= ((((__vcmpgeu4(wds[q], t4) & 0x01010101u) * 0x01020408u) >> 24) & 0xFu) << (4 * q);
-                return m;
-            };
-            for (int i = tid; i < Rv * WW; i += K2T) {
-                const uint32_t k = C[i];
-                uint32_t cw = 0, sw = 0;
-                if (k) {
-                    const int r = i / WW, w = i - r * WW;
-                    const uint4 *vp = reinterpret_cast<const uint4 *>(vb + (size_t)r * A.W + w * 32);
-                    const uint4 a = __ldg(vp);
-                    const uint4 b = (w * 32 + 16 < A.W) ? __ldg(vp + 1) : make_uint4(0, 0, 0, 0);
-                    cw = k & ge_bits(a, b, lo4);
-                    sw = k & ge_bits(a, b, hi4);
-                    C[i] = cw;
-                }
-                S[WW + i] = sw;
-                if (A.dbg_c) {
-                    A.dbg_c[((size_t)f * H + b0) * WW + i] = cw;
-                    A.dbg_s[((size_t)f * H + b0) * WW + i] = sw;
-                }
-            }
-        }
     }
     __syncthreads();
     K2TICK(tL);
@@ -832,35 +848,42 @@ bool launch_canny_cluster(const uint8_t *blur, const uint32_t *hist, const uint8
     return true;
 }
 
-// Fused form, first pass: K2b straight from the K / V planes of k1_fused.  Frames whose magnitude floor turned out to be
-// above their true low are listed in redo_list (and skipped); launch_canny_cluster_redo finishes them after
-// launch_fused_edge_redo has rebuilt their planes.
+// Fused form: thresholds + candidate / strong planes from k1_fused's K / V planes (k2t_threshold), then K2b.
+// frame_list == null: first pass over frames 0..n-1; frames whose magnitude floor turned out to be above their true low
+// are flagged, listed in redo_list and skipped.  frame_list == redo_list: the redo pass, after launch_fused_edge_redo
+// has rebuilt those frames' planes with the exact floor.
 bool launch_canny_cluster_fused(const uint32_t *k_bits, const uint8_t *v_plane, const uint32_t *hist, const uint8_t *lut_low,
                                 const uint8_t *lut_high, const uint32_t *roi_bits, int4 *thr, const int *pre, int *pre_redo,
-                                int *redo_list, int *redo_count, const int *frame_list, int *n_edges, int *rounds,
-                                uint32_t *points, int *n_points, uint32_t *pmask_bits, uint32_t *edge_bits, uint32_t *dbg_c,
-                                uint32_t *dbg_s, LaneGeom g, int n, cudaStream_t st, int *launches)
+                                int *redo_list, int *redo_count, int *redo_flag, const int *frame_list, int *n_edges,
+                                int *rounds, uint32_t *points, int *n_points, uint32_t *pmask_bits, uint32_t *edge_bits,
+                                uint32_t *c_bits, uint32_t *s_bits, LaneGeom g, int n, cudaStream_t st, int *launches)
 {
     const int H = g.H, W = g.W, WW = (W + 31) / 32;
     int G = 1, R = 0;
     size_t smem = 0;
     if (!k2b_plan(H, W, &G, &R, &smem)) return false;
-    K2Args A{};
-    A.k_bits = k_bits; A.v_plane = v_plane; A.hist = hist; A.lut_low = lut_low; A.lut_high = lut_high; A.thr = thr;
-    A.pre = frame_list ? pre_redo : pre; A.pre_redo = pre_redo; A.redo_list = redo_list; A.redo_count = redo_count;
-    A.frame_list = frame_list; A.n_list = frame_list ? redo_count : nullptr;
-    A.dbg_c = dbg_c; A.dbg_s = dbg_s; A.roi_bits = roi_bits;
-    A.n_edges = n_edges; A.rounds = rounds; A.n_points = n_points; A.points = points;
-    A.pmask_bits = pmask_bits; A.edge_bits = edge_bits;
-    A.H = H; A.W = W; A.WW = WW; A.R = R; A.g = g;
     if (!frame_list) {
         cudaMemsetAsync(n_edges, 0, sizeof(int) * n, st);
         cudaMemsetAsync(n_points, 0, sizeof(int) * n, st);
         cudaMemsetAsync(redo_count, 0, sizeof(int), st);
     }
+    K2tArgs T{};
+    T.k_bits = k_bits; T.v_plane = v_plane; T.hist = hist; T.lut_low = lut_low; T.lut_high = lut_high; T.thr = thr;
+    T.pre = frame_list ? pre_redo : pre; T.pre_redo = pre_redo; T.redo_list = redo_list; T.redo_count = redo_count;
+    T.redo_flag = redo_flag; T.frame_list = frame_list; T.n_list = frame_list ? redo_count : nullptr;
+    T.c_bits = c_bits; T.s_bits = s_bits; T.H = H; T.W = W; T.WW = WW;
+    T.words_per_cta = 256 * 8;
+    dim3 tgrid((H * WW + T.words_per_cta - 1) / T.words_per_cta, n);
+    k2t_threshold<<<tgrid, 256, 0, st>>>(T);
+    K2Args A{};
+    A.c_bits = c_bits; A.s_bits = s_bits; A.skip_flag = redo_flag;
+    A.frame_list = frame_list; A.n_list = frame_list ? redo_count : nullptr; A.roi_bits = roi_bits;
+    A.n_edges = n_edges; A.rounds = rounds; A.n_points = n_points; A.points = points;
+    A.pmask_bits = pmask_bits; A.edge_bits = edge_bits;
+    A.H = H; A.W = W; A.WW = WW; A.R = R; A.g = g;
     cudaError_t e = k2b_launch(A, G, smem, n, st);
     if (e != cudaSuccess) { cudaGetLastError(); return false; }
-    *launches += 1;
+    *launches += 2;
     return true;
 }
 

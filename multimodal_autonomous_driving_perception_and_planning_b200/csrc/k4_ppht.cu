@@ -12,6 +12,7 @@
 #include "lane_common.cuh"
 
 #include <math.h>
+#include <type_traits>
 #include <stdio.h>
 #include <stdlib.h>
 
@@ -506,7 +507,8 @@ __global__ void __launch_bounds__(NT2) k4_ppht_v2(uint32_t *__restrict__ points_
 // 64-bit word per CTA per batch (first triggering point) and one per trigger (arg-max), exchanged
 // through DSMEM slots with a sequence number -- no cluster barrier on the hot path.
 constexpr int BATCH3 = 64;
-constexpr int LIST_CAP3 = 3072;
+constexpr int LIST_CAP3 = 3072;      // points of a frame kept in shared memory
+constexpr int OVER_CAP3 = 13312;     // further points kept in a private global (L2) extension of the list
 
 struct XchgSlots {
     unsigned long long v[2][16];   // [seq parity][source rank] = seq << 32 | payload
@@ -571,6 +573,7 @@ __device__ __forceinline__ int scell_get(const uint32_t *cells32, int cell)
 // bin over the batch (counts inside a batch are monotone, so no other bin can trigger earlier).
 __global__ void __launch_bounds__(416, 2) k4_ppht_v3(const uint32_t *__restrict__ points_all, const int *__restrict__ n_points,
                            const uint32_t *__restrict__ pmask_all, uint32_t *__restrict__ pmask_work,
+                           uint32_t *__restrict__ over_all,
                            const int2 *__restrict__ win, int cells_max, int G, int nvw, int tpa,
                            int32_t *__restrict__ lines_all, int *__restrict__ n_lines, LaneGeom g, LaneHoughParams hp, int prof)
 {
@@ -623,10 +626,16 @@ __global__ void __launch_bounds__(416, 2) k4_ppht_v3(const uint32_t *__restrict_
     if (tid < 32) { s_slots.v[0][tid & 15] = 0; s_slots.v[1][tid & 15] = 0; }
     const int count0 = n_points[f];
     const uint32_t *glist = points_all + (size_t)f * g.max_points;
-    uint32_t *list = s_list;
-    const bool dense = count0 > LIST_CAP3;          // point list does not fit: the frame is left to v2
-    if (!dense)
-        for (int i = tid; i < count0; i += blockDim.x) s_list[i] = glist[i];
+    // The list lives in shared memory up to LIST_CAP3 points; a longer one (every 4K generator frame: 3.3 k points)
+    // continues in this CTA's private global extension.  Swap-remove only ever touches a random index and the current
+    // tail, so once the list has shrunk below LIST_CAP3 everything is in shared memory again.
+    uint32_t *over = over_all + ((size_t)f * G + rank) * OVER_CAP3;
+    const bool dense = count0 > LIST_CAP3 + OVER_CAP3 || (count0 > LIST_CAP3 && !over_all);   // left to v2
+    if (!dense) {
+        for (int i = tid; i < min(count0, LIST_CAP3); i += blockDim.x) s_list[i] = glist[i];
+        for (int i = LIST_CAP3 + tid; i < count0; i += blockDim.x) __stcg(&over[i - LIST_CAP3], glist[i]);
+    }
+    const bool has_over = !dense && count0 > LIST_CAP3;
     const int n_batches = (count0 + BATCH3 - 1) / BATCH3;
     uint64_t rng = 0xFFFFFFFFFFFFFFFFull;
     int remaining = count0, nl = 0;
@@ -652,7 +661,17 @@ __global__ void __launch_bounds__(416, 2) k4_ppht_v3(const uint32_t *__restrict_
     // Producer warp: draw the next min(BATCH3, remaining) points.  The generator is a serial chain (lane 0),
     // the 64 remainders are independent (all lanes), and the swap-remove on the list runs four steps at a time
     // with the values a later step would have read forwarded in registers.
-    auto draw = [&](uint32_t *buf) {
+    auto draw_impl = [&](uint32_t *buf, auto over_tag) {
+        // OVER = false (the usual case) keeps the list accesses plain shared-memory loads and stores
+        constexpr bool OVER = decltype(over_tag)::value;
+        auto lget = [&](int i) -> uint32_t {
+            if constexpr (OVER) return i < LIST_CAP3 ? s_list[i] : __ldcg(&over[i - LIST_CAP3]);
+            else return s_list[i];
+        };
+        auto lset = [&](int i, uint32_t v) {
+            if constexpr (OVER) { if (i < LIST_CAP3) s_list[i] = v; else __stcg(&over[i - LIST_CAP3], v); }
+            else s_list[i] = v;
+        };
         const int P = remaining < BATCH3 ? remaining : BATCH3;
         if (lane == 0) {
             for (int k = 0; k < P; k++) {
@@ -668,8 +687,8 @@ __global__ void __launch_bounds__(416, 2) k4_ppht_v3(const uint32_t *__restrict_
             for (; k + 4 <= P; k += 4) {
                 const int i0 = s_rnd[k], i1 = s_rnd[k + 1], i2 = s_rnd[k + 2], i3 = s_rnd[k + 3];
                 const int l0 = remaining - k - 1, l1 = l0 - 1, l2 = l0 - 2, l3 = l0 - 3;
-                uint32_t a0 = list[i0], a1 = list[i1], a2 = list[i2], a3 = list[i3];
-                uint32_t b0 = list[l0], b1 = list[l1], b2 = list[l2], b3 = list[l3];
+                uint32_t a0 = lget(i0), a1 = lget(i1), a2 = lget(i2), a3 = lget(i3);
+                uint32_t b0 = lget(l0), b1 = lget(l1), b2 = lget(l2), b3 = lget(l3);
                 // step 0 writes list[i0] = b0; later reads of slot i0 must see it, and so on down the chain
                 if (i1 == i0) a1 = b0;
                 if (l1 == i0) b1 = b0;
@@ -678,16 +697,19 @@ __global__ void __launch_bounds__(416, 2) k4_ppht_v3(const uint32_t *__restrict_
                 if (i3 == i2) a3 = b2; else if (i3 == i1) a3 = b1; else if (i3 == i0) a3 = b0;
                 if (l3 == i2) b3 = b2; else if (l3 == i1) b3 = b1; else if (l3 == i0) b3 = b0;
                 buf[k] = a0; buf[k + 1] = a1; buf[k + 2] = a2; buf[k + 3] = a3;
-                list[i0] = b0; list[i1] = b1; list[i2] = b2; list[i3] = b3;   // in order: later steps win
+                lset(i0, b0); lset(i1, b1); lset(i2, b2); lset(i3, b3);       // in order: later steps win
             }
             for (; k < P; k++) {
                 const int i = s_rnd[k], l = remaining - k - 1;
-                buf[k] = list[i];
-                list[i] = list[l];
+                buf[k] = lget(i);
+                lset(i, lget(l));
             }
         }
         remaining -= P;
         __syncwarp();
+    };
+    auto draw = [&](uint32_t *buf) {
+        if (has_over) draw_impl(buf, std::true_type{}); else draw_impl(buf, std::false_type{});
     };
     if (producer && n_batches > 0) draw(s_buf[0]);
     __syncthreads();
@@ -1043,7 +1065,7 @@ void launch_ppht_v2(uint32_t *points, const int *n_points, uint32_t *pmask, uint
 
 // v3 launch: false if the geometry does not fit (caller uses v2)
 bool launch_ppht_v3(const uint32_t *points, const int *n_points, const uint32_t *pmask, uint32_t *pmask_work,
-                    const int2 *win3, int cells_max, int G, int32_t *lines, int *n_lines, LaneGeom g,
+                    uint32_t *list_over, const int2 *win3, int cells_max, int G, int32_t *lines, int *n_lines, LaneGeom g,
                     LaneHoughParams hp, int n, cudaStream_t st, int *launches)
 {
     if (G < 1 || (g.bh * ((g.W + 31) / 32)) % 4 != 0 || ((uintptr_t)pmask % 16) != 0) return false;
@@ -1068,7 +1090,7 @@ bool launch_ppht_v3(const uint32_t *points, const int *n_points, const uint32_t 
     attr[0].val.clusterDim.x = G; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    cudaError_t e = cudaLaunchKernelEx(&cfg, k4_ppht_v3, points, n_points, pmask, pmask_work, win3, cells_max, G, nvw, tpa,
+    cudaError_t e = cudaLaunchKernelEx(&cfg, k4_ppht_v3, points, n_points, pmask, pmask_work, list_over, win3, cells_max, G, nvw, tpa,
                                        lines, n_lines, g, hp, getenv("LANE_B200_PPHT_PROF") ? 1 : 0);
     if (e != cudaSuccess) { cudaGetLastError(); return false; }
     *launches += 1;
@@ -1076,6 +1098,7 @@ bool launch_ppht_v3(const uint32_t *points, const int *n_points, const uint32_t 
 }
 
 int lane_ppht_list_cap_v3() { return LIST_CAP3; }
+int lane_ppht_over_cap_v3() { return OVER_CAP3; }
 
 // Plan the v3 layout: smallest cluster size whose per-CTA cell count fits shared memory.  win3[n] = (rmin_n,
 // first cell inside CTA n % G).  Returns G (0 if nothing fits) and *cells_max.

@@ -40,7 +40,8 @@ struct lane_ctx {
     std::string err;
 
     // device buffers
-    uint8_t *d_frames = nullptr;      // staging for host frames (lazy)
+    uint8_t *d_frames = nullptr;      // staging for host frames / BGR output of the NV12 conversion (lazy)
+    uint8_t *d_nv12 = nullptr;        // staging for host NV12 frames (lazy)
     uint8_t *d_blur = nullptr;        // blurred plane: unfused path and verification taps only (lazy)
     uint32_t *d_kbits = nullptr;      // [B][H][WW] NMS survivors of the fused edge kernel
     uint8_t *d_vplane = nullptr;      // [B][H][W]  their magnitudes (sparse: only survivors' bytes are ever written / read)
@@ -70,6 +71,7 @@ struct lane_ctx {
     int ppht_v1 = 0, ppht_v2 = 0;     // LANE_B200_K4=v1|v2 pins an older PPHT kernel (A/B checks)
     int2 *d_win3 = nullptr;           // v3 layout: (rmin, first cell inside the owning CTA)
     uint32_t *d_pmask_work = nullptr; // [B][G3][bh][WW] private mask copies of the v3 cluster CTAs
+    uint32_t *d_list_over = nullptr;  // [B][G3][over_cap] private extensions of the v3 point list (ROIs with many pixels)
     int G3 = 0, cells_max3 = 0;
     LaneFitScratch fit{};
     int *d_stream_id = nullptr;
@@ -77,6 +79,13 @@ struct lane_ctx {
     uint8_t *d_prev_valid = nullptr;
     int stream_cap = 0;
     int32_t *d_std_accum = nullptr;
+    // batched standard Hough (lane_hough_lines_batch), allocated on first use
+    int32_t *d_hb_accum = nullptr, *d_hb_sorted = nullptr;
+    int2 *d_hb_tmp = nullptr;
+    int *d_hb_count = nullptr;
+    int hb_cap = 0;
+    bool hb_accum_ready = false;
+    cudaEvent_t hb_ev[2] = {};
     int2 *d_peaks = nullptr;
     int *d_n_peaks = nullptr;
     int *d_task_counter = nullptr;
@@ -134,12 +143,12 @@ cudaError_t dalloc(T **p, size_t count)
 void free_all(lane_ctx *c)
 {
     cudaSetDevice(c->device);
-    void *ptrs[] = {c->d_frames, c->d_blur, c->d_kbits, c->d_vplane, c->d_pre, c->d_cls, c->d_cls_dbg, c->d_roi, c->d_pmask, c->d_gray_dbg, c->d_hist,
-                    c->d_roi_bits, c->d_pmask_bits, c->d_edge_bits, c->d_dbg_c, c->d_dbg_s, c->d_accum16, c->d_win, c->d_win3, c->d_pmask_work,
+    void *ptrs[] = {c->d_frames, c->d_nv12, c->d_blur, c->d_kbits, c->d_vplane, c->d_pre, c->d_cls, c->d_cls_dbg, c->d_roi, c->d_pmask, c->d_gray_dbg, c->d_hist,
+                    c->d_roi_bits, c->d_pmask_bits, c->d_edge_bits, c->d_dbg_c, c->d_dbg_s, c->d_accum16, c->d_win, c->d_win3, c->d_pmask_work, c->d_list_over,
                     c->d_points, c->d_points_dbg, c->d_lut, c->d_thr, c->d_seedsA, c->d_seedsB, c->d_seed_count,
                     c->d_n_edges, c->d_n_points, c->d_rounds, c->d_n_lines, c->d_accum, c->d_lines, c->fit.raw, c->fit.big,
                     c->fit.side_n, c->fit.side_flags, c->d_stream_id, c->d_prev_fit, c->d_prev_valid,
-                    c->slots[0].d_records, c->slots[1].d_records, c->d_std_accum, c->d_peaks, c->d_n_peaks, c->d_task_counter};
+                    c->slots[0].d_records, c->slots[1].d_records, c->d_std_accum, c->d_hb_accum, c->d_hb_sorted, c->d_hb_tmp, c->d_hb_count, c->d_peaks, c->d_n_peaks, c->d_task_counter};
     for (void *p : ptrs)
         if (p) cudaFree(p);
     free(c->h_roi);
@@ -154,6 +163,8 @@ void free_all(lane_ctx *c)
     for (auto &e : c->copy_ev)
         if (e) cudaEventDestroy(e);
     if (c->start_ev) cudaEventDestroy(c->start_ev);
+    for (auto &e : c->hb_ev)
+        if (e) cudaEventDestroy(e);
     delete c->pool;
     for (auto &p : c->h_stage)
         if (p) cudaFreeHost(p);
@@ -249,31 +260,36 @@ int run_stages(lane_ctx *c, const uint8_t *frames_dev, int off, int m, const int
         if (!c->d_kbits) {
             CU(dalloc(&c->d_kbits, (size_t)c->max_batch * planes));
             CU(dalloc(&c->d_vplane, (size_t)c->max_batch * P));
-            CU(dalloc(&c->d_pre, (size_t)c->max_batch * 3 + 4));
+            CU(dalloc(&c->d_pre, (size_t)c->max_batch * 4 + 4));
         }
         if (c->debug) { rc = ensure_blur(c); if (rc) return rc; }
         const size_t B = (size_t)c->max_batch;
-        int *pre = c->d_pre + o, *pre_redo = c->d_pre + B + o, *redo_list = c->d_pre + 2 * B + o, *redo_count = c->d_pre + 3 * B;
+        int *pre = c->d_pre + o, *pre_redo = c->d_pre + B + o, *redo_list = c->d_pre + 2 * B + o, *redo_flag = c->d_pre + 3 * B + o,
+            *redo_count = c->d_pre + 4 * B;
         uint32_t *kb = c->d_kbits + o * planes;
         uint8_t *vp = c->d_vplane + o * P, *bd = c->debug ? c->d_blur + o * P : nullptr;
-        uint32_t *dc = c->debug ? cb : nullptr, *ds = c->debug ? sb : nullptr;
         int *LK = &L[LANE_STAGE_BLUR_HIST], *LC = &L[LANE_STAGE_CANNY];
         if (launch_fused_edge(fr, c->d_lut, hist, pre, kb, vp, bd, c->d_task_counter, m, H, W, c->st, LK)) {
             rc = stage_check(c, "k1_fused"); if (rc) return rc;
             if (timed) { rc = mark(c, LANE_STAGE_CANNY); if (rc) return rc; }
             fused = launch_canny_cluster_fused(kb, vp, hist, c->d_lut, c->d_lut + 511, c->d_roi_bits, thr, pre, pre_redo,
-                                               redo_list, redo_count, nullptr, n_edges, rounds, points, n_points, pmask_bits,
-                                               edge_bits, dc, ds, g, m, c->st, LC) &&
+                                               redo_list, redo_count, redo_flag, nullptr, n_edges, rounds, points, n_points,
+                                               pmask_bits, edge_bits, cb, sb, g, m, c->st, LC) &&
                     // frames whose sampled floor was above their true low (normally none): rebuild K / V with the exact
                     // floor and finish them; both kernels return at once when the list is empty
                     launch_fused_edge_redo(fr, redo_list, redo_count, pre_redo, kb, vp, bd, c->d_task_counter, m, H, W, c->st, LC) &&
                     launch_canny_cluster_fused(kb, vp, hist, c->d_lut, c->d_lut + 511, c->d_roi_bits, thr, pre, pre_redo,
-                                               redo_list, redo_count, redo_list, n_edges, rounds, points, n_points,
-                                               pmask_bits, edge_bits, dc, ds, g, m, c->st, LC);
+                                               redo_list, redo_count, redo_flag, redo_list, n_edges, rounds, points, n_points,
+                                               pmask_bits, edge_bits, cb, sb, g, m, c->st, LC);
         }
         if (!fused) fprintf(stderr, "lane_b200: fused edge path rejected by device %d, using the unfused kernels\n", c->device);
         c->last_cluster = fused;
         rc = stage_check(c, "k2_canny_cluster (fused input)"); if (rc) return rc;
+        if (getenv("LANE_B200_SYNC_DEBUG")) {
+            int nredo = 0;
+            cudaMemcpy(&nredo, redo_count, sizeof(int), cudaMemcpyDeviceToHost);
+            if (nredo) fprintf(stderr, "lane_b200: %d of %d frames redone with the exact magnitude floor\n", nredo, m);
+        }
     }
     c->last_paths = fused ? LANE_PATH_FUSED_EDGE : 0;
     if (!fused) {
@@ -321,7 +337,7 @@ int run_stages(lane_ctx *c, const uint8_t *frames_dev, int off, int m, const int
         // up the frames v3 flagged (point list larger than its shared-memory list), or runs alone if v3 cannot launch.
         bool v3 = !c->ppht_v2 && c->G3 > 0 &&
                   launch_ppht_v3(points, n_points, pmask_bits, c->d_pmask_work + o * c->G3 * std::max(g.bh, 1) * WW,
-                                 c->d_win3, c->cells_max3, c->G3, lines, n_lines, g, c->hp, m, c->st, &L[LANE_STAGE_PPHT]);
+                                 c->d_list_over ? c->d_list_over + o * c->G3 * lane_ppht_over_cap_v3() : nullptr, c->d_win3, c->cells_max3, c->G3, lines, n_lines, g, c->hp, m, c->st, &L[LANE_STAGE_PPHT]);
         launch_ppht_v2(points, n_points, pmask_bits, c->d_accum16 + o * (c->cells_per_frame / 2), c->d_win,
                        c->cells_per_frame, lines, n_lines, g, c->hp, m, c->st, &L[LANE_STAGE_PPHT], v3 ? 1 : 0);
         if (v3) c->last_paths |= LANE_PATH_PPHT_DSMEM;
@@ -340,7 +356,7 @@ int run_stages(lane_ctx *c, const uint8_t *frames_dev, int off, int m, const int
 // copied on a second stream while the previous chunk computes (the EMA state stays on the device across chunks,
 // which run in order on the compute stream).
 int enqueue(lane_ctx *c, const uint8_t *frames, bool on_device, int n, const int32_t *stream_id, int S,
-            const double *prev_fit, const uint8_t *prev_valid)
+            const double *prev_fit, const uint8_t *prev_valid, bool nv12 = false)
 {
     int rc = LANE_OK;
     lane_ctx::slot_t &sl = c->slots[c->cur];
@@ -353,12 +369,21 @@ int enqueue(lane_ctx *c, const uint8_t *frames, bool on_device, int n, const int
     }
     const int32_t *sid = stream_id ? c->d_stream_id : nullptr;
     const uint8_t *frames_dev = frames;
+    const size_t bgr_bytes = (size_t)c->g.H * c->g.W * 3;
+    if (nv12 && !c->d_frames) CU(dalloc(&c->d_frames, (size_t)c->max_batch * bgr_bytes));
     if (on_device) {
-        rc = run_stages(c, frames, 0, n, sid, S, c->profiling);
+        if (nv12) {                                  // decoder output already on the device: convert, then the usual path
+            launch_nv12_to_bgr(frames, c->d_frames, n, c->g.H, c->g.W, c->st);
+            frames_dev = c->d_frames;
+        }
+        rc = run_stages(c, frames_dev, 0, n, sid, S, c->profiling);
         if (rc) return rc;
     } else {
-        const size_t bytes = (size_t)c->g.H * c->g.W * 3;
-        if (!c->d_frames) CU(dalloc(&c->d_frames, (size_t)c->max_batch * bytes));
+        // bytes per frame that cross PCIe: 3 B/px for BGR, 1.5 B/px for NV12 (converted on the device, chunk by chunk)
+        const size_t bytes = nv12 ? bgr_bytes / 2 : bgr_bytes;
+        if (!c->d_frames) CU(dalloc(&c->d_frames, (size_t)c->max_batch * bgr_bytes));
+        if (nv12 && !c->d_nv12) CU(dalloc(&c->d_nv12, (size_t)c->max_batch * bytes));
+        uint8_t *d_in = nv12 ? c->d_nv12 : c->d_frames;
         if (!c->copy_st) {
             CU(cudaStreamCreateWithFlags(&c->copy_st, cudaStreamNonBlocking));
             for (auto &e : c->copy_ev) CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
@@ -389,7 +414,7 @@ int enqueue(lane_ctx *c, const uint8_t *frames, bool on_device, int n, const int
         for (int off = 0; off < n; off += chunk, k++) {
             const int m = std::min(chunk, n - off);
             if (!pageable) {
-                CU(cudaMemcpyAsync(c->d_frames + (size_t)off * bytes, frames + (size_t)off * bytes, bytes * m,
+                CU(cudaMemcpyAsync(d_in + (size_t)off * bytes, frames + (size_t)off * bytes, bytes * m,
                                    cudaMemcpyHostToDevice, c->copy_st));
             } else {
                 const size_t total = bytes * m;
@@ -398,7 +423,7 @@ int enqueue(lane_ctx *c, const uint8_t *frames, bool on_device, int n, const int
                     const size_t nb = std::min(LANE_STAGE_BYTES, total - done);
                     if (c->stage_used[slot]) CU(cudaEventSynchronize(c->stage_ev[slot]));   // its last DMA has left
                     c->pool->run(c->h_stage[slot], frames + (size_t)off * bytes + done, nb);
-                    CU(cudaMemcpyAsync(c->d_frames + (size_t)off * bytes + done, c->h_stage[slot], nb, cudaMemcpyHostToDevice,
+                    CU(cudaMemcpyAsync(d_in + (size_t)off * bytes + done, c->h_stage[slot], nb, cudaMemcpyHostToDevice,
                                        c->copy_st));
                     CU(cudaEventRecord(c->stage_ev[slot], c->copy_st));
                     c->stage_used[slot] = true;
@@ -407,6 +432,8 @@ int enqueue(lane_ctx *c, const uint8_t *frames, bool on_device, int n, const int
             cudaEvent_t ev = c->copy_ev[k % LANE_COPY_EVENTS];
             CU(cudaEventRecord(ev, c->copy_st));
             CU(cudaStreamWaitEvent(c->st, ev, 0));
+            if (nv12)
+                launch_nv12_to_bgr(c->d_nv12 + (size_t)off * bytes, c->d_frames + (size_t)off * bgr_bytes, m, c->g.H, c->g.W, c->st);
             rc = run_stages(c, c->d_frames, off, m, sid, S, false);
             if (rc) return rc;
         }
@@ -599,8 +626,13 @@ int lane_set_roi_mask(lane_ctx *c, const uint8_t *mask)
         CU(cudaMemcpy(c->d_win3, win3, sizeof(win3), cudaMemcpyHostToDevice));
         if (c->d_pmask_work) cudaFree(c->d_pmask_work);
         c->d_pmask_work = nullptr;
-        if (c->G3 > 0)
+        if (c->d_list_over) cudaFree(c->d_list_over);
+        c->d_list_over = nullptr;
+        if (c->G3 > 0) {
             CU(dalloc(&c->d_pmask_work, (size_t)c->max_batch * c->G3 * std::max(g.bh, 1) * WW));
+            if (cnt > lane_ppht_list_cap_v3())       // the ROI can hold more edge pixels than the shared-memory list
+                CU(dalloc(&c->d_list_over, (size_t)c->max_batch * c->G3 * lane_ppht_over_cap_v3()));
+        }
     }
     CU(dalloc(&c->d_pmask_bits, (size_t)c->max_batch * std::max(g.bh, 1) * WW));
     CU(dalloc(&c->d_points, (size_t)c->max_batch * g.max_points));
@@ -731,6 +763,24 @@ int lane_detect_batch(lane_ctx *c, const uint8_t *frames, int frames_on_device, 
     return lane_detect_collect(c, prev_fit, prev_valid, out);
 }
 
+int lane_detect_batch_nv12(lane_ctx *c, const uint8_t *frames_nv12, int frames_on_device, int n, const int32_t *stream_id,
+                           int n_streams, double *prev_fit, uint8_t *prev_valid, lane_record *out)
+{
+    int rc = check_call(c, frames_nv12, n, n_streams, prev_fit, prev_valid);
+    if (rc) return rc;
+    if (!out) return fail(c, LANE_ERR_INVALID, "out is null");
+    if ((c->g.H | c->g.W) & 1) return fail(c, LANE_ERR_INVALID, "NV12 needs even width and height (%dx%d)", c->g.W, c->g.H);
+    CU(cudaSetDevice(c->device));
+    if (stream_id)
+        for (int i = 0; i < n; i++)
+            if (stream_id[i] < 0 || stream_id[i] >= n_streams)
+                return fail(c, LANE_ERR_INVALID, "stream_id[%d]=%d outside [0,%d)", i, stream_id[i], n_streams);
+    if (c->profiling) CU(cudaEventRecord(c->slots[c->cur].ev[LANE_STAGE_H2D], c->st));
+    rc = enqueue(c, frames_nv12, frames_on_device != 0, n, stream_id, n_streams, prev_fit, prev_valid, true);
+    if (rc) return rc;
+    return lane_detect_collect(c, prev_fit, prev_valid, out);
+}
+
 int lane_get_stage_ms(lane_ctx *c, float ms[LANE_NUM_STAGES], int32_t launches[LANE_NUM_STAGES])
 {
     if (!c) return LANE_ERR_INVALID;
@@ -853,6 +903,46 @@ int lane_hough_accumulator(lane_ctx *c, int fi, int32_t *accum_host, int thresho
     }
     CU(cudaStreamSynchronize(c->st));
     if (n_peaks) *n_peaks = found;
+    return LANE_OK;
+}
+
+int lane_hough_lines_batch(lane_ctx *c, int threshold, int max_peaks, int32_t *peaks_host, int32_t *n_peaks_host,
+                           int32_t *accum_host, float *device_ms)
+{
+    if (!c || max_peaks < 1 || !peaks_host || !n_peaks_host) return LANE_ERR_INVALID;
+    if (c->q_count) return fail(c, LANE_ERR_STATE, "collect the batch first");
+    const int n = c->slots[c->cur].n;
+    if (n < 1) return fail(c, LANE_ERR_STATE, "no batch has run on this context");
+    CU(cudaSetDevice(c->device));
+    const LaneGeom &g = c->g;
+    const size_t cells = (size_t)(LANE_NUM_ANGLES + 2) * (g.numrho + 2), B = (size_t)c->max_batch;
+    if (max_peaks > c->hb_cap) {
+        for (void **p : {(void **)&c->d_hb_sorted, (void **)&c->d_hb_tmp}) {
+            if (*p) cudaFree(*p);
+            *p = nullptr;
+        }
+        CU(dalloc(&c->d_hb_sorted, B * max_peaks * 3));
+        CU(dalloc(&c->d_hb_tmp, B * max_peaks));
+        c->hb_cap = max_peaks;
+    }
+    if (!c->d_hb_count) {
+        CU(dalloc(&c->d_hb_count, B));
+        CU(cudaEventCreate(&c->hb_ev[0]));
+        CU(cudaEventCreate(&c->hb_ev[1]));
+    }
+    if (accum_host && !c->d_hb_accum) CU(dalloc(&c->d_hb_accum, B * cells));
+    CU(cudaEventRecord(c->hb_ev[0], c->st));
+    if (!launch_hough_batch(c->d_edge_bits, c->d_roi_bits, accum_host ? c->d_hb_accum : nullptr, c->d_hb_tmp, c->d_hb_sorted,
+                            c->d_hb_count, g, threshold, max_peaks, n, c->st))
+        return fail(c, LANE_ERR_UNSUPPORTED, "frame %dx%d: a Hough row does not fit shared memory", g.W, g.H);
+    CU(cudaEventRecord(c->hb_ev[1], c->st));
+    CU(cudaMemcpyAsync(n_peaks_host, c->d_hb_count, sizeof(int) * n, cudaMemcpyDeviceToHost, c->st));
+    CU(cudaMemcpyAsync(peaks_host, c->d_hb_sorted, sizeof(int32_t) * (size_t)n * max_peaks * 3, cudaMemcpyDeviceToHost, c->st));
+    if (accum_host)
+        CU(cudaMemcpyAsync(accum_host, c->d_hb_accum, sizeof(int32_t) * (size_t)n * cells, cudaMemcpyDeviceToHost, c->st));
+    CU(cudaStreamSynchronize(c->st));
+    CU(cudaGetLastError());
+    if (device_ms) CU(cudaEventElapsedTime(device_ms, c->hb_ev[0], c->hb_ev[1]));
     return LANE_OK;
 }
 

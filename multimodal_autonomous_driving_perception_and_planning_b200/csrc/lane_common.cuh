@@ -66,6 +66,9 @@ bool launch_fused_edge_redo(const uint8_t *frames, const int *frame_list, const 
                             cudaStream_t st, int *launches);
 void launch_gray_debug(const uint8_t *frame, uint8_t *gray, int H, int W, cudaStream_t st);
 
+// ---- K0b: NV12 -> BGR (device pointers, enqueued on st) ---------------------------------
+void launch_nv12_to_bgr(const uint8_t *src, uint8_t *dst, int n, int H, int W, cudaStream_t st);
+
 // ---- K2 ---------------------------------------------------------------------------------
 // thr: int4 per frame = (median_x2, low, high, 0)
 void launch_thresholds(const uint32_t *hist, const uint8_t *lut_low, const uint8_t *lut_high, int4 *thr,
@@ -89,9 +92,9 @@ bool launch_canny_cluster(const uint8_t *blur, const uint32_t *hist, const uint8
                           int *task_counter, LaneGeom g, int n, cudaStream_t st, int *launches);
 bool launch_canny_cluster_fused(const uint32_t *k_bits, const uint8_t *v_plane, const uint32_t *hist, const uint8_t *lut_low,
                                 const uint8_t *lut_high, const uint32_t *roi_bits, int4 *thr, const int *pre, int *pre_redo,
-                                int *redo_list, int *redo_count, const int *frame_list, int *n_edges, int *rounds,
-                                uint32_t *points, int *n_points, uint32_t *pmask_bits, uint32_t *edge_bits, uint32_t *dbg_c,
-                                uint32_t *dbg_s, LaneGeom g, int n, cudaStream_t st, int *launches);
+                                int *redo_list, int *redo_count, int *redo_flag, const int *frame_list, int *n_edges,
+                                int *rounds, uint32_t *points, int *n_points, uint32_t *pmask_bits, uint32_t *edge_bits,
+                                uint32_t *c_bits, uint32_t *s_bits, LaneGeom g, int n, cudaStream_t st, int *launches);
 void launch_bytes_to_bits(const uint8_t *bytes, uint32_t *bits, int n, int rows, int W, int row_stride,
                           cudaStream_t st, int *launches);
 void launch_mask_rows(const uint32_t *edge_bits, const uint32_t *roi_bits, uint32_t *pmask_bits, LaneGeom g, int n,
@@ -102,6 +105,10 @@ void launch_hough_accum(const uint32_t *points, const int *n_points, int32_t *ac
                         cudaStream_t st);
 void launch_hough_peaks(const int32_t *accum_padded, int numrho, int threshold, int2 *peaks, int max_peaks,
                         int *n_peaks, cudaStream_t st);
+// batched form: every frame of the batch, from the edge bit-planes (edge & ROI), peaks ordered on the device
+bool launch_hough_batch(const uint32_t *edge_bits, const uint32_t *roi_bits, int32_t *accum, int2 *peaks_tmp,
+                        int32_t *peaks_sorted, int *n_peaks, LaneGeom g, int threshold, int max_peaks, int n,
+                        cudaStream_t st);
 void lane_upload_tables();       // trig tables -> __constant__ (both Hough variants)
 void lane_upload_tables_std();
 
@@ -119,8 +126,10 @@ int lane_ppht_windows(const uint8_t *mask, int H, int W, int2 *win);   // return
 // v3: cells in distributed shared memory, cluster of G CTAs per frame, angle n owned by CTA n % G
 int lane_ppht_plan_v3(const int2 *win, int cells_total, int2 *win3, int *cells_max);
 int lane_ppht_list_cap_v3();
+int lane_ppht_over_cap_v3();
+// list_over: [n][G][lane_ppht_over_cap_v3()] private list extensions (null = frames above the shared list go to v2)
 bool launch_ppht_v3(const uint32_t *points, const int *n_points, const uint32_t *pmask_bits, uint32_t *pmask_work,
-                    const int2 *win3, int cells_max, int G, int32_t *lines, int *n_lines, LaneGeom g,
+                    uint32_t *list_over, const int2 *win3, int cells_max, int G, int32_t *lines, int *n_lines, LaneGeom g,
                     LaneHoughParams hp, int n, cudaStream_t st, int *launches);
 
 // ---- K5 ---------------------------------------------------------------------------------

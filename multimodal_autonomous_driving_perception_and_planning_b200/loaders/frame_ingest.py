@@ -70,6 +70,35 @@ class FrameIngest:
             raise _native.LaneError(rc, (lib.lane_last_error(None) or b"").decode())
         return dst
 
+    def from_nv12(self, frames):
+        """Decoder output -> BGR: ``frames`` uint8 ``[N, H*3/2, W]`` in NV12 layout (numpy or CUDA tensor) becomes
+        ``[N, H, W, 3]``, equal to ``cv2.cvtColor(f, cv2.COLOR_YUV2BGR_NV12)`` per frame, followed by the resize when
+        ``target_size`` is set (what ``VideoDataLoader.read_frame`` returns for that frame)."""
+        shape = tuple(frames.shape)
+        if len(shape) != 3 or shape[1] % 3 or shape[2] % 2 or (shape[1] * 2 // 3) % 2:
+            raise cv2.error(f"FrameIngest: expected NV12 frames [N, H*3/2, W] with even H and W, got {shape}")
+        if str(frames.dtype).replace("torch.", "") != "uint8":
+            raise cv2.error(f"FrameIngest: expected uint8 frames, got {frames.dtype}")
+        n, h, w = shape[0], shape[1] * 2 // 3, shape[2]
+        lib = _native.lib()
+        if isinstance(frames, np.ndarray):
+            src = np.ascontiguousarray(frames)
+            dst = np.empty((n, h, w, 3), np.uint8)
+            rc = lib.lane_nv12_to_bgr_batch(src.ctypes.data_as(C.c_void_p), n, h, w, dst.ctypes.data_as(C.c_void_p), 0,
+                                            self._device_index(), None)
+        else:
+            import torch
+            if not frames.is_cuda:
+                raise cv2.error("FrameIngest: torch input must be a CUDA tensor (pass numpy for host frames)")
+            src = frames.contiguous()
+            dst = torch.empty((n, h, w, 3), dtype=torch.uint8, device=src.device)
+            stream = torch.cuda.current_stream(src.device).cuda_stream
+            rc = lib.lane_nv12_to_bgr_batch(C.c_void_p(src.data_ptr()), n, h, w, C.c_void_p(dst.data_ptr()), 1,
+                                            src.device.index, C.c_void_p(stream))
+        if rc:
+            raise _native.LaneError(rc, (lib.lane_last_error(None) or b"").decode())
+        return self.resize_batch(dst)
+
     def resize(self, frame: np.ndarray) -> np.ndarray:
         """One frame, as ``read_frame`` does it."""
         return self.resize_batch(frame[None])[0]

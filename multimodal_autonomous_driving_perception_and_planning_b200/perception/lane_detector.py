@@ -137,9 +137,13 @@ class LaneDetector:
             out.append((pair[0], pair[1]))
         return out
 
-    def _run(self, frames, stream_id, n_streams, prev_fit, prev_valid) -> np.ndarray:
-        """Chunked native calls over frames [N,H,W,3] (numpy or CUDA torch); state arrays updated in place."""
+    def _run(self, frames, stream_id, n_streams, prev_fit, prev_valid, nv12: bool = False) -> np.ndarray:
+        """Chunked native calls over frames [N,H,W,3] (numpy or CUDA torch; [N,H*3/2,W] when ``nv12``); state arrays
+        updated in place."""
         n, h, w = int(frames.shape[0]), int(frames.shape[1]), int(frames.shape[2])
+        if nv12:
+            h = h * 2 // 3
+        fbytes = h * w * 3 // 2 if nv12 else h * w * 3
         ctx = self._context(h, w, n, frames)
         s, oms = self.smoothing_factor, 1 - self.smoothing_factor
         chunks = []
@@ -153,8 +157,8 @@ class LaneDetector:
 
         def call(c, a, b):
             sid = None if stream_id is None else stream_id[a:b]
-            src = frames.data_ptr() + a * h * w * 3 if on_device else frames[a:b]
-            return c.detect(src, b - a, on_device, sid, n_streams, prev_fit, prev_valid, s, oms)
+            src = frames.data_ptr() + a * fbytes if on_device else frames[a:b]
+            return c.detect(src, b - a, on_device, sid, n_streams, prev_fit, prev_valid, s, oms, nv12=nv12)
 
         for a in range(0, n, ctx.max_batch):
             b = min(a + ctx.max_batch, n)
@@ -216,6 +220,28 @@ class LaneDetector:
         recs = self._run(frames, None, 1, fit, valid)
         lanes = self._lanes_from_records(recs)
         # like the reference (:210-216), prev_*_fit aliases the last returned polynomial of that side
+        for left, right in lanes:
+            if left is not None:
+                self.prev_left_fit = left.polynomial
+            if right is not None:
+                self.prev_right_fit = right.polynomial
+        return lanes
+
+    def detect_batch_nv12(self, frames) -> List[LanePair]:
+        """``detect_batch`` for frames still in a video decoder's NV12 layout: uint8 ``[N, H*3/2, W]`` (Y plane, then
+        the interleaved half-resolution UV plane), numpy or CUDA tensor.  Equal to ``detect_batch`` on
+        ``cv2.cvtColor(f, cv2.COLOR_YUV2BGR_NV12)`` of every frame -- the conversion runs on the device, so a host batch
+        moves 1.5 B/px over PCIe instead of 3."""
+        shape = tuple(frames.shape)
+        if len(shape) != 3 or shape[1] % 3 or shape[2] % 2 or (shape[1] * 2 // 3) % 2:
+            raise cv2.error(f"LaneDetector: expected NV12 frames of shape [N, H*3/2, W] with even H and W, got {shape}")
+        if str(frames.dtype).replace("torch.", "") != "uint8":
+            raise cv2.error(f"LaneDetector: frames must be uint8, got {frames.dtype}")
+        if shape[0] == 0:
+            return []
+        fit, valid = self._state_arrays()
+        recs = self._run(frames, None, 1, fit, valid, nv12=True)
+        lanes = self._lanes_from_records(recs)
         for left, right in lanes:
             if left is not None:
                 self.prev_left_fit = left.polynomial

@@ -121,3 +121,81 @@ def test_second_device_in_one_process_takes_the_fast_paths():
             assert det2._ctx.device == dev and det2.last_records.tobytes() == want.tobytes()
             det2.close()
         det.close()
+
+
+# ---- NV12 ingest (second half) -----------------------------------------------------------
+@pytest.mark.parametrize("h,w", [(480, 640), (1080, 1920), (34, 18), (2, 2), (66, 250)])
+def test_nv12_to_bgr_matches_cv2_and_oracle(h, w):
+    import torch
+    from multimodal_autonomous_driving_perception_and_planning_b200 import FrameIngest
+    from oracle import nv12 as onv
+    rng = np.random.default_rng(h + w)
+    nv12 = rng.integers(0, 256, (3, h * 3 // 2, w), dtype=np.uint8)
+    want = np.stack([cv2.cvtColor(f, cv2.COLOR_YUV2BGR_NV12) for f in nv12])
+    ing = FrameIngest(None)
+    got_host = ing.from_nv12(nv12)
+    got_dev = ing.from_nv12(torch.from_numpy(nv12).cuda())
+    assert got_host.dtype == np.uint8 and got_host.shape == want.shape
+    assert np.array_equal(got_host, want) and np.array_equal(got_dev.cpu().numpy(), want)
+    assert np.array_equal(got_host[0], onv.nv12_to_bgr(nv12[0]))
+
+
+def test_detect_batch_nv12_equals_detect_batch_on_converted_frames():
+    """Host NV12 frames (1.5 B/px over PCIe) -> device conversion -> lane path == cv2.cvtColor + detect_batch, and
+    == the cv2 reference pipeline on the converted frames."""
+    import torch
+    from oracle import nv12 as onv
+    frames = gen_frames(1920, 1080, 6)
+    nv12 = np.stack([onv.bgr_to_nv12_for_tests(f) for f in frames])
+    bgr = np.stack([cv2.cvtColor(f, cv2.COLOR_YUV2BGR_NV12) for f in nv12])
+    a = LaneDetector(max_batch=4)
+    la = a.detect_batch_nv12(nv12)                      # two chunks, host input
+    ra = a.last_records.copy()
+    b = LaneDetector(max_batch=6)
+    b.detect_batch(bgr)
+    assert ra.tobytes() == b.last_records.tobytes()
+    c = LaneDetector(max_batch=6)
+    c.detect_batch_nv12(torch.from_numpy(nv12).cuda())  # device input
+    assert c.last_records.tobytes() == ra.tobytes()
+    ref = Cv2LaneOracle()
+    for i in range(6):
+        _same_lanes(la[i], ref.detect(bgr[i]), 1080)
+    with pytest.raises(cv2.error):
+        a.detect_batch_nv12(np.zeros((1, 100, 64), np.uint8))
+    for d in (a, b, c):
+        d.close()
+
+
+# ---- batched standard Hough (north-star kernel #3) -----------------------------------------------------------
+@pytest.mark.parametrize("w,h,n", [(640, 480, 6), (1920, 1080, 3), (250, 66, 2)])
+def test_hough_lines_batch_matches_cv2_and_oracle(w, h, n):
+    """Accumulators bit-exact against the oracle's restatement of cv2.HoughLines' voting, peaks (votes included, order
+    included) against the oracle and against cv2.HoughLinesWithAccumulator itself -- every frame of the batch, no debug
+    mode."""
+    from oracle import stages as S
+    rng = np.random.default_rng(w)
+    frames = gen_frames(w, h, n) if w >= 640 else [rng.integers(0, 256, (h, w, 3), dtype=np.uint8) for _ in range(n)]
+    det = LaneDetector(max_batch=n)
+    det.detect_batch(np.stack(frames))
+    for thr in (5, 50):
+        peaks, counts, acc, ms = det._ctx.hough_lines_batch(n, threshold=thr, max_peaks=1 << 15, with_accum=True)
+        ref = Cv2LaneOracle()
+        for i, f in enumerate(frames):
+            masked = ref.masked(ref.edges(ref.blurred(f)))
+            want_acc = S.hough_accum(masked)
+            assert np.array_equal(acc[i], want_acc), (w, h, i)
+            want_peaks = S.hough_peaks(want_acc, h, w, thr)
+            assert counts[i] == len(want_peaks) and np.array_equal(peaks[i], want_peaks), (w, h, i, thr)
+            lines = cv2.HoughLinesWithAccumulator(masked, 1, np.pi / 180, thr)
+            if lines is None:
+                assert counts[i] == 0
+            else:
+                lines = lines.reshape(-1, 3)
+                numrho = 2 * (w + h) + 1
+                assert np.array_equal(lines[:, 2].astype(np.int32), peaks[i][:, 2])
+                assert np.allclose(lines[:, 0], peaks[i][:, 0] - (numrho - 1) * 0.5)
+                assert np.allclose(lines[:, 1], peaks[i][:, 1] * np.float32(np.pi / 180), atol=1e-5)
+    # peaks-only production form gives the same lists
+    peaks2, counts2, acc2, _ = det._ctx.hough_lines_batch(n, threshold=50, max_peaks=256)
+    assert acc2 is None and all(np.array_equal(a, b) for a, b in zip(peaks, peaks2))
+    det.close()
