@@ -12,12 +12,18 @@ with one NCCL gather per step (BASELINE config 3 semantics).
 
 value   frames/s with the frames already resident in HBM when the timed region starts.
 e2e     frames/s through the public API (LaneDetector.detect_batch) with HOST (pinned) frames:
-        host->device copy and device->host records inside the timed region.
-roofline  K1 (fused gray+blur+histogram), algorithmic 4 B/px (3 B/px BGR read + 1 B/px plane write,
-        SURVEY.md 8d) over its CUDA-event time measured live on the launching stream; roofline.edge_path
-        is the same 4 B/px over K1 + K2a + K2b (everything from BGR frames to the edge map and point list).
+        host->device copy and device->host records inside the timed region.  e2e.pcie_frac relates the bytes/s it moves to
+        a plain pinned cudaMemcpyAsync of the same payload measured in the same process (with every rank copying at the
+        same time): the host->device link is what bounds it.  e2e_nv12 is the same leg with the frames in a video
+        decoder's NV12 layout (1.5 B/px over the link, converted to BGR on the device, bit-exact vs cv2).
+roofline  the EDGE PATH -- everything from BGR frames to the Canny edge map and ROI point list: k1_probe + k1_fused
+        (gray + blur + histogram + Sobel + NMS), k2t_threshold, k2_canny_cluster -- algorithmic 4 B/px (3 B/px BGR read +
+        1 B/px edge-map write, SURVEY.md 8d) over its CUDA-event time measured live on the launching stream;
+        roofline.k1_fused is the same figure for the fused kernel's stage alone.
 cpu_baseline  the reference's OpenCV path (oracle/cv2_pipeline.py: the reference call sequence on
         the same cv2/numpy) on this box's host cores, bounded sample.
+--config3  BASELINE config 3 instead of the weak-scaling default: an 8-camera 1080p rig, --frames-per-stream frames per
+        camera, whole streams sharded over the N ranks (8/N cameras per GPU, strong scaling), records gathered to rank 0.
 """
 import argparse
 import json
@@ -147,6 +153,8 @@ def main():
     ap.add_argument("--cpu-frames", type=int, default=1024, help="CPU baseline sample: frames per host core")
     ap.add_argument("--skip-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
     ap.add_argument("--skip-e2e", action="store_true", help="skip the e2e leg (profiling runs)")
+    ap.add_argument("--config3", action="store_true", help="BASELINE config 3: 8 cameras sharded by stream (strong scaling)")
+    ap.add_argument("--frames-per-stream", type=int, default=512, help="config 3: frames per camera per step")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -194,7 +202,7 @@ def main():
 
     import torch
     import torch.distributed as dist
-    from multimodal_autonomous_driving_perception_and_planning_b200 import LaneDetector, _native, multi_camera_batch
+    from multimodal_autonomous_driving_perception_and_planning_b200 import LaneDetector, _native
 
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
@@ -202,58 +210,83 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
 
     # ---- inputs: this rank's camera stream(s); generated on the host with cv2, uploaded once
-    n = args.frames
-    host = multi_camera_batch(1, n, W, H, period=args.distinct)[0] if world == 1 else None
-    if world > 1:
-        from multimodal_autonomous_driving_perception_and_planning_b200 import SyntheticDataGenerator
-        host = np.empty((n, H, W, 3), np.uint8)
-        d = min(args.distinct, n)
-        SyntheticDataGenerator(W, H).generate_batch(d, start_frame=rank * 1000, out=host[:d])
-        for t in range(d, n):
-            host[t] = host[t % d]
-    pinned = torch.from_numpy(host).pin_memory()
-    frames_dev = pinned.to(dev, non_blocking=False)
+    from multimodal_autonomous_driving_perception_and_planning_b200 import SyntheticDataGenerator, bgr_to_nv12
+    from multimodal_autonomous_driving_perception_and_planning_b200.distributed import RecordGatherer, streams_of_rank
+
+    def make_stream(cam, t):
+        """t frames of camera `cam`: --distinct generator frames (phase cam * 1000) tiled in time."""
+        out = np.empty((t, H, W, 3), np.uint8)
+        d = min(args.distinct, t)
+        SyntheticDataGenerator(W, H).generate_batch(d, start_frame=cam * 1000, out=out[:d])
+        for i in range(d, t):
+            out[i] = out[i % d]
+        return out
+
+    if args.config3:
+        cams = streams_of_rank(8, world, rank)               # whole cameras per rank: 8/N each
+        n = args.frames_per_stream                           # frames per native call = one camera's sequence
+    else:
+        cams = [rank]
+        n = args.frames
+    S = len(cams)
+    host_streams = [make_stream(c, n) for c in cams]
+    pinned = torch.from_numpy(host_streams[0][:min(n, args.frames)]).pin_memory()    # the e2e leg's host batch
+    dev_streams = [torch.from_numpy(h).to(dev) for h in host_streams]
     torch.cuda.synchronize()
+    frames_step = S * n                                      # frames this rank processes per step
 
     det = LaneDetector(device=local, max_batch=n)
-    ctx = det._context(H, W, n)                           # native context for n frames per call
+    ctx = det._context(H, W, n)                              # native context for n frames per call
     stream = torch.cuda.ExternalStream(ctx.stream(), device=dev)
-    prev_fit = np.zeros((1, 2, 3), np.float64)
-    prev_valid = np.zeros((1, 2), np.uint8)
-    rec_bytes = _native.RECORD_DTYPE.itemsize * n
-    from multimodal_autonomous_driving_perception_and_planning_b200.distributed import RecordGatherer
+    prev_fit = np.zeros((S, 2, 3), np.float64)
+    prev_valid = np.zeros((S, 2), np.uint8)
+    rec_bytes = _native.RECORD_DTYPE.itemsize * frames_step
     gatherer = RecordGatherer(n, dev) if world > 1 else None
+    sids = [np.full(n, k, np.int32) for k in range(S)]
 
-    pending = [None]                                      # records of the previous step, not gathered yet
-    queued = [0]                                          # batches in flight on the context
+    # Streaming form of the C ABI: a step is one native batch per camera of this rank.  Batches are enqueued two deep with the
+    # EMA state carried on the device (exactly the state chain of calling detect() frame after frame on one detector
+    # per camera), so the GPU goes from one batch's last kernel to the next batch's first without waiting for the host; all
+    # batches run in order on one stream.  The records of every batch are gathered to rank 0 (the path's only
+    # collective, NCCL over NVLink) straight from the context's device copy: lane_ctx_records_device stays valid until the
+    # batch after next is enqueued, and the context's stream waits for the gather before that slot is reused.
+    state = {"queued": 0, "next": 0, "first": True, "last_recs": None, "last_bufs": None}
 
-    def step(last=False):
-        # Streaming form of the C ABI: the next batch is enqueued before the previous one is collected, with the EMA
-        # state carried on the device (exactly the state chain of calling detect() frame after frame), so the GPU goes
-        # from one batch's last kernel to the next batch's first without waiting for the host.  All batches run in
-        # order on one stream; nothing overlaps.  The previous step's record gather (the path's only collective, NCCL
-        # over NVLink) is issued while the kernels run.  `last` ends a run of steps: K steps = K batches + K gathers.
-        if queued[0] == 0:
-            ctx.enqueue(frames_dev.data_ptr(), n, None, 1, prev_fit, prev_valid, 0.7, 1 - 0.7)   # explicit state
-            queued[0] += 1
-        if not last:
-            ctx.enqueue(frames_dev.data_ptr(), n, None, 1, None, None, 0.7, 1 - 0.7)            # queued behind it
-            queued[0] += 1
-        if world > 1 and pending[0] is not None:
-            gatherer.gather(pending[0], to_host=False)
-        recs = ctx.collect(prev_fit, prev_valid)
-        queued[0] -= 1
-        pending[0] = recs
-        return recs
+    def enqueue_next():
+        k = state["next"] % S
+        if state["first"]:
+            ctx.enqueue(dev_streams[k].data_ptr(), n, sids[k], S, prev_fit, prev_valid, 0.7, 1 - 0.7)   # explicit state
+            state["first"] = False
+        else:
+            ctx.enqueue(dev_streams[k].data_ptr(), n, sids[k], S, None, None, 0.7, 1 - 0.7)            # state on the device
+        state["next"] += 1
+        state["queued"] += 1
 
-    def flush():
-        while queued[0]:
-            ctx.collect(prev_fit, prev_valid)
-            queued[0] -= 1
-        if world > 1 and pending[0] is not None:
-            gatherer.gather(pending[0], to_host=False)
-            stream.wait_stream(torch.cuda.current_stream(dev))   # the timing event below fires after the gather
-        pending[0] = None
+    def run_batches(total, on_collect=None):
+        """total batches through the two-deep queue; every collected batch is gathered (N > 1)."""
+        done = 0
+        issued = 0
+        while issued < min(2, total):
+            enqueue_next(); issued += 1
+        while done < total:
+            recs = ctx.collect(prev_fit, prev_valid)
+            state["queued"] -= 1
+            done += 1
+            state["last_recs"] = recs
+            if on_collect:
+                on_collect()
+            ev = None
+            if gatherer is not None:
+                state["last_bufs"] = gatherer.gather_device(ctx.records_device_ptr(), to_host=False)
+                ev = torch.cuda.Event()
+                ev.record(torch.cuda.current_stream(dev))
+            if issued < total:
+                if ev is not None:
+                    stream.wait_event(ev)                    # the slot's records are still being read by the collective
+                enqueue_next(); issued += 1
+        if gatherer is not None:
+            stream.wait_stream(torch.cuda.current_stream(dev))   # timing events on the context's stream see the gathers
+        state["first"] = True                                # the next run starts from the host copy of the state again
 
     def barrier():
         if world > 1:
@@ -262,27 +295,25 @@ def main():
 
     sampler = ClockSampler(local) if rank == 0 else None
     t_load0 = time.perf_counter()
-    nw = max(args.warmup, 3)
-    for i in range(nw):
-        recs = step(last=(i == nw - 1))
-    flush()
-    found = int(recs["side"]["valid"].sum())
+    run_batches(max(args.warmup, 3) * S)
+    found = int(state["last_recs"]["side"]["valid"].sum())
 
     # ---- timed region: value (device-resident inputs)
     ctx.set_profiling(True)
     stage_sum = {k: 0.0 for k in _native.STAGE_NAMES}
-    launches = 0
+    launches = [0]
+
+    def account():
+        ms, ln = ctx.stage_ms()
+        for k in stage_sum:
+            stage_sum[k] += ms[k]
+        launches[0] += sum(ln.values())
+
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t0 = time.perf_counter()
     e0.record(stream)
-    for i in range(args.steps):
-        step(last=(i == args.steps - 1))
-        ms, ln = ctx.stage_ms()
-        for k in stage_sum:
-            stage_sum[k] += ms[k]
-        launches += sum(ln.values())
-    flush()
+    run_batches(args.steps * S, account)
     e1.record(stream)
     barrier()
     t1 = time.perf_counter()
@@ -293,33 +324,89 @@ def main():
         tm = torch.tensor([dev_ms], device=dev)
         dist.all_reduce(tm, op=dist.ReduceOp.MAX)
         dev_ms = float(tm.item())
-    value = args.gpus * n * args.steps / (dev_ms / 1e3)
+    total_frames = frames_step * args.steps
+    if world > 1:
+        tf = torch.tensor([total_frames], device=dev, dtype=torch.int64)
+        dist.all_reduce(tf)
+        total_frames = int(tf.item())
+    value = total_frames / (dev_ms / 1e3)
+
+    # ---- multi-GPU correctness, outside the timed region: did rank 0 receive every rank's records?
+    gather_verified, lanes_per_rank = None, None
+    if world > 1:
+        import hashlib
+        local_hash = int.from_bytes(hashlib.sha256(state["last_recs"].tobytes()).digest()[:7], "little")
+        hashes = [torch.zeros(1, dtype=torch.int64, device=dev) for _ in range(world)]
+        dist.all_gather(hashes, torch.tensor([local_hash], dtype=torch.int64, device=dev))
+        if rank == 0:
+            got = [b.cpu().numpy().view(_native.RECORD_DTYPE) for b in state["last_bufs"]]
+            mine = [int.from_bytes(hashlib.sha256(g.tobytes()).digest()[:7], "little") for g in got]
+            gather_verified = mine == [int(h.item()) for h in hashes]
+            lanes_per_rank = [int(g["side"]["valid"].sum()) for g in got]
 
     # ---- e2e: public API with host (pinned) frames, H2D + records D2H inside the timed region
     host_frames = pinned.numpy()
-    det.reset()
-    off = None
+    ne = host_frames.shape[0]
     e2e_steps = 0 if args.skip_e2e else args.steps
-    for _ in range(2 if e2e_steps else 0):
-        det.detect_batch(host_frames)
-    barrier()
-    t2 = time.perf_counter()
-    for _ in range(e2e_steps):
-        lanes = det.detect_batch(host_frames)
-        off = det.get_lane_center_offset(W, *lanes[-1])
-    barrier()
-    e2e_s = max(time.perf_counter() - t2, 1e-9)
-    if world > 1:
-        tm = torch.tensor([e2e_s], device=dev)
-        dist.all_reduce(tm, op=dist.ReduceOp.MAX)
-        e2e_s = float(tm.item())
-    e2e_val = args.gpus * n * e2e_steps / e2e_s
+
+    def e2e_leg(call, arg):
+        det.reset()
+        for _ in range(2 if e2e_steps else 0):
+            call(arg)
+        barrier()
+        t = time.perf_counter()
+        last = None
+        for _ in range(e2e_steps):
+            lanes = call(arg)
+            last = det.get_lane_center_offset(W, *lanes[-1])
+        barrier()
+        sec = max(time.perf_counter() - t, 1e-9)
+        if world > 1:
+            tt = torch.tensor([sec], device=dev)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            sec = float(tt.item())
+        return args.gpus * ne * e2e_steps / sec, sec, last
+
+    e2e_val, e2e_s, off = e2e_leg(det.detect_batch, host_frames)
+    # the same leg with the frames in a decoder's NV12 layout: half the bytes over the link, converted on the device
+    nv12_val, nv12_bytes = None, 0
+    if e2e_steps:
+        nv12 = torch.from_numpy(bgr_to_nv12(host_frames)).pin_memory().numpy()
+        nv12_bytes = int(nv12.nbytes)
+        nv12_val, _, _ = e2e_leg(det.detect_batch_nv12, nv12)
+        del nv12
+    # the roof of the e2e leg: a plain pinned copy of the same payload, every rank copying at the same time
+    pcie_gbs = None
+    if e2e_steps:
+        dst = torch.empty(host_frames.nbytes, dtype=torch.uint8, device=dev)
+        src = pinned.view(-1)
+        quarter = (src.numel() + 3) // 4
+
+        def plain_copy():
+            for a in range(0, src.numel(), quarter):
+                dst[a:a + quarter].copy_(src[a:a + quarter], non_blocking=True)
+
+        for _ in range(2):
+            plain_copy()
+        barrier()
+        tc = time.perf_counter()
+        reps = max(3, e2e_steps // 2)
+        for _ in range(reps):
+            plain_copy()
+        barrier()
+        sec = max(time.perf_counter() - tc, 1e-9)
+        if world > 1:
+            tt = torch.tensor([sec], device=dev)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            sec = float(tt.item())
+        pcie_gbs = host_frames.nbytes * reps / sec / 1e9        # per GPU, with all N ranks copying
+        del dst
     clocks = None
     if sampler:
         # nvidia-smi samples every 20 ms: the timed region alone is tens of ms, so the record spans everything that ran
-        # under load (warm-up, timed region, e2e leg) and says how many samples fell inside the timed region itself
+        # under load (warm-up, timed region, e2e legs) and says how many samples fell inside the timed region itself
         clocks = sampler.stop(t_load0, time.perf_counter())
-        clocks["window"] = "warm-up + timed region + e2e leg"
+        clocks["window"] = "warm-up + timed region + e2e legs"
         clocks["samples_in_timed_region"] = sum(1 for (t, _) in sampler.lines if timed_window[0] <= t <= timed_window[1])
 
     if rank == 0:
@@ -329,31 +416,54 @@ def main():
         except OSError:
             pass
         peak = float(peaks.get("hbm_gbs", 6650.0))
-        k1_ms = stage_sum["blur_hist"] / args.steps
-        achieved = n * ALGO_BYTES_PER_FRAME / (k1_ms / 1e3) / 1e9 if k1_ms > 0 else 0.0
-        canny_ms = (stage_sum["canny"] + stage_sum["compact"]) / args.steps
-        edge_achieved = n * ALGO_BYTES_PER_FRAME / ((k1_ms + canny_ms) / 1e3) / 1e9 if k1_ms > 0 else 0.0
+        batches = args.steps * S
+        k1_ms = stage_sum["blur_hist"] / batches             # per native batch of n frames
+        canny_ms = (stage_sum["canny"] + stage_sum["compact"]) / batches
+        edge_ms = k1_ms + canny_ms
+        algo = n * ALGO_BYTES_PER_FRAME
+        edge_achieved = algo / (edge_ms / 1e3) / 1e9 if edge_ms > 0 else 0.0
+        k1_achieved = algo / (k1_ms / 1e3) / 1e9 if k1_ms > 0 else 0.0
+        # dram__bytes_read.sum + dram__bytes_write.sum of the edge-path kernels of one 256 x 1080p batch, exported from the
+        # committed ncu capture (profiles/r2_edge_traffic.json names the report and the per-kernel figures)
+        traffic, traffic_src = None, None
+        try:
+            tr = json.load(open(os.path.join(ROOT, "profiles", "r2_edge_traffic.json")))
+            if n == tr.get("frames_per_launch") and (W, H) == tuple(tr.get("resolution", ())):
+                traffic, traffic_src = float(tr["edge_path_dram_bytes"]), "profiles/r2_edge_traffic.json"
+        except (OSError, ValueError, KeyError):
+            pass
+        e2e_bytes_s = ne * ALGO_BYTES_PER_FRAME * 0.75 * e2e_steps / e2e_s if e2e_steps else 0.0   # 3 B/px per GPU
         out = dict(base, value=value, ms_per_step=dev_ms / args.steps, dtype="u8/int32/f64",
-                   config={"workload": workload, "frames_per_gpu_per_step": n, "resolution": [W, H],
-                           "l2_policy": "inputs larger than L2 (1.6 GB of frames per step vs 126 MB L2)",
+                   scaling="strong" if args.config3 else "weak",
+                   config={"workload": workload if not args.config3 else
+                           (f"BASELINE configs[2]: 8-camera 1920x1080 rig, {n} frames per camera per step ({args.distinct} "
+                            f"distinct generator frames per camera tiled in time), whole cameras sharded over the GPUs, "
+                            f"records gathered to rank 0, full detect path"),
+                           "frames_per_gpu_per_step": frames_step, "frames_per_native_batch": n, "resolution": [W, H],
+                           "l2_policy": "inputs larger than L2 (1.6 GB of frames per 256-frame batch vs 126 MB L2)",
                            "parallelism": f"stream-sharded x{args.gpus}, NCCL gather of records only"},
-                   roofline={"bound": "hbm", "kernel": "K1 blur_hist (gray + 5x5 blur + histogram)",
-                             "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                   roofline={"bound": "hbm",
+                             "kernel": "edge path: k1_probe + k1_fused (gray, 5x5 blur, histogram, Sobel, NMS) + k2t_threshold + "
+                                       "k2_canny_cluster (hysteresis, ROI, point list)",
+                             "achieved": edge_achieved, "peak": peak, "unit": "GB/s", "frac": edge_achieved / peak,
                              "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 (of fallback)",
-                             # dram__bytes_read.sum + dram__bytes_write.sum of one k1_strip launch (256 x 1080p), from
-                             # the ncu --set full capture summarised in profiles/r1_final_ncu_summary.md
-                             "traffic": (2.180e9 if (n == 256) else None), "traffic_source": "profiles/r1_final_ncu_summary.md",
-                             "ms_per_launch": k1_ms,
-                             "algorithmic_bytes_per_launch": n * ALGO_BYTES_PER_FRAME,
-                             # SURVEY 8d also asks for the same 4 B/px over ALL edge kernels (BGR in -> edge map out):
-                             # K1 + K2a (Sobel/NMS) + K2b (hysteresis/ROI/compaction); those two are issue/latency bound
-                             "edge_path": {"kernels": "K1 + K2a + K2b", "ms": k1_ms + canny_ms,
-                                           "achieved": edge_achieved, "frac": edge_achieved / peak}},
-                   stage_ms_per_step={k: v / args.steps for k, v in stage_sum.items()},
+                             "traffic": traffic, "traffic_source": traffic_src,
+                             "ms_per_launch": edge_ms, "algorithmic_bytes_per_launch": algo,
+                             "frac_of_nominal_8TBs": edge_achieved / 8000.0,
+                             "k1_fused": {"ms": k1_ms, "achieved": k1_achieved, "frac": k1_achieved / peak}},
+                   stage_ms_per_batch={k: v / batches for k, v in stage_sum.items()},
                    e2e={"value": e2e_val, "unit": "frames/s", "h2d_bytes_per_step": int(host_frames.nbytes),
-                        "d2h_bytes_per_step": int(rec_bytes), "api": "LaneDetector.detect_batch(numpy pinned)"},
-                   gpu_launches=launches, clocks=clocks, lanes_found_last_step=found,
+                        "d2h_bytes_per_step": int(_native.RECORD_DTYPE.itemsize * ne),
+                        "api": "LaneDetector.detect_batch(numpy pinned)",
+                        "pcie_gbs_plain_copy_per_gpu": pcie_gbs,
+                        "pcie_frac": (e2e_bytes_s / 1e9 / pcie_gbs) if pcie_gbs else None},
+                   e2e_nv12={"value": nv12_val, "unit": "frames/s", "h2d_bytes_per_step": nv12_bytes,
+                             "api": "LaneDetector.detect_batch_nv12(numpy pinned): NV12 -> BGR on the device, bit-exact vs cv2"},
+                   gpu_launches=launches[0], clocks=clocks, lanes_found_last_batch=found,
                    last_offset=None if off is None else float(off))
+        if world > 1:
+            out["gather_verified"] = gather_verified
+            out["lanes_found_per_rank_at_rank0"] = lanes_per_rank
         if cpu_baseline:
             out["cpu_baseline"] = cpu_baseline
         print(json.dumps(out))

@@ -1,9 +1,9 @@
 """B200-native batched lane detection: a drop-in for the lane-detection hot path of
 bhavyageethika/multimodal_autonomous_driving_perception_and_planning
 (``src/perception/lane_detector.py``).  See DESIGN.md / INTEGRATION.md at the repo root."""
-from .generators import SyntheticDataGenerator, multi_camera_batch
+from .generators import SyntheticDataGenerator, bgr_to_nv12, multi_camera_batch
 from .loaders import FrameIngest
 from .perception import LaneDetector, LaneLine
 
-__all__ = ["FrameIngest", "LaneDetector", "LaneLine", "SyntheticDataGenerator", "multi_camera_batch"]
+__all__ = ["FrameIngest", "LaneDetector", "LaneLine", "SyntheticDataGenerator", "bgr_to_nv12", "multi_camera_batch"]
 __version__ = "0.1.0"

@@ -197,6 +197,11 @@ struct FusedArgs {
     const int *n_list;             // redo pass: number of entries in frame_list (device memory)
     uint32_t *hist;                // [n][256]; not touched in the redo pass (it is final already)
     const int *pre;                // [n] magnitude floor of the frame
+    // first pass: the warp that finishes a frame last turns its histogram into the Canny thresholds
+    int *frame_done;               // [n] tasks of the frame finished so far (zeroed by the launcher)
+    const uint8_t *lut_low, *lut_high;
+    int4 *thr;                     // [n] (2 * median, low, high, floor used)
+    int *pre_redo, *redo_list, *redo_count, *redo_flag;   // frames whose true low is below the floor: redone with pre = low
     uint32_t *k_bits;              // [n][H][WW]
     uint8_t *v_plane;              // [n][H][W]
     uint8_t *blur_dbg;             // [n][H][W] or null: the blurred plane, for the verification taps only
@@ -482,6 +487,26 @@ __global__ void __launch_bounds__(FWARPS * 32, MINB) k1_fused(FusedArgs A)
 #pragma unroll
             for (int b = 0; b < 8; b++)
                 if (const uint32_t t = tab[b * 32 + lane]) atomicAdd(&A.hist[f * 256 + b * 32 + lane], t);
+            // np.median + thresholds (lane_detector.py:79-81) once per frame, by whoever completes it
+            __threadfence();
+            int done = 0;
+            if (lane == 0) done = atomicAdd(&A.frame_done[f], 1);
+            done = __shfl_sync(0xffffffffu, done, 0);
+            if (done == nb * n_strips - 1) {
+                __threadfence();
+                const int m2 = median_x2_warp(A.hist + f * 256, (long long)H * W, lane);
+                int low = A.lut_low[m2], high = A.lut_high[m2];
+                if (low > high) { const int t = low; low = high; high = t; }
+                if (lane == 0) {
+                    A.thr[f] = make_int4(m2, low, high, (int)pre);
+                    const int again = low < (int)pre;      // the sampled floor was too high: K misses candidates
+                    A.redo_flag[f] = again;
+                    if (again) {
+                        A.pre_redo[f] = low;
+                        A.redo_list[atomicAdd(A.redo_count, 1)] = f;
+                    }
+                }
+            }
         }
         __syncwarp();                                     // the table is zeroed again at the start of the next task
     }
@@ -503,13 +528,22 @@ __global__ void __launch_bounds__(256) k1_probe(const uint8_t *__restrict__ fram
     __syncthreads();
     const uint8_t *src = frames + (size_t)f * H * W * 3;
     const int ny = min(H, 64), nx = min(W, 64);
-    for (int i = tid; i < ny * nx; i += 256) {
-        const int iy = i / nx, ix = i - iy * nx;
-        const int y = (int)(((long long)(2 * iy + 1) * H) / (2 * ny)), x = (int)(((long long)(2 * ix + 1) * W) / (2 * nx));
-        const uint8_t *p = src + ((size_t)y * W + x) * 3;
-        const uint32_t g = (3735u * p[0] + 19235u * p[1] + 9798u * p[2] + (1u << 14)) >> 15;
-        atomicAdd(&h[g], 1u);
+    // sixteen samples per thread, every load issued before the first is used (the samples are DRAM misses)
+    uint32_t g[16];
+#pragma unroll
+    for (int u = 0; u < 16; u++) {
+        const int i = tid + u * 256;
+        g[u] = 0xFFFFFFFFu;
+        if (i < ny * nx) {
+            const int iy = i / nx, ix = i - iy * nx;
+            const int y = (int)(((long long)(2 * iy + 1) * H) / (2 * ny)), x = (int)(((long long)(2 * ix + 1) * W) / (2 * nx));
+            const uint8_t *p = src + ((size_t)y * W + x) * 3;
+            g[u] = 3735u * __ldg(p) + 19235u * __ldg(p + 1) + 9798u * __ldg(p + 2);
+        }
     }
+#pragma unroll
+    for (int u = 0; u < 16; u++)
+        if (g[u] != 0xFFFFFFFFu) atomicAdd(&h[(g[u] + (1u << 14)) >> 15], 1u);
     __syncthreads();
     if (tid == 0) {
         const int half = (ny * nx) / 2;
@@ -575,14 +609,19 @@ static bool fused_launch(FusedArgs A, cudaStream_t st)
 }
 
 // First pass over frames 0..n-1: estimate the floors, then gray + blur + histogram + Sobel + NMS in one kernel.
-bool launch_fused_edge(const uint8_t *frames, const uint8_t *lut_low, uint32_t *hist, int *pre, uint32_t *k_bits,
-                       uint8_t *v_plane, uint8_t *blur_dbg, int *task_counter, int n, int H, int W, cudaStream_t st,
-                       int *launches)
+bool launch_fused_edge(const uint8_t *frames, const uint8_t *lut_low, const uint8_t *lut_high, uint32_t *hist, int4 *thr,
+                       int *pre, int *pre_redo, int *redo_list, int *redo_count, int *redo_flag, int *frame_done,
+                       uint32_t *k_bits, uint8_t *v_plane, uint8_t *blur_dbg, int *task_counter, int n, int H, int W,
+                       cudaStream_t st, int *launches)
 {
     static const int forced = getenv("LANE_K1F_PRE") ? atoi(getenv("LANE_K1F_PRE")) : -1;
     cudaMemsetAsync(hist, 0, sizeof(uint32_t) * 256 * n, st);
+    cudaMemsetAsync(frame_done, 0, sizeof(int) * n, st);
+    cudaMemsetAsync(redo_count, 0, sizeof(int), st);
     k1_probe<<<n, 256, 0, st>>>(frames, lut_low, pre, H, W, forced);
     FusedArgs A{};
+    A.frame_done = frame_done; A.lut_low = lut_low; A.lut_high = lut_high; A.thr = thr; A.pre_redo = pre_redo;
+    A.redo_list = redo_list; A.redo_count = redo_count; A.redo_flag = redo_flag;
     A.frames = frames; A.frame_list = nullptr; A.n_list = nullptr; A.hist = hist; A.pre = pre; A.k_bits = k_bits;
     A.v_plane = v_plane; A.blur_dbg = blur_dbg; A.task_counter = task_counter;
     A.n_frames = n; A.H = H; A.W = W; A.WW = (W + 31) / 32;

@@ -73,34 +73,6 @@ __device__ __forceinline__ uint32_t h2fma2(uint32_t a, uint32_t b)   // 2*a + b
     return d;
 }
 
-// median of the blurred plane (x2) from its histogram; warp-collective
-__device__ int median_x2_warp(const uint32_t *h, long long P, int lane)
-{
-    uint32_t c[8], s = 0;
-#pragma unroll
-    for (int i = 0; i < 8; i++) { c[i] = h[lane * 8 + i]; s += c[i]; }
-    uint32_t inc = s;
-    for (int o = 1; o < 32; o <<= 1) {
-        uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
-        if (lane >= o) inc += t;
-    }
-    const long long exc = (long long)inc - s;
-    const long long k0 = (P & 1) ? P / 2 : P / 2 - 1, k1 = P / 2;
-    int v0 = -1, v1 = -1;
-    long long run = exc;
-#pragma unroll
-    for (int i = 0; i < 8; i++) {
-        run += c[i];
-        if (v0 < 0 && exc <= k0 && run > k0) v0 = lane * 8 + i;
-        if (v1 < 0 && exc <= k1 && run > k1) v1 = lane * 8 + i;
-    }
-    for (int o = 16; o; o >>= 1) {
-        v0 = max(v0, __shfl_xor_sync(0xffffffffu, v0, o));
-        v1 = max(v1, __shfl_xor_sync(0xffffffffu, v1, o));
-    }
-    return v0 + v1;
-}
-
 // Sobel + NMS for one (strip, row range) task; writes the C/S words of rows [q0,q1) of the frame's planes.
 //
 // Dense part (every pixel, two per instruction): column sums T(c) = B(c) + B(c+1) give the Sobel column filters as
@@ -388,12 +360,9 @@ __device__ __forceinline__ void chase_column(uint32_t cA, uint32_t sA, uint32_t 
 struct K2tArgs {
     const uint32_t *k_bits;            // [n][H][WW]
     const uint8_t *v_plane;            // [n][H][W]
-    const uint32_t *hist;              // [n][256]
-    const uint8_t *lut_low, *lut_high;
-    int4 *thr;                         // [n] (median_x2, low, high, floor used)
+    int4 *thr;                         // [n] (median_x2, low, high, floor used), written by k1_fused
     const int *pre;                    // [n] floor k1_fused used for this pass
-    int *pre_redo;                     // [n] floor for the redo pass (= the true low)
-    int *redo_list, *redo_count, *redo_flag;
+    const int *redo_flag;              // [n] first pass: frames listed for the redo pass are skipped
     const int *frame_list, *n_list;    // redo pass: frames to process (null = all)
     uint32_t *c_bits, *s_bits;         // [n][H][WW]
     int H, W, WW, words_per_cta;
@@ -401,35 +370,17 @@ struct K2tArgs {
 
 __global__ void __launch_bounds__(256) k2t_threshold(K2tArgs A)
 {
-    __shared__ int s_low, s_high;
     int f = blockIdx.y;
     if (A.frame_list) {
         if (f >= *A.n_list) return;
         f = A.frame_list[f];
     }
-    const int tid = threadIdx.x, lane = tid & 31;
-    if (tid < 32) {
-        const int m2 = median_x2_warp(A.hist + f * 256, (long long)A.H * A.W, lane);
-        int low = A.lut_low[m2], high = A.lut_high[m2];
-        if (low > high) { int t = low; low = high; high = t; }
-        if (lane == 0) {
-            s_low = low; s_high = high;
-            if (blockIdx.x == 0) {
-                const int pre = A.pre[f];
-                A.thr[f] = make_int4(m2, low, high, pre);
-                if (!A.frame_list) {
-                    const int redo = low < pre;
-                    A.redo_flag[f] = redo;
-                    if (redo) {
-                        A.pre_redo[f] = low;
-                        A.redo_list[atomicAdd(A.redo_count, 1)] = f;
-                    }
-                }
-            }
-        }
-    }
-    __syncthreads();
-    if (!A.frame_list && s_low < A.pre[f]) return;          // this frame's planes are rebuilt in the redo pass
+    const int tid = threadIdx.x;
+    // thresholds and the redo decision were formed by the warp of k1_fused that finished the frame last
+    const int4 t = A.thr[f];
+    if (!A.frame_list && A.redo_flag[f]) return;            // this frame's planes are rebuilt in the redo pass
+    if (A.frame_list && blockIdx.x == 0 && tid == 0) A.thr[f] = make_int4(t.x, t.y, t.z, A.pre[f]);
+    const int s_low = t.y, s_high = t.z;
     const uint32_t lo4 = (uint32_t)s_low * 0x01010101u, hi4 = (uint32_t)s_high * 0x01010101u;
     const int n_words = A.H * A.WW;
     const uint32_t *kb = A.k_bits + (size_t)f * n_words;
@@ -444,16 +395,25 @@ __global__ void __launch_bounds__(256) k2t_threshold(K2tArgs A)
         return m;
     };
     const int w0 = blockIdx.x * A.words_per_cta, w1 = min(w0 + A.words_per_cta, n_words);
-    for (int i = w0 + tid; i < w1; i += 256) {
-        const uint32_t k = kb[i];
+    // eight words per thread, all K words requested before any is looked at
+    uint32_t k[8];
+#pragma unroll
+    for (int u = 0; u < 8; u++) {
+        const int i = w0 + tid + u * 256;
+        k[u] = i < w1 ? __ldg(kb + i) : 0u;
+    }
+#pragma unroll
+    for (int u = 0; u < 8; u++) {
+        const int i = w0 + tid + u * 256;
+        if (i >= w1) break;
         uint32_t cw = 0, sw = 0;
-        if (k) {
+        if (k[u]) {
             const int r = i / A.WW, w = i - r * A.WW;
             const uint4 *vp = reinterpret_cast<const uint4 *>(vb + (size_t)r * A.W + w * 32);
             const uint4 a = __ldg(vp);
             const uint4 b = (w * 32 + 16 < A.W) ? __ldg(vp + 1) : make_uint4(0, 0, 0, 0);
-            cw = k & ge_bits(a, b, lo4);
-            sw = k & ge_bits(a, b, hi4);
+            cw = k[u] & ge_bits(a, b, lo4);
+            sw = k[u] & ge_bits(a, b, hi4);
         }
         cb[i] = cw;
         sb[i] = sw;
@@ -865,14 +825,12 @@ bool launch_canny_cluster_fused(const uint32_t *k_bits, const uint8_t *v_plane, 
     if (!frame_list) {
         cudaMemsetAsync(n_edges, 0, sizeof(int) * n, st);
         cudaMemsetAsync(n_points, 0, sizeof(int) * n, st);
-        cudaMemsetAsync(redo_count, 0, sizeof(int), st);
     }
     K2tArgs T{};
-    T.k_bits = k_bits; T.v_plane = v_plane; T.hist = hist; T.lut_low = lut_low; T.lut_high = lut_high; T.thr = thr;
-    T.pre = frame_list ? pre_redo : pre; T.pre_redo = pre_redo; T.redo_list = redo_list; T.redo_count = redo_count;
+    T.k_bits = k_bits; T.v_plane = v_plane; T.thr = thr; T.pre = frame_list ? pre_redo : pre;
     T.redo_flag = redo_flag; T.frame_list = frame_list; T.n_list = frame_list ? redo_count : nullptr;
     T.c_bits = c_bits; T.s_bits = s_bits; T.H = H; T.W = W; T.WW = WW;
-    T.words_per_cta = 256 * 8;
+    T.words_per_cta = 256 * 8;              // the kernel handles exactly eight words per thread
     dim3 tgrid((H * WW + T.words_per_cta - 1) / T.words_per_cta, n);
     k2t_threshold<<<tgrid, 256, 0, st>>>(T);
     K2Args A{};

@@ -260,16 +260,17 @@ int run_stages(lane_ctx *c, const uint8_t *frames_dev, int off, int m, const int
         if (!c->d_kbits) {
             CU(dalloc(&c->d_kbits, (size_t)c->max_batch * planes));
             CU(dalloc(&c->d_vplane, (size_t)c->max_batch * P));
-            CU(dalloc(&c->d_pre, (size_t)c->max_batch * 4 + 4));
+            CU(dalloc(&c->d_pre, (size_t)c->max_batch * 5 + 4));
         }
         if (c->debug) { rc = ensure_blur(c); if (rc) return rc; }
         const size_t B = (size_t)c->max_batch;
         int *pre = c->d_pre + o, *pre_redo = c->d_pre + B + o, *redo_list = c->d_pre + 2 * B + o, *redo_flag = c->d_pre + 3 * B + o,
-            *redo_count = c->d_pre + 4 * B;
+            *frame_done = c->d_pre + 4 * B + o, *redo_count = c->d_pre + 5 * B;
         uint32_t *kb = c->d_kbits + o * planes;
         uint8_t *vp = c->d_vplane + o * P, *bd = c->debug ? c->d_blur + o * P : nullptr;
         int *LK = &L[LANE_STAGE_BLUR_HIST], *LC = &L[LANE_STAGE_CANNY];
-        if (launch_fused_edge(fr, c->d_lut, hist, pre, kb, vp, bd, c->d_task_counter, m, H, W, c->st, LK)) {
+        if (launch_fused_edge(fr, c->d_lut, c->d_lut + 511, hist, thr, pre, pre_redo, redo_list, redo_count, redo_flag, frame_done,
+                              kb, vp, bd, c->d_task_counter, m, H, W, c->st, LK)) {
             rc = stage_check(c, "k1_fused"); if (rc) return rc;
             if (timed) { rc = mark(c, LANE_STAGE_CANNY); if (rc) return rc; }
             fused = launch_canny_cluster_fused(kb, vp, hist, c->d_lut, c->d_lut + 511, c->d_roi_bits, thr, pre, pre_redo,

@@ -58,9 +58,10 @@ void launch_blur_hist(const uint8_t *frames, uint8_t *blur, uint32_t *hist, int 
                       cudaStream_t st, int *launches, int *task_counter, int force_tile, int gaussian_blur);
 // fused edge kernel (k1_fused.cu): probe + gray + blur + histogram + Sobel + NMS -> K bit-plane, V byte plane
 bool lane_fused_edge_supported(int H, int W, const void *frames);
-bool launch_fused_edge(const uint8_t *frames, const uint8_t *lut_low, uint32_t *hist, int *pre, uint32_t *k_bits,
-                       uint8_t *v_plane, uint8_t *blur_dbg, int *task_counter, int n, int H, int W, cudaStream_t st,
-                       int *launches);
+bool launch_fused_edge(const uint8_t *frames, const uint8_t *lut_low, const uint8_t *lut_high, uint32_t *hist, int4 *thr,
+                       int *pre, int *pre_redo, int *redo_list, int *redo_count, int *redo_flag, int *frame_done,
+                       uint32_t *k_bits, uint8_t *v_plane, uint8_t *blur_dbg, int *task_counter, int n, int H, int W,
+                       cudaStream_t st, int *launches);
 bool launch_fused_edge_redo(const uint8_t *frames, const int *frame_list, const int *n_list, const int *pre,
                             uint32_t *k_bits, uint8_t *v_plane, uint8_t *blur_dbg, int *task_counter, int n, int H, int W,
                             cudaStream_t st, int *launches);
@@ -145,6 +146,38 @@ void launch_fit(const int32_t *lines, const int *n_lines, LaneFitScratch fs, con
                 lane_record *records, LaneGeom g, int n, cudaStream_t st, int *launches);
 
 #ifdef __CUDACC__
+// median of the blurred plane (x2) from its histogram; warp-collective
+static __device__ __forceinline__ int median_x2_warp(const uint32_t *h, long long P, int lane)
+{
+    uint32_t c[8], s = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        c[i] = __ldcg(h + lane * 8 + i);   // from L2: the counts were accumulated with atomics by other SMs
+        s += c[i];
+    }
+    uint32_t inc = s;
+    for (int o = 1; o < 32; o <<= 1) {
+        uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += t;
+    }
+    const long long exc = (long long)inc - s;
+    const long long k0 = (P & 1) ? P / 2 : P / 2 - 1, k1 = P / 2;
+    int v0 = -1, v1 = -1;
+    long long run = exc;
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        run += c[i];
+        if (v0 < 0 && exc <= k0 && run > k0) v0 = lane * 8 + i;
+        if (v1 < 0 && exc <= k1 && run > k1) v1 = lane * 8 + i;
+    }
+    for (int o = 16; o; o >>= 1) {
+        v0 = max(v0, __shfl_xor_sync(0xffffffffu, v0, o));
+        v1 = max(v1, __shfl_xor_sync(0xffffffffu, v1, o));
+    }
+    return v0 + v1;
+}
+
+
 // ---- TMA bulk copy (cp.async.bulk, SASS UBLKCP) + mbarrier helpers -------------------------------------
 static __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 static __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count)
