@@ -624,6 +624,19 @@ int lane_set_roi_mask(lane_ctx *c, const uint8_t *mask)
         CU(dalloc(&c->d_accum16, (size_t)c->max_batch * (c->cells_per_frame / 2)));
         int2 win3[LANE_NUM_ANGLES];
         c->G3 = lane_ppht_plan_v3(win, c->cells_per_frame, win3, &c->cells_max3);
+        {
+            // v3 keeps a frame's cells in the shared memory of a cluster, so the number of frames in flight is what the
+            // cells leave room for: 74 at 1080p (G = 4, two CTAs per SM) but only 18 at 4K (G = 16), where the
+            // global-memory kernel with every frame of the batch in flight is faster (measured on B200, 128 x 4K:
+            // v3 3.55 ms, v2 2.47 ms).  Take v3 only when it can keep at least 32 frames going.
+            const char *e = getenv("LANE_B200_K4");
+            const bool forced = e && !strcmp(e, "v3");
+            if (c->G3 > 0 && !forced) {
+                const size_t per_cta = (size_t)c->cells_max3 * 2 + sizeof(uint32_t) * lane_ppht_list_cap_v3() + 4700;
+                const int ctas = per_cta <= 112 * 1024 ? 2 : 1;
+                if (lane_sm_count() * ctas / c->G3 < 32) c->G3 = 0;
+            }
+        }
         CU(cudaMemcpy(c->d_win3, win3, sizeof(win3), cudaMemcpyHostToDevice));
         if (c->d_pmask_work) cudaFree(c->d_pmask_work);
         c->d_pmask_work = nullptr;

@@ -199,3 +199,73 @@ def test_hough_lines_batch_matches_cv2_and_oracle(w, h, n):
     peaks2, counts2, acc2, _ = det._ctx.hough_lines_batch(n, threshold=50, max_peaks=256)
     assert acc2 is None and all(np.array_equal(a, b) for a, b in zip(peaks, peaks2))
     det.close()
+
+
+# ---- BASELINE config 2 for real: every distinct frame of the bench batch against cv2 ---------------------------
+def test_config2_every_distinct_frame_of_the_bench_batch_against_cv2():
+    """The bench workload: 256 x 1080p = 64 distinct generator frames tiled in time, one launch per kernel.  Every
+    distinct frame's full-frame Canny map and HoughLinesP segment list must equal cv2's, its standard-Hough accumulator
+    the oracle's restatement of cv2.HoughLines' voting and its peaks cv2.HoughLinesWithAccumulator's (votes and order),
+    and the lanes the cv2 reference pipeline's frame after frame (EMA chain over all 256 frames)."""
+    import torch
+    from multimodal_autonomous_driving_perception_and_planning_b200 import multi_camera_batch
+    from oracle import stages as S
+    batch = multi_camera_batch(1, 256, 1920, 1080, period=64)[0]
+    det = LaneDetector(max_batch=256)
+    lanes = det.detect_batch(torch.from_numpy(batch).cuda())          # device-resident: one 256-frame launch per kernel
+    recs = det.last_records
+    assert det._ctx.last_paths() == _native.PATH_ALL_FAST
+    ref = Cv2LaneOracle()
+    edges_ref, masked_ref = [], []
+    for i in range(64):
+        e = ref.edges(ref.blurred(batch[i]))
+        m = ref.masked(e)
+        edges_ref.append(e); masked_ref.append(m)
+        segs = ref.segments(m)
+        for j in (i, i + 64, i + 192):                                 # the tiled copies give the same per-frame results
+            assert np.array_equal(det._ctx.tap(_native.TAP_EDGES, j), e), (i, j)
+            assert np.array_equal(det._ctx.tap(_native.TAP_SEGMENTS, j), segs), (i, j)
+            assert recs[j]["n_edges"] == int((e != 0).sum()) and recs[j]["n_roi_points"] == int((m != 0).sum())
+    for i in range(256):                                               # the EMA chain of the reference over the whole batch
+        _same_lanes(lanes[i], ref.detect(batch[i]), 1080)
+    peaks, counts, acc, ms = det._ctx.hough_lines_batch(256, threshold=50, max_peaks=512)
+    det2 = LaneDetector(max_batch=64)
+    det2.detect_batch(torch.from_numpy(batch[:64]).cuda())
+    peaks2, counts2, acc2, _ = det2._ctx.hough_lines_batch(64, threshold=50, max_peaks=512, with_accum=True)
+    for i in range(64):
+        want = S.hough_accum(masked_ref[i])
+        assert np.array_equal(acc2[i], want), i
+        want_peaks = S.hough_peaks(want, 1080, 1920, 50)
+        for got in (peaks2[i], peaks[i], peaks[i + 128]):
+            assert np.array_equal(got, want_peaks), i
+        lines = cv2.HoughLinesWithAccumulator(masked_ref[i], 1, np.pi / 180, 50)
+        lines = np.zeros((0, 3)) if lines is None else lines.reshape(-1, 3)
+        assert np.array_equal(lines[:, 2].astype(np.int32), want_peaks[:, 2])
+    det.close(); det2.close()
+
+
+@pytest.mark.parametrize("ppht", ["auto", "v3"])
+def test_config4_batch_of_4k_frames_against_cv2(ppht, monkeypatch):
+    """BASELINE config 4 geometry (3840x2160: 16-CTA hysteresis clusters, point lists longer than the PPHT's shared
+    list) on a batch of distinct frames: edge maps, ROI counts and segments equal cv2's; lanes equal the cv2 pipeline's.
+    "auto" takes the PPHT kernel the context picks for this geometry (global-memory cells: only 18 frames would fit the
+    distributed-shared-memory kernel at a time); "v3" pins the DSMEM kernel, whose point list then continues in its
+    global extension (3.3 k points per frame against 3072 in shared memory)."""
+    import torch
+    if ppht == "v3":
+        monkeypatch.setenv("LANE_B200_K4", "v3")
+    frames = np.stack(gen_frames(3840, 2160, 8))
+    det = LaneDetector(max_batch=8)
+    lanes = det.detect_batch(torch.from_numpy(frames).cuda())
+    recs = det.last_records
+    assert det._ctx.last_paths() & _native.PATH_FUSED_EDGE and det._ctx.last_paths() & _native.PATH_CLUSTER_CANNY
+    assert bool(det._ctx.last_paths() & _native.PATH_PPHT_DSMEM) == (ppht == "v3")
+    ref = Cv2LaneOracle()
+    for i, f in enumerate(frames):
+        e = ref.edges(ref.blurred(f))
+        m = ref.masked(e)
+        assert np.array_equal(det._ctx.tap(_native.TAP_EDGES, i), e), i
+        assert recs[i]["n_roi_points"] == int((m != 0).sum()) and recs[i]["n_roi_points"] > 3072
+        assert np.array_equal(det._ctx.tap(_native.TAP_SEGMENTS, i), ref.segments(m)), i
+        _same_lanes(lanes[i], ref.detect(f), 2160)
+    det.close()
