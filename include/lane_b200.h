@@ -196,6 +196,11 @@ LANE_API int lane_hough_accumulator(lane_ctx *ctx, int frame_index, int32_t *acc
 LANE_API int lane_hough_lines_batch(lane_ctx *ctx, int threshold, int max_peaks, int32_t *peaks_host,
                            int32_t *n_peaks_host, int32_t *accum_host, float *device_ms);
 
+/* Edge pixels of the Canny map inside the rectangle [x0,x1) x [y0,y1), for every frame of the last batch (int32[n]):
+ * SceneClassifier's centre-region edge density, np.sum(edges[h//3:2*h//3, w//3:2*w//3] > 0)
+ * (/root/reference/src/tagging/scene_classifier.py:148-150), as a popcount on the device. */
+LANE_API int lane_edge_count_rect(lane_ctx *ctx, int x0, int y0, int x1, int y1, int32_t *counts_host);
+
 /* ---- frame ingest (the step before the path) -------------------------------------------
  * Replaces the pixel work of VideoDataLoader.read_frame / read_frame_at
  * (/root/reference/data/loaders/video_loader.py:96-131): `frame = cv2.resize(frame, self.target_size)` (:108, :128),

@@ -94,6 +94,7 @@ _PROTOS = {
     "lane_set_profiling": (C.c_int, [C.c_void_p, C.c_int]),
     "lane_get_stage_ms": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "lane_debug_tap": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]),
+    "lane_edge_count_rect": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "lane_hough_lines_batch": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
                                          C.POINTER(C.c_float)]),
     "lane_hough_accumulator": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int,
@@ -275,6 +276,12 @@ class LaneContext:
         if what in (TAP_POINTS, TAP_SEGMENTS):
             rows = written.value // (out.shape[1] * 4)
             return out[:rows].copy()
+        return out
+
+    def edge_count_rect(self, n: int, x0: int, y0: int, x1: int, y1: int) -> np.ndarray:
+        """Edge pixels inside [x0,x1) x [y0,y1) of each of the ``n`` frames of the last batch (device popcount)."""
+        out = np.zeros(n, np.int32)
+        self._check(lib().lane_edge_count_rect(self._h, int(x0), int(y0), int(x1), int(y1), _ptr(out)))
         return out
 
     def hough_lines_batch(self, n: int, threshold: int = 50, max_peaks: int = 256, with_accum: bool = False):

@@ -845,6 +845,41 @@ bool launch_canny_cluster_fused(const uint32_t *k_bits, const uint8_t *v_plane, 
     return true;
 }
 
+// edge pixels inside [x0,x1) x [y0,y1) of every frame's edge bit-plane (SceneClassifier's centre-region edge density,
+// src/tagging/scene_classifier.py:148-150): one CTA per frame, popcounts of the masked words
+namespace {
+__global__ void __launch_bounds__(256) k_edge_count_rect(const uint32_t *__restrict__ edge_bits, int *__restrict__ counts, int H,
+                                                         int WW, int x0, int y0, int x1, int y1)
+{
+    __shared__ int s_red[8];
+    const int f = blockIdx.x, tid = threadIdx.x;
+    const uint32_t *eb = edge_bits + (size_t)f * H * WW;
+    const int w0 = x0 >> 5, w1 = (x1 + 31) >> 5, nw = w1 - w0;
+    int cnt = 0;
+    for (int i = tid; i < (y1 - y0) * nw; i += 256) {
+        const int y = y0 + i / nw, w = w0 + i % nw;
+        uint32_t m = eb[(size_t)y * WW + w];
+        if (w == w0) m &= 0xFFFFFFFFu << (x0 & 31);
+        if (w == w1 - 1 && (x1 & 31)) m &= 0xFFFFFFFFu >> (32 - (x1 & 31));
+        cnt += __popc(m);
+    }
+    for (int o = 16; o; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+    if ((tid & 31) == 0) s_red[tid >> 5] = cnt;
+    __syncthreads();
+    if (tid == 0) {
+        int t = 0;
+        for (int i = 0; i < 8; i++) t += s_red[i];
+        counts[f] = t;
+    }
+}
+}  // namespace
+
+void launch_edge_count_rect(const uint32_t *edge_bits, int *counts, int n, int H, int W, int x0, int y0, int x1, int y1,
+                            cudaStream_t st)
+{
+    k_edge_count_rect<<<n, 256, 0, st>>>(edge_bits, counts, H, (W + 31) / 32, x0, y0, x1, y1);
+}
+
 void launch_bytes_to_bits(const uint8_t *bytes, uint32_t *bits, int n, int rows, int W, int row_stride,
                           cudaStream_t st, int *launches)
 {

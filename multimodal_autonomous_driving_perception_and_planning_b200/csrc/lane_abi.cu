@@ -920,6 +920,23 @@ int lane_hough_accumulator(lane_ctx *c, int fi, int32_t *accum_host, int thresho
     return LANE_OK;
 }
 
+int lane_edge_count_rect(lane_ctx *c, int x0, int y0, int x1, int y1, int32_t *counts_host)
+{
+    if (!c || !counts_host) return LANE_ERR_INVALID;
+    if (c->q_count) return fail(c, LANE_ERR_STATE, "collect the batch first");
+    const int n = c->slots[c->cur].n;
+    if (n < 1) return fail(c, LANE_ERR_STATE, "no batch has run on this context");
+    if (x0 < 0 || y0 < 0 || x1 > c->g.W || y1 > c->g.H || x0 >= x1 || y0 >= y1)
+        return fail(c, LANE_ERR_INVALID, "bad rectangle [%d,%d) x [%d,%d)", x0, x1, y0, y1);
+    CU(cudaSetDevice(c->device));
+    // d_n_lines is free between batches (K5 has consumed it); reuse it as the result buffer
+    launch_edge_count_rect(c->d_edge_bits, c->d_n_lines, n, c->g.H, c->g.W, x0, y0, x1, y1, c->st);
+    CU(cudaMemcpyAsync(counts_host, c->d_n_lines, sizeof(int) * n, cudaMemcpyDeviceToHost, c->st));
+    CU(cudaStreamSynchronize(c->st));
+    CU(cudaGetLastError());
+    return LANE_OK;
+}
+
 int lane_hough_lines_batch(lane_ctx *c, int threshold, int max_peaks, int32_t *peaks_host, int32_t *n_peaks_host,
                            int32_t *accum_host, float *device_ms)
 {

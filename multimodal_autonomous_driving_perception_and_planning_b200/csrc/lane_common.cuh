@@ -96,6 +96,8 @@ bool launch_canny_cluster_fused(const uint32_t *k_bits, const uint8_t *v_plane, 
                                 int *redo_list, int *redo_count, int *redo_flag, const int *frame_list, int *n_edges,
                                 int *rounds, uint32_t *points, int *n_points, uint32_t *pmask_bits, uint32_t *edge_bits,
                                 uint32_t *c_bits, uint32_t *s_bits, LaneGeom g, int n, cudaStream_t st, int *launches);
+void launch_edge_count_rect(const uint32_t *edge_bits, int *counts, int n, int H, int W, int x0, int y0, int x1, int y1,
+                            cudaStream_t st);
 void launch_bytes_to_bits(const uint8_t *bytes, uint32_t *bits, int n, int rows, int W, int row_stride,
                           cudaStream_t st, int *launches);
 void launch_mask_rows(const uint32_t *edge_bits, const uint32_t *roi_bits, uint32_t *pmask_bits, LaneGeom g, int n,
