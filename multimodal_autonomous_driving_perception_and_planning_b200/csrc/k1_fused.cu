@@ -528,22 +528,27 @@ __global__ void __launch_bounds__(256) k1_probe(const uint8_t *__restrict__ fram
     __syncthreads();
     const uint8_t *src = frames + (size_t)f * H * W * 3;
     const int ny = min(H, 64), nx = min(W, 64);
-    // sixteen samples per thread, every load issued before the first is used (the samples are DRAM misses)
-    uint32_t g[16];
+    if (ny == 64 && nx == 64) {
+        // sixteen samples per thread, every load issued before the first is used (the samples are DRAM misses); sample
+        // (iy, ix) of the 64 x 64 lattice sits at the centre of its cell (32-bit arithmetic: sides are below 32768)
+        uint32_t g[16];
 #pragma unroll
-    for (int u = 0; u < 16; u++) {
-        const int i = tid + u * 256;
-        g[u] = 0xFFFFFFFFu;
-        if (i < ny * nx) {
-            const int iy = i / nx, ix = i - iy * nx;
-            const int y = (int)(((long long)(2 * iy + 1) * H) / (2 * ny)), x = (int)(((long long)(2 * ix + 1) * W) / (2 * nx));
-            const uint8_t *p = src + ((size_t)y * W + x) * 3;
+        for (int u = 0; u < 16; u++) {
+            const uint32_t i = tid + u * 256, iy = i >> 6, ix = i & 63u;
+            const uint32_t y = ((2u * iy + 1u) * (uint32_t)H) >> 7, x = ((2u * ix + 1u) * (uint32_t)W) >> 7;
+            const uint8_t *p = src + (y * (uint32_t)W + x) * 3u;
             g[u] = 3735u * __ldg(p) + 19235u * __ldg(p + 1) + 9798u * __ldg(p + 2);
         }
-    }
 #pragma unroll
-    for (int u = 0; u < 16; u++)
-        if (g[u] != 0xFFFFFFFFu) atomicAdd(&h[(g[u] + (1u << 14)) >> 15], 1u);
+        for (int u = 0; u < 16; u++) atomicAdd(&h[(g[u] + (1u << 14)) >> 15], 1u);
+    } else {                                              // frames smaller than the lattice: every row / column once
+        for (int i = tid; i < ny * nx; i += 256) {
+            const int iy = i / nx, ix = i - iy * nx;
+            const int y = ((2 * iy + 1) * H) / (2 * ny), x = ((2 * ix + 1) * W) / (2 * nx);
+            const uint8_t *p = src + ((size_t)y * W + x) * 3;
+            atomicAdd(&h[(3735u * p[0] + 19235u * p[1] + 9798u * p[2] + (1u << 14)) >> 15], 1u);
+        }
+    }
     __syncthreads();
     if (tid == 0) {
         const int half = (ny * nx) / 2;
