@@ -1,6 +1,7 @@
 """Secondary BASELINE configs (not the bench.py headline line): run on the GPU box, prints one JSON per config.
 
   config 1  300 x 640x480 generator frames, one stream (the demo's shape): GPU fps (host frames) vs CPU oracle port
+  config 2  (add-on) batched standard Hough (K3) device time for the 256 x 1080p bench batch
   config 4  128 x 3840x2160: device-resident fps, per-stage ms, hysteresis rounds
   config 5  batch = 1 streaming latency at 1280x720: p50/p99 per-frame latency vs the CPU path
   noise     64 x 1080p uniform-noise frames (dense edges: worst case for K2/K4), device-resident
@@ -62,6 +63,17 @@ def main():
     out.append({"config": "1: 300 x 640x480 one stream, host frames through LaneDetector.detect_batch", "gpu_fps": gpu,
                 "cpu_fps_1proc": cpu_fps(list(frames), 300), "lanes_found": sum(a is not None and b is not None for a, b in lanes)})
     det.close()
+    # ---- config 2 add-on: batched standard Hough (K3) over the bench batch, peaks only
+    n = 256
+    host = multi_camera_batch(1, n, 1920, 1080, period=64)[0]
+    dev = torch.from_numpy(host).cuda()
+    det = LaneDetector(max_batch=n)
+    det.detect_batch(dev)
+    hb = [det._ctx.hough_lines_batch(n, threshold=50, max_peaks=256)[3] for _ in range(4)]
+    peaks, counts, _, _ = det._ctx.hough_lines_batch(n, threshold=50, max_peaks=256)
+    out.append({"config": "2 (add-on): standard Hough of 256 x 1920x1080 frames, threshold 50, peaks ordered on the device",
+                "hough_std_ms": float(min(hb[1:])), "peaks_mean": float(counts.mean())})
+    det.close(); del dev
     # ---- config 4
     n = 128
     host = multi_camera_batch(1, n, 3840, 2160, period=4)[0]
