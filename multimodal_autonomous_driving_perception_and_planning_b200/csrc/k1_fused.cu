@@ -291,9 +291,9 @@ __global__ void __launch_bounds__(FWARPS * 32, MINB) k1_fused(FusedArgs A)
         int sa = 0, sb = RS, sc = 2 * RS;                 // ring slots of M rows s-2, s-1, s
 
         uint32_t w[12];
-        auto load_row = [&](int y, bool interior = false) {
+        auto load_row = [&](int y) {
             // BORDER_REFLECT_101 for the gray rows above / below the frame (|y|, then mirrored at the bottom)
-            const int ya = abs(y), yy = interior ? y : min(ya, 2 * H - 2 - ya);
+            const int ya = abs(y), yy = min(ya, 2 * H - 2 - ya);
             if (in_img) {
                 const uint4 *p = reinterpret_cast<const uint4 *>(src + (uint32_t)(yy * W) * 3u);
                 uint4 a = ldg_stream(p), b = ldg_stream(p + 1), c = ldg_stream(p + 2);
@@ -321,11 +321,10 @@ __global__ void __launch_bounds__(FWARPS * 32, MINB) k1_fused(FusedArgs A)
         // One row of the steady state.  No persistent array is assigned under a condition here (the frame borders are
         // patched in shared memory by a rare branch below): every conditional assignment to the column state costs a
         // block of register moves per row once the compiler has to merge the two versions.
-        auto row_step = [&](auto slot, auto lean_tag, int y) {
+        auto row_step = [&](auto slot, int y) {
             constexpr int c = decltype(slot)::value, o = c ^ 1;
-            constexpr bool LEAN = decltype(lean_tag)::value;      // interior band: no frame border anywhere near
             gray16(w, sg[c]);
-            if (y < y_last) load_row(y + 1, LEAN);             // prefetch the next row behind the arithmetic
+            if (y < y_last) load_row(y + 1);             // prefetch the next row behind the arithmetic
             uint32_t V[8];
 #pragma unroll
             for (int j = 0; j < 8; j++) {                // [1 1]^4 down the column; stages < 2048 as exact add.f16x2
@@ -419,7 +418,7 @@ __global__ void __launch_bounds__(FWARPS * 32, MINB) k1_fused(FusedArgs A)
             uint4 *mrow = reinterpret_cast<uint4 *>(Mring + sc + xb);
             uint4 *xrow = reinterpret_cast<uint4 *>(DXr + (s & 1) * 512 + xb);
             uint4 *yrow = reinterpret_cast<uint4 *>(DYr + (s & 1) * 512 + xb);
-            if (!LEAN && (s <= 0 || s >= H - 1)) {
+            if (s <= 0 || s >= H - 1) {
                 // Frame borders (warp-uniform, two rows per frame).  The blurred plane is extended by BORDER_REPLICATE
                 // (row -1 := row 0, row H := row H-1) while the rows the filter state saw there came from the reflected
                 // gray rows, and the magnitude is zero outside the frame: redo this row's gradient from the state.
@@ -476,20 +475,11 @@ __global__ void __launch_bounds__(FWARPS * 32, MINB) k1_fused(FusedArgs A)
             fill_step(std::integral_constant<int, 1>{}, y++);
             fill_step(std::integral_constant<int, 0>{}, y++);
             fill_step(std::integral_constant<int, 1>{}, y++);
-            if (q0 >= 4 && q1 + 4 <= H) {                 // interior band (8 of 10 at 1080p): the lean step
-                for (;;) {
-                    row_step(std::integral_constant<int, 0>{}, std::true_type{}, y);
-                    if (++y > y_last) break;
-                    row_step(std::integral_constant<int, 1>{}, std::true_type{}, y);
-                    if (++y > y_last) break;
-                }
-            } else {
-                for (;;) {
-                    row_step(std::integral_constant<int, 0>{}, std::false_type{}, y);
-                    if (++y > y_last) break;
-                    row_step(std::integral_constant<int, 1>{}, std::false_type{}, y);
-                    if (++y > y_last) break;
-                }
+            for (;;) {
+                row_step(std::integral_constant<int, 0>{}, y);
+                if (++y > y_last) break;
+                row_step(std::integral_constant<int, 1>{}, y);
+                if (++y > y_last) break;
             }
         }
         __syncwarp();

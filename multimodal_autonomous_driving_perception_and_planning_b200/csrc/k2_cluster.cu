@@ -370,53 +370,53 @@ struct K2tArgs {
 
 __global__ void __launch_bounds__(256) k2t_threshold(K2tArgs A)
 {
-    int f = blockIdx.y;
-    if (A.frame_list) {
-        if (f >= *A.n_list) return;
-        f = A.frame_list[f];
-    }
-    const int tid = threadIdx.x;
-    // thresholds and the redo decision were formed by the warp of k1_fused that finished the frame last
-    const int4 t = A.thr[f];
-    if (!A.frame_list && A.redo_flag[f]) return;            // this frame's planes are rebuilt in the redo pass
-    if (A.frame_list && blockIdx.x == 0 && tid == 0) A.thr[f] = make_int4(t.x, t.y, t.z, A.pre[f]);
-    const int s_low = t.y, s_high = t.z;
-    const uint32_t lo4 = (uint32_t)s_low * 0x01010101u, hi4 = (uint32_t)s_high * 0x01010101u;
-    const int n_words = A.H * A.WW;
-    const uint32_t *kb = A.k_bits + (size_t)f * n_words;
-    uint32_t *cb = A.c_bits + (size_t)f * n_words, *sb = A.s_bits + (size_t)f * n_words;
-    const uint8_t *vb = A.v_plane + (size_t)f * A.H * A.W;
-    auto ge_bits = [](const uint4 &a, const uint4 &b, uint32_t t4) {
-        const uint32_t wds[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
-        uint32_t m = 0;
+    // first pass: blockIdx.y = frame.  Redo pass: a few rows of CTAs walk the (normally empty) list of frames.
+    const int n_list = A.frame_list ? *A.n_list : (int)gridDim.y;
+    for (int fi = blockIdx.y; fi < n_list; fi += gridDim.y) {
+        const int f = A.frame_list ? A.frame_list[fi] : fi;
+        const int tid = threadIdx.x;
+        // thresholds and the redo decision were formed by the warp of k1_fused that finished the frame last
+        const int4 t = A.thr[f];
+        if (!A.frame_list && A.redo_flag[f]) continue;          // this frame's planes are rebuilt in the redo pass
+        if (A.frame_list && blockIdx.x == 0 && tid == 0) A.thr[f] = make_int4(t.x, t.y, t.z, A.pre[f]);
+        const int s_low = t.y, s_high = t.z;
+        const uint32_t lo4 = (uint32_t)s_low * 0x01010101u, hi4 = (uint32_t)s_high * 0x01010101u;
+        const int n_words = A.H * A.WW;
+        const uint32_t *kb = A.k_bits + (size_t)f * n_words;
+        uint32_t *cb = A.c_bits + (size_t)f * n_words, *sb = A.s_bits + (size_t)f * n_words;
+        const uint8_t *vb = A.v_plane + (size_t)f * A.H * A.W;
+        auto ge_bits = [](const uint4 &a, const uint4 &b, uint32_t t4) {
+            const uint32_t wds[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+            uint32_t m = 0;
 #pragma unroll
-        for (int q = 0; q < 8; q++)     // per byte 0/1 (V >= t), gathered into a nibble by one multiply
-            m |= ((((__vcmpgeu4(wds[q], t4) & 0x01010101u) * 0x01020408u) >> 24) & 0xFu) << (4 * q);
-        return m;
-    };
-    const int w0 = blockIdx.x * A.words_per_cta, w1 = min(w0 + A.words_per_cta, n_words);
-    // eight words per thread, all K words requested before any is looked at
-    uint32_t k[8];
+            for (int q = 0; q < 8; q++)     // per byte 0/1 (V >= t), gathered into a nibble by one multiply
+                m |= ((((__vcmpgeu4(wds[q], t4) & 0x01010101u) * 0x01020408u) >> 24) & 0xFu) << (4 * q);
+            return m;
+        };
+        const int w0 = blockIdx.x * A.words_per_cta, w1 = min(w0 + A.words_per_cta, n_words);
+        // eight words per thread, all K words requested before any is looked at
+        uint32_t k[8];
 #pragma unroll
-    for (int u = 0; u < 8; u++) {
-        const int i = w0 + tid + u * 256;
-        k[u] = i < w1 ? __ldg(kb + i) : 0u;
-    }
-#pragma unroll
-    for (int u = 0; u < 8; u++) {
-        const int i = w0 + tid + u * 256;
-        if (i >= w1) break;
-        uint32_t cw = 0, sw = 0;
-        if (k[u]) {
-            const int r = i / A.WW, w = i - r * A.WW;
-            const uint4 *vp = reinterpret_cast<const uint4 *>(vb + (size_t)r * A.W + w * 32);
-            const uint4 a = __ldg(vp);
-            const uint4 b = (w * 32 + 16 < A.W) ? __ldg(vp + 1) : make_uint4(0, 0, 0, 0);
-            cw = k[u] & ge_bits(a, b, lo4);
-            sw = k[u] & ge_bits(a, b, hi4);
+        for (int u = 0; u < 8; u++) {
+            const int i = w0 + tid + u * 256;
+            k[u] = i < w1 ? __ldg(kb + i) : 0u;
         }
-        cb[i] = cw;
-        sb[i] = sw;
+#pragma unroll
+        for (int u = 0; u < 8; u++) {
+            const int i = w0 + tid + u * 256;
+            if (i >= w1) break;
+            uint32_t cw = 0, sw = 0;
+            if (k[u]) {
+                const int r = i / A.WW, w = i - r * A.WW;
+                const uint4 *vp = reinterpret_cast<const uint4 *>(vb + (size_t)r * A.W + w * 32);
+                const uint4 a = __ldg(vp);
+                const uint4 b = (w * 32 + 16 < A.W) ? __ldg(vp + 1) : make_uint4(0, 0, 0, 0);
+                cw = k[u] & ge_bits(a, b, lo4);
+                sw = k[u] & ge_bits(a, b, hi4);
+            }
+            cb[i] = cw;
+            sb[i] = sw;
+        }
     }
 }
 
@@ -831,7 +831,7 @@ bool launch_canny_cluster_fused(const uint32_t *k_bits, const uint8_t *v_plane, 
     T.redo_flag = redo_flag; T.frame_list = frame_list; T.n_list = frame_list ? redo_count : nullptr;
     T.c_bits = c_bits; T.s_bits = s_bits; T.H = H; T.W = W; T.WW = WW;
     T.words_per_cta = 256 * 8;              // the kernel handles exactly eight words per thread
-    dim3 tgrid((H * WW + T.words_per_cta - 1) / T.words_per_cta, n);
+    dim3 tgrid((H * WW + T.words_per_cta - 1) / T.words_per_cta, frame_list ? std::min(n, 8) : n);
     k2t_threshold<<<tgrid, 256, 0, st>>>(T);
     K2Args A{};
     A.c_bits = c_bits; A.s_bits = s_bits; A.skip_flag = redo_flag;
