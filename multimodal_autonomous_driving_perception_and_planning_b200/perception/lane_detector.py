@@ -122,19 +122,20 @@ class LaneDetector:
 
     # ------------------------------------------------------------------ record decoding
     def _lanes_from_records(self, recs: np.ndarray) -> List[LanePair]:
-        out: List[LanePair] = []
+        """Records -> (left, right) pairs.  The point and coefficient arrays of a batch are copied out of the record
+        buffer once; every LaneLine then holds its own rows of those copies (host time matters here: at 8 000 frames/s
+        end to end, two array copies per lane were 7 % of the call)."""
         sides = recs["side"]
+        valid = sides["valid"].astype(bool)
+        points = np.ascontiguousarray(sides["points"], dtype=np.int32)          # [n, 2, 50, 2]
+        coeffs = np.ascontiguousarray(sides["coeffs"], dtype=np.float64)        # [n, 2, 3]
+        conf = sides["confidence"].tolist()
+        out: List[LanePair] = []
         for i in range(len(recs)):
-            pair = []
-            for s in (0, 1):
-                sd = sides[i, s]
-                if sd["valid"]:
-                    pair.append(LaneLine(points=sd["points"].astype(np.int32, copy=True), side=_SIDES[s],
-                                         confidence=float(sd["confidence"]),
-                                         polynomial=sd["coeffs"].astype(np.float64, copy=True)))
-                else:
-                    pair.append(None)
-            out.append((pair[0], pair[1]))
+            v = valid[i]
+            left = LaneLine(points[i, 0], "left", conf[i][0], coeffs[i, 0]) if v[0] else None
+            right = LaneLine(points[i, 1], "right", conf[i][1], coeffs[i, 1]) if v[1] else None
+            out.append((left, right))
         return out
 
     def _run(self, frames, stream_id, n_streams, prev_fit, prev_valid, nv12: bool = False) -> np.ndarray:
@@ -219,13 +220,19 @@ class LaneDetector:
         fit, valid = self._state_arrays()
         recs = self._run(frames, None, 1, fit, valid)
         lanes = self._lanes_from_records(recs)
-        # like the reference (:210-216), prev_*_fit aliases the last returned polynomial of that side
-        for left, right in lanes:
+        self._adopt_state(lanes)
+        return lanes
+
+    def _adopt_state(self, lanes: List[LanePair]):
+        """Like the reference (:210-216), prev_*_fit aliases the last returned polynomial of that side."""
+        for left, _ in reversed(lanes):
             if left is not None:
                 self.prev_left_fit = left.polynomial
+                break
+        for _, right in reversed(lanes):
             if right is not None:
                 self.prev_right_fit = right.polynomial
-        return lanes
+                break
 
     def detect_batch_nv12(self, frames) -> List[LanePair]:
         """``detect_batch`` for frames still in a video decoder's NV12 layout: uint8 ``[N, H*3/2, W]`` (Y plane, then
@@ -242,11 +249,7 @@ class LaneDetector:
         fit, valid = self._state_arrays()
         recs = self._run(frames, None, 1, fit, valid, nv12=True)
         lanes = self._lanes_from_records(recs)
-        for left, right in lanes:
-            if left is not None:
-                self.prev_left_fit = left.polynomial
-            if right is not None:
-                self.prev_right_fit = right.polynomial
+        self._adopt_state(lanes)
         return lanes
 
     def detect_streams(self, frames, stream_ids: Optional[Sequence[int]] = None) -> List[LanePair]:
