@@ -238,6 +238,51 @@ typedef struct lane_frame_stat {
 LANE_API int lane_frame_stats(const uint8_t *frames, int on_device, int n, int height, int width, lane_frame_stat *out,
                               int device, void *cuda_stream);
 
+/* ---- drawing (the step after the path, and its input fixture) -----------------------------
+ * Batched, bit-exact device forms of the OpenCV drawing calls the reference makes on every frame:
+ *   LaneDetector.draw_lanes                      /root/reference/src/perception/lane_detector.py:220-251
+ *   OverlayRenderer.draw_lane_offset_indicator   /root/reference/src/visualization/overlays.py:103-148
+ *   SyntheticDataGenerator.generate_*            /root/reference/data/generators/__pycache__/synthetic_data.cpython-312.pyc
+ * frames: uint8 [n][height][width][3] BGR, drawn IN PLACE; device pointer when on_device = 1 (work enqueued on
+ * `cuda_stream`), host pointer otherwise (copied in, drawn, copied back).  Both calls return after the stream has been
+ * synchronised.  device_ms (optional): device time of the command upload + rasterisation.  Need no context; errors via
+ * lane_last_error(NULL). */
+
+/* A stream of cv2-level drawing calls per frame, executed in order (painter's order, as consecutive cv2 calls are).
+ * commands: int32 words; command_begin: int64 [n + 1], frame f owns words [command_begin[f], command_begin[f + 1]).
+ * color = b | g << 8 | r << 16.  Every command reproduces OpenCV 4.13 for uint8 images, LINE_8, shift 0:
+ *   LANE_DRAW_LINE              x1 y1 x2 y2 color thickness                cv2.line
+ *   LANE_DRAW_RECTANGLE         x1 y1 x2 y2 color thickness(<0: filled)    cv2.rectangle
+ *   LANE_DRAW_CIRCLE            cx cy radius color thickness(<0 only)      cv2.circle, filled
+ *   LANE_DRAW_FILLPOLY          color npts x0 y0 x1 y1 ...                 cv2.fillPoly(img, [pts], color)
+ *   LANE_DRAW_POLYLINES         color thickness closed npts x0 y0 ...      cv2.polylines(img, [pts], closed, color, thickness)
+ *   LANE_DRAW_FILLPOLY_WEIGHTED color alpha beta gamma(float32 bits) npts x0 y0 ...
+ *                               o = img.copy(); cv2.fillPoly(o, [pts], color); img = cv2.addWeighted(img, alpha, o, beta, gamma)
+ *                               (gamma must be 0, as everywhere in the reference: cv2's scalar tail rounds otherwise)
+ *   LANE_DRAW_BITMAP            x y w h color bits[h][(w + 31) / 32]       pixels (x + i, y + j) with bit i of row j set get
+ *                               `color` (how cv2.putText output enters: rendered once per string on the host)
+ *   LANE_DRAW_ROWS              y_start count x1 x2 color[count]           cv2.line((x1, y), (x2, y), color[y - y_start], 1)
+ *                               for count consecutive rows (the generator's sky gradient) */
+#define LANE_DRAW_LINE 1
+#define LANE_DRAW_RECTANGLE 2
+#define LANE_DRAW_CIRCLE 3
+#define LANE_DRAW_FILLPOLY 4
+#define LANE_DRAW_POLYLINES 5
+#define LANE_DRAW_FILLPOLY_WEIGHTED 6
+#define LANE_DRAW_BITMAP 7
+#define LANE_DRAW_ROWS 8
+LANE_API int lane_draw_commands(uint8_t *frames, int on_device, int n, int height, int width, const int32_t *commands,
+                                const int64_t *command_begin, int device, void *cuda_stream, float *device_ms);
+
+/* LaneDetector.draw_lanes (lane_detector.py:220-251) for a batch: the lane area between the two 50-point polylines
+ * filled with (0, 255, 100) at weight 0.3 (only when fill_lane and both sides are valid), then the left polyline in
+ * (255, 0, 0) and the right one in (0, 0, 255), thickness 3.
+ *   left_points / right_points   host int32 [n][LANE_NUM_POINTS][2] (x, y) = LaneLine.points (lane_side.points)
+ *   left_valid / right_valid     host uint8 [n], 0 = that side is None */
+LANE_API int lane_draw_lanes_batch(uint8_t *frames, int on_device, int n, int height, int width, const int32_t *left_points,
+                                   const uint8_t *left_valid, const int32_t *right_points, const uint8_t *right_valid,
+                                   int fill_lane, int device, void *cuda_stream, float *device_ms);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,397 @@
+// K7: batched cv2-exact rasteriser (the step right after the lane path, and its input fixture).
+//
+// What it replaces, for a whole batch of frames resident in HBM:
+//   LaneDetector.draw_lanes                      /root/reference/src/perception/lane_detector.py:220-251
+//       cv2.fillPoly on a copy + cv2.addWeighted(frame, 0.7, overlay, 0.3, 0) + cv2.polylines(.., thickness 3)
+//   OverlayRenderer.draw_lane_offset_indicator   /root/reference/src/visualization/overlays.py:103-148
+//       cv2.rectangle (filled, outlined), cv2.line, filled cv2.circle, cv2.putText (as a host-rendered bit mask)
+//   SyntheticDataGenerator.generate_frame_with_vehicles (bytecode only)
+//       cv2.line (thickness 1 and 2), cv2.rectangle, cv2.fillPoly, filled cv2.circle
+//
+// Two layers.  The host layer (this file, plain C++) turns cv2-level calls into row-separable device primitives with
+// OpenCV 4.13's own integer / double arithmetic (clipLine's truncating double division, Bresenham end points, the
+// 16.16 DDA that outlines FillConvexPoly, FillConvexPoly's rounded edge steps, the pre-clip of thick segments against the
+// image grown by `thickness`, ThickLine's cvRound'ed normal, the midpoint circle, fillPoly's edge table built from the
+// clipped end points) -- restated in oracle/draw.py and pinned there against cv2 itself.  The device layer rasterises:
+// one CTA per (band of rows, frame) walks the frame's primitive list in order (painter's order is what cv2 gives), a
+// barrier between primitives that touch the band; inside a primitive every row / point is independent:
+//   TRAP      rows y0..y1 of a trapezoid with 16.16 edges  -> 16-byte stores of the 3-byte colour pattern
+//   ROWS      consecutive full-width rows, one colour each (the generator's sky gradient: 540 cv2.line calls)
+//   LINE8     8-connected Bresenham line, point i in closed form: minor = (2*dmin*i + dmaj - 1) / (2*dmaj)
+//   LINE2     16.16 DDA line, point i in closed form
+//   POLYFILL  fillPoly's scan conversion: a warp per row gathers the active edges, orders their x, fills the pairs
+//   MASK_BEGIN .. MASK_BLEND   the primitives in between set bits of a shared-memory coverage mask of the band instead
+//             of writing pixels; MASK_BLEND then applies cv2.addWeighted's float32 fma(a, alpha, fma(b, beta, gamma))
+//             once per covered pixel (a pixel on the polygon outline AND inside it is blended once, as cv2's overlay is)
+//   BITMAP    1-bit mask blit (text)
+// HBM-bound byte work: no tensor cores, no GEMM shapes.
+#include <math.h>
+#include <string.h>
+
+#include <algorithm>
+#include <mutex>
+#include <vector>
+
+#include "draw_prims.h"
+#include "lane_common.cuh"
+
+using namespace lane_draw;
+
+namespace {
+
+// ------------------------------------------------------------------------------------------------ device side
+struct Target {
+    uint8_t *frame;      // this frame
+    uint32_t *mask;      // band mask in shared memory
+    int H, W, WW;        // WW = words per mask row
+    int by0, by1;        // band rows [by0, by1]
+    bool to_mask;
+};
+
+__device__ __forceinline__ uint32_t pattern_word(uint32_t color, int q)   // 4 bytes of the BGR pattern starting at channel q
+{
+    const uint32_t c0 = color & 255, c1 = (color >> 8) & 255, c2 = (color >> 16) & 255;
+    const uint32_t w0 = c0 | c1 << 8 | c2 << 16 | c0 << 24, w1 = c1 | c2 << 8 | c0 << 16 | c1 << 24,
+                   w2 = c2 | c0 << 8 | c1 << 16 | c2 << 24;
+    return q == 0 ? w0 : q == 1 ? w1 : w2;
+}
+
+// pixels x1..x2 (already clipped, x1 <= x2) of row y, by one warp
+__device__ void warp_span(const Target &t, int y, int x1, int x2, uint32_t color, int lane)
+{
+    if (t.to_mask) {
+        uint32_t *row = t.mask + (size_t)(y - t.by0) * t.WW;
+        const int w1 = x1 >> 5, w2 = x2 >> 5;
+        for (int w = w1 + lane; w <= w2; w += 32) {
+            uint32_t m = 0xffffffffu;
+            if (w == w1) m &= 0xffffffffu << (x1 & 31);
+            if (w == w2) m &= 0xffffffffu >> (31 - (x2 & 31));
+            atomicOr(row + w, m);
+        }
+        return;
+    }
+    uint8_t *row = t.frame + (size_t)y * t.W * 3;
+    const long b0 = 3L * x1, b1 = 3L * x2 + 3;
+    const uintptr_t base = (uintptr_t)row;
+    long al = (long)(((base + b0 + 15) & ~(uintptr_t)15) - base);
+    if (al > b1) al = b1;
+    if (lane < al - b0) {
+        const long o = b0 + lane;
+        row[o] = (uint8_t)(color >> (8 * (o % 3)));
+    }
+    const long nvec = (b1 - al) >> 4;
+    for (long v = lane; v < nvec; v += 32) {
+        const long o = al + 16 * v;
+        const int q = (int)(o % 3);
+        uint4 val;
+        val.x = pattern_word(color, q);
+        val.y = pattern_word(color, (q + 1) % 3);
+        val.z = pattern_word(color, (q + 2) % 3);
+        val.w = val.x;
+        *(uint4 *)(row + o) = val;
+    }
+    const long t0 = al + 16 * nvec;
+    if (lane < b1 - t0) {
+        const long o = t0 + lane;
+        row[o] = (uint8_t)(color >> (8 * (o % 3)));
+    }
+}
+
+__device__ __forceinline__ void plot(const Target &t, int x, int y, uint32_t color)
+{
+    if ((unsigned)x >= (unsigned)t.W || y < t.by0 || y > t.by1) return;
+    if (t.to_mask) {
+        atomicOr(t.mask + (size_t)(y - t.by0) * t.WW + (x >> 5), 1u << (x & 31));
+    } else {
+        uint8_t *p = t.frame + ((size_t)y * t.W + x) * 3;
+        p[0] = (uint8_t)color;
+        p[1] = (uint8_t)(color >> 8);
+        p[2] = (uint8_t)(color >> 16);
+    }
+}
+
+__device__ __forceinline__ void clipped_span(const Target &t, int y, long x1, long x2, uint32_t color, int lane)
+{
+    if (x2 >= 0 && x1 < t.W) {
+        if (x1 < 0) x1 = 0;
+        if (x2 >= t.W) x2 = t.W - 1;
+        if (x1 <= x2) warp_span(t, y, (int)x1, (int)x2, color, lane);
+    }
+}
+
+__global__ void __launch_bounds__(DRAW_THREADS) k7_draw(uint8_t *frames, const Prim *prims, const int64_t *prim_begin,
+                                                       const int64_t *side, int H, int W)
+{
+    extern __shared__ uint32_t smem[];
+    const int f = blockIdx.y, band = blockIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = DRAW_THREADS / 32;
+    Target t;
+    t.frame = frames + (size_t)f * H * W * 3;
+    t.H = H; t.W = W; t.WW = (W + 31) >> 5;
+    t.by0 = band * BAND_ROWS;
+    t.by1 = min(H, t.by0 + BAND_ROWS) - 1;
+    t.mask = smem;
+    t.to_mask = false;
+    int64_t *row_x = (int64_t *)(smem + (size_t)BAND_ROWS * t.WW + (((size_t)BAND_ROWS * t.WW) & 1)) + warp * MAX_ROW_EDGES;
+
+    const int64_t p_end = prim_begin[f + 1];
+    for (int64_t pi = prim_begin[f]; pi < p_end; pi++) {
+        const Prim p = prims[pi];
+        if (p.op == P_MASK_BEGIN) {              // band-uniform state: no row test
+            __syncthreads();
+            for (int i = tid; i < BAND_ROWS * t.WW; i += DRAW_THREADS) t.mask[i] = 0;
+            t.to_mask = true;
+            __syncthreads();
+            continue;
+        }
+        const int ya = max(p.y0, t.by0), yb = min(p.y1, t.by1);
+        if (p.op == P_MASK_BLEND) {
+            __syncthreads();
+            t.to_mask = false;
+            if (ya <= yb) {
+                const float alpha = __int_as_float((int)(uint32_t)p.a), beta = __int_as_float((int)(uint32_t)(p.a >> 32));
+                const float gamma = __int_as_float((int)(uint32_t)p.b);
+                const bool outside_too = (p.b >> 32) & 1;
+                const int x0 = (int)p.c, x1 = (int)p.d, bw = x1 - x0 + 1;
+                const int total = (yb - ya + 1) * bw;
+                for (int i = tid; i < total; i += DRAW_THREADS) {
+                    const int y = ya + i / bw, x = x0 + i % bw;
+                    const bool in = (t.mask[(size_t)(y - t.by0) * t.WW + (x >> 5)] >> (x & 31)) & 1;
+                    if (!in && !outside_too) continue;
+                    uint8_t *px = t.frame + ((size_t)y * W + x) * 3;
+#pragma unroll
+                    for (int ch = 0; ch < 3; ch++) {
+                        const float a = (float)px[ch];
+                        const float o = in ? (float)((p.color >> (8 * ch)) & 255) : a;
+                        const int r = __float2int_rn(fmaf(a, alpha, fmaf(o, beta, gamma)));
+                        px[ch] = (uint8_t)min(255, max(0, r));
+                    }
+                }
+            }
+            __syncthreads();
+            continue;
+        }
+        if (ya > yb) continue;
+        switch (p.op) {
+        case P_TRAP:
+            for (int y = ya + warp; y <= yb; y += nwarps) {
+                int64_t l = p.a + (int64_t)(y - p.y0) * p.b, r = p.c + (int64_t)(y - p.y0) * p.d;
+                if (l > r) { const int64_t s = l; l = r; r = s; }
+                clipped_span(t, y, (long)((l + HALF) >> XY_SHIFT), (long)((r + HALF) >> XY_SHIFT), p.color, lane);
+            }
+            break;
+        case P_ROWS: {
+            const uint32_t *colors = (const uint32_t *)(side + p.a);
+            const int x1 = (int)p.b, x2 = (int)p.c;
+            for (int y = ya + warp; y <= yb; y += nwarps) clipped_span(t, y, x1, x2, colors[y - p.y0 + (int)p.d], lane);
+            break;
+        }
+        case P_LINE8: {
+            const int x1 = (int)(p.a >> 32), y1 = (int)(uint32_t)p.a;
+            const int dmaj = (int)(p.b >> 32), dmin = (int)(uint32_t)p.b;
+            const bool vert = p.c & 1;
+            const int sy = (p.c & 2) ? -1 : 1;
+            for (int i = tid; i <= dmaj; i += DRAW_THREADS) {
+                const int k = dmaj ? (int)((2LL * dmin * i + dmaj - 1) / (2LL * dmaj)) : 0;
+                if (vert) plot(t, x1 + k, y1 + sy * i, p.color);
+                else plot(t, x1 + i, y1 + sy * k, p.color);
+            }
+            break;
+        }
+        case P_LINE2: {
+            const int m0 = (int)(p.a >> 32), count = (int)(uint32_t)p.a;
+            for (int i = tid; i < count; i += DRAW_THREADS) {
+                const int minor = (int)((p.b + (int64_t)i * p.c) >> XY_SHIFT);
+                if (p.d & 1) plot(t, m0 + i, minor, p.color);
+                else plot(t, minor, m0 + i, p.color);
+            }
+            break;
+        }
+        case P_POLYFILL: {
+            const int64_t *edges = side + p.a;      // (y0, y1, x, dx) per edge
+            const int ne = (int)p.b;
+            for (int y = ya + warp; y <= yb; y += nwarps) {
+                int n = 0;
+                for (int e0 = 0; e0 < ne; e0 += 32) {
+                    const int e = e0 + lane;
+                    bool act = false;
+                    int64_t x = 0;
+                    if (e < ne) {
+                        const int64_t ey0 = edges[4 * e], ey1 = edges[4 * e + 1];
+                        act = ey0 <= y && y < ey1;
+                        if (act) x = edges[4 * e + 2] + (y - ey0) * edges[4 * e + 3];
+                    }
+                    const unsigned m = __ballot_sync(0xffffffffu, act);
+                    const int pos = n + __popc(m & ((1u << lane) - 1));
+                    if (act && pos < MAX_ROW_EDGES) row_x[pos] = x;
+                    n += __popc(m);
+                }
+                n = min(n, MAX_ROW_EDGES);
+                __syncwarp();
+                // rank sort (n is 2 for a simple polygon)
+                int64_t mine[MAX_ROW_EDGES / 32];
+                int rank[MAX_ROW_EDGES / 32];
+#pragma unroll
+                for (int j = 0; j < MAX_ROW_EDGES / 32; j++) {
+                    const int i = lane + 32 * j;
+                    rank[j] = 0;
+                    if (i < n) {
+                        mine[j] = row_x[i];
+                        for (int k = 0; k < n; k++) {
+                            const int64_t o = row_x[k];
+                            rank[j] += (o < mine[j]) || (o == mine[j] && k < i);
+                        }
+                    }
+                }
+                __syncwarp();
+#pragma unroll
+                for (int j = 0; j < MAX_ROW_EDGES / 32; j++)
+                    if (lane + 32 * j < n) row_x[rank[j]] = mine[j];
+                __syncwarp();
+                for (int k = 0; k + 1 < n; k += 2)
+                    clipped_span(t, y, (long)((row_x[k] + XY_ONE - 1) >> XY_SHIFT), (long)(row_x[k + 1] >> XY_SHIFT), p.color, lane);
+                __syncwarp();
+            }
+            break;
+        }
+        case P_BITMAP: {
+            const uint32_t *bits = (const uint32_t *)(side + p.a);
+            const int bx = (int)(p.b >> 32), by = (int)(uint32_t)p.b, bw = (int)(p.c >> 32), bh = (int)(uint32_t)p.c;
+            const int wpr = (bw + 31) >> 5;
+            (void)bh;
+            for (int i = tid; i < (yb - ya + 1) * wpr; i += DRAW_THREADS) {
+                const int y = ya + i / wpr, w = i % wpr;
+                uint32_t m = bits[(size_t)(y - by) * wpr + w];
+                while (m) {
+                    const int b = __ffs(m) - 1;
+                    m &= m - 1;
+                    plot(t, bx + 32 * w + b, y, p.color);
+                }
+            }
+            break;
+        }
+        default: break;
+        }
+        __syncthreads();
+    }
+}
+
+// grow-only device / pinned staging per device; the entry points are blocking, so one set per device is enough
+struct DrawCache {
+    void *d = nullptr, *h = nullptr;
+    size_t cap = 0;
+};
+std::mutex g_draw_mutex;
+DrawCache g_draw_cache[LANE_MAX_DEVICES];
+
+int run_builder(Builder &b, uint8_t *frames, int on_device, int n, int device, cudaStream_t st, double *host_ms, float *device_ms)
+{
+    auto fail = [](int code, const char *msg) { lane_set_global_error(msg); return code; };
+    const int H = b.H, W = b.W;
+    const size_t frame_bytes = (size_t)n * H * W * 3;
+    const size_t nb_begin = (size_t)(n + 1) * 8, nb_prims = b.prims.size() * sizeof(Prim), nb_side = std::max<size_t>(b.side.size(), 1) * 8;
+    const size_t off_prims = (nb_begin + 63) & ~(size_t)63, off_side = (off_prims + nb_prims + 63) & ~(size_t)63;
+    const size_t total = off_side + nb_side;
+    std::lock_guard<std::mutex> lk(g_draw_mutex);
+    DrawCache &c = g_draw_cache[device & (LANE_MAX_DEVICES - 1)];
+    if (c.cap < total) {
+        if (c.d) cudaFree(c.d);
+        if (c.h) cudaFreeHost(c.h);
+        c = DrawCache{};
+        const size_t cap = std::max(total + total / 2, (size_t)1 << 20);
+        if (cudaMalloc(&c.d, cap) != cudaSuccess || cudaMallocHost(&c.h, cap) != cudaSuccess) {
+            if (c.d) cudaFree(c.d);
+            c = DrawCache{};
+            cudaGetLastError();
+            return fail(LANE_ERR_CUDA, "lane_draw: staging allocation failed");
+        }
+        c.cap = cap;
+    }
+    uint8_t *h = (uint8_t *)c.h, *d = (uint8_t *)c.d;
+    memcpy(h, b.begin.data(), nb_begin);
+    if (nb_prims) memcpy(h + off_prims, b.prims.data(), nb_prims);
+    if (!b.side.empty()) memcpy(h + off_side, b.side.data(), b.side.size() * 8);
+    uint8_t *d_frames = frames;
+    if (!on_device) {
+        if (cudaMalloc((void **)&d_frames, frame_bytes) != cudaSuccess) { cudaGetLastError(); return fail(LANE_ERR_CUDA, "lane_draw: device allocation failed"); }
+        cudaMemcpyAsync(d_frames, frames, frame_bytes, cudaMemcpyHostToDevice, st);
+    }
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    if (device_ms) { cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventRecord(e0, st); }
+    cudaMemcpyAsync(d, h, total, cudaMemcpyHostToDevice, st);
+    const int bands = (H + BAND_ROWS - 1) / BAND_ROWS, WW = (W + 31) >> 5;
+    const size_t mask_words = (size_t)BAND_ROWS * WW;
+    const size_t smem = (mask_words + (mask_words & 1)) * 4 + (size_t)(DRAW_THREADS / 32) * MAX_ROW_EDGES * 8;
+    static bool configured[LANE_MAX_DEVICES];
+    if (smem > 48 * 1024 && !configured[device & (LANE_MAX_DEVICES - 1)]) {
+        cudaFuncSetAttribute(k7_draw, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        configured[device & (LANE_MAX_DEVICES - 1)] = true;
+    }
+    if (smem > 200 * 1024) {
+        if (!on_device) cudaFree(d_frames);
+        return fail(LANE_ERR_UNSUPPORTED, "lane_draw: frame too wide for the band mask");
+    }
+    k7_draw<<<dim3(bands, n), DRAW_THREADS, smem, st>>>(d_frames, (const Prim *)(d + off_prims), (const int64_t *)d,
+                                                        (const int64_t *)(d + off_side), H, W);
+    cudaError_t e = cudaGetLastError();
+    if (device_ms) cudaEventRecord(e1, st);
+    if (e == cudaSuccess && !on_device) cudaMemcpyAsync(frames, d_frames, frame_bytes, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    if (e == cudaSuccess && device_ms) cudaEventElapsedTime(device_ms, e0, e1);
+    if (e0) { cudaEventDestroy(e0); cudaEventDestroy(e1); }
+    if (!on_device) cudaFree(d_frames);
+    (void)host_ms;
+    if (e != cudaSuccess) return fail(LANE_ERR_CUDA, cudaGetErrorString(e));
+    return LANE_OK;
+}
+
+int prepare_device(int device, const char *who)
+{
+    auto fail = [](int code, const char *msg) { lane_set_global_error(msg); return code; };
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+        return fail(LANE_ERR_NO_DEVICE, "no CUDA device visible: this library has no CPU fallback");
+    if (device < 0 || device >= ndev) { (void)who; return fail(LANE_ERR_INVALID, "lane_draw: device out of range"); }
+    if (cudaSetDevice(device) != cudaSuccess) return fail(LANE_ERR_CUDA, "cudaSetDevice failed");
+    return LANE_OK;
+}
+
+}  // namespace
+
+extern "C" int lane_draw_commands(uint8_t *frames, int on_device, int n, int height, int width, const int32_t *commands,
+                                  const int64_t *command_begin, int device, void *cuda_stream, float *device_ms)
+{
+    auto fail = [](int code, const char *msg) { lane_set_global_error(msg); return code; };
+    if (!frames || !commands || !command_begin || n < 1 || height < 1 || width < 1)
+        return fail(LANE_ERR_INVALID, "lane_draw_commands: bad arguments");
+    if (height > 32767 || width > 32767) return fail(LANE_ERR_UNSUPPORTED, "lane_draw_commands: frame larger than 32767 px");
+    if (int rc = prepare_device(device, "lane_draw_commands")) return rc;
+    Builder b;
+    b.H = height; b.W = width;
+    b.begin.reserve(n + 1);
+    for (int f = 0; f < n; f++) {
+        b.begin.push_back((int64_t)b.prims.size());
+        if (command_begin[f + 1] < command_begin[f]) return fail(LANE_ERR_INVALID, "lane_draw_commands: command_begin must not decrease");
+        const char *err = nullptr;
+        if (!parse_commands(b, commands + command_begin[f], command_begin[f + 1] - command_begin[f], &err)) return fail(LANE_ERR_INVALID, err);
+    }
+    b.begin.push_back((int64_t)b.prims.size());
+    return run_builder(b, frames, on_device, n, device, (cudaStream_t)cuda_stream, nullptr, device_ms);
+}
+
+extern "C" int lane_draw_lanes_batch(uint8_t *frames, int on_device, int n, int height, int width, const int32_t *left_points,
+                                     const uint8_t *left_valid, const int32_t *right_points, const uint8_t *right_valid,
+                                     int fill_lane, int device, void *cuda_stream, float *device_ms)
+{
+    auto fail = [](int code, const char *msg) { lane_set_global_error(msg); return code; };
+    if (!frames || !left_points || !right_points || !left_valid || !right_valid || n < 1 || height < 1 || width < 1)
+        return fail(LANE_ERR_INVALID, "lane_draw_lanes_batch: bad arguments");
+    if (height > 32767 || width > 32767) return fail(LANE_ERR_UNSUPPORTED, "lane_draw_lanes_batch: frame larger than 32767 px");
+    if (int rc = prepare_device(device, "lane_draw_lanes_batch")) return rc;
+    Builder b;
+    b.H = height; b.W = width;
+    b.begin.reserve(n + 1);
+    build_draw_lanes(b, n, left_points, left_valid, right_points, right_valid, fill_lane);
+    b.begin.push_back((int64_t)b.prims.size());
+    return run_builder(b, frames, on_device, n, device, (cudaStream_t)cuda_stream, nullptr, device_ms);
+}

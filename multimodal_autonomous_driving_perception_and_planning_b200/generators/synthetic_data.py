@@ -23,6 +23,64 @@ import numpy as np
 _VEHICLE_COLORS = [(0, 100, 200), (200, 50, 50), (50, 200, 50), (200, 200, 50)]
 
 
+class _Cv2Canvas:
+    """The scene code draws through this: cv2 on a host image ..."""
+
+    def __init__(self, img):
+        self.img = img
+
+    def line(self, p1, p2, color, thickness):
+        cv2.line(self.img, p1, p2, color, thickness)
+
+    def rectangle(self, p1, p2, color, thickness):
+        cv2.rectangle(self.img, p1, p2, color, thickness)
+
+    def circle(self, center, radius, color, thickness):
+        cv2.circle(self.img, center, radius, color, thickness)
+
+    def fillPoly(self, pts, color):
+        cv2.fillPoly(self.img, [pts], color)
+
+    def rows(self, y_start, x1, x2, colors):
+        for i, c in enumerate(colors):
+            cv2.line(self.img, (x1, y_start + i), (x2, y_start + i), c, 1)
+
+    def cached(self, cache, key, paint):
+        paint(self)
+
+
+class _ListCanvas:
+    """... or the same calls recorded into a DrawList for the device rasteriser (csrc/k7_draw.cu)."""
+
+    def __init__(self, dl, frame):
+        self.dl, self.frame = dl, frame
+
+    def line(self, p1, p2, color, thickness):
+        self.dl.line(self.frame, p1, p2, color, thickness)
+
+    def rectangle(self, p1, p2, color, thickness):
+        self.dl.rectangle(self.frame, p1, p2, color, thickness)
+
+    def circle(self, center, radius, color, thickness):
+        self.dl.circle(self.frame, center, radius, color, thickness)
+
+    def fillPoly(self, pts, color):
+        self.dl.fillPoly(self.frame, pts, color)
+
+    def rows(self, y_start, x1, x2, colors):
+        self.dl.rows(self.frame, y_start, x1, x2, colors)
+
+    def cached(self, cache, key, paint):
+        """Frame-independent layers (sky, ground, trees) are encoded once per generator and replayed as words."""
+        words = cache.get(key)
+        if words is None:
+            from ..visualization.draw_list import DrawList
+            tmp = DrawList(1)
+            paint(_ListCanvas(tmp, 0))
+            words = cache[key] = tmp.encoded(0)
+        self.dl.extend(self.frame, words)
+
+
 class SyntheticDataGenerator:
     def __init__(self, width: int = 640, height: int = 480, fps: float = 30.0):
         self.width = width
@@ -30,25 +88,32 @@ class SyntheticDataGenerator:
         self.fps = fps
         self.dt = 1.0 / fps
         self.frame_count = 0
+        self._static = {}            # encoded frame-independent layers of the device path
 
     # ------------------------------------------------------------------ scene layers
-    def generate_road_frame(self) -> np.ndarray:
+    def _paint_road(self, cv):
         w, h = self.width, self.height
         half = h // 2
-        img = np.zeros((h, w, 3), dtype=np.uint8)
-        for y in range(half):
-            r = y / half
-            cv2.line(img, (0, y), (w, y), (int(200 - 80 * r), int(180 - 60 * r), int(255 - 55 * r)), 1)
-        cv2.rectangle(img, (0, half), (w, h), (60, 60, 60), -1)
+
+        def backdrop(c):
+            c.rows(0, 0, w, [(int(200 - 80 * (y / half)), int(180 - 60 * (y / half)), int(255 - 55 * (y / half)))
+                             for y in range(half)])
+            c.rectangle((0, half), (w, h), (60, 60, 60), -1)
+
+        cv.cached(self._static, ("backdrop", w, h), backdrop)
         vp_x = w // 2 + int(20 * np.sin(self.frame_count * 0.02))
         vp_y = half
         road = np.array([[vp_x, vp_y], [50, h], [w - 50, h]], dtype=np.int32)
-        cv2.fillPoly(img, [road], (80, 80, 80))
-        self._draw_lane_markings(img, vp_x, vp_y)
-        self._draw_environment(img, half)
+        cv.fillPoly(road, (80, 80, 80))
+        self._draw_lane_markings(cv, vp_x, vp_y)
+        cv.cached(self._static, ("environment", w, h), lambda c: self._draw_environment(c, half))
+
+    def generate_road_frame(self) -> np.ndarray:
+        img = np.zeros((self.height, self.width, 3), dtype=np.uint8)
+        self._paint_road(_Cv2Canvas(img))
         return img
 
-    def _draw_lane_markings(self, img, vp_x, vp_y):
+    def _draw_lane_markings(self, cv, vp_x, vp_y):
         h = self.height
         n = 10
         scroll = (self.frame_count * 5) % (h // n)
@@ -59,15 +124,14 @@ class SyntheticDataGenerator:
         for i in range(n):
             ya, yb = row(i / n), row((i + 0.5) / n)
             if ya >= vp_y and yb >= vp_y:
-                cv2.line(img, (vp_x, ya), (vp_x, yb), (255, 255, 200), 2)
+                cv.line((vp_x, ya), (vp_x, yb), (255, 255, 200), 2)
         for side in (-1, 1):
             spread = side * 150
             for i in range(n):
                 t1, t2 = i / n, (i + 0.6) / n
-                cv2.line(img, (int(vp_x + spread * t1), row(t1)), (int(vp_x + spread * t2), row(t2)),
-                         (255, 255, 255), 2)
+                cv.line((int(vp_x + spread * t1), row(t1)), (int(vp_x + spread * t2), row(t2)), (255, 255, 255), 2)
 
-    def _draw_environment(self, img, horizon_y):
+    def _draw_environment(self, cv, horizon_y):
         w, h = self.width, self.height
         for i in range(5):
             t = (i + 0.5) / 5
@@ -75,22 +139,27 @@ class SyntheticDataGenerator:
             inset = int(30 + 50 * t)
             tall = int(30 + 40 * t)
             for x in (inset, w - inset):
-                cv2.line(img, (x, base), (x, base - tall), (80, 50, 30), 2)
-                cv2.circle(img, (x, base - tall - 10), int(15 * t + 5), (50, 120, 50), -1)
+                cv.line((x, base), (x, base - tall), (80, 50, 30), 2)
+                cv.circle((x, base - tall - 10), int(15 * t + 5), (50, 120, 50), -1)
+
+    @staticmethod
+    def _paint_vehicle(cv, x, y, scale=1.0, color=(0, 100, 200)):
+        bw, bh = int(60 * scale), int(40 * scale)
+        cv.rectangle((x - bw // 2, y - bh // 2), (x + bw // 2, y + bh // 2), color, -1)
+        cv.rectangle((x - bw // 2, y - bh // 2), (x + bw // 2, y + bh // 2), (0, 0, 0), 1)
+        cv.rectangle((x - bw // 3, y - bh // 2), (x + bw // 3, y - bh // 4), (100, 100, 100), -1)
+        rad = int(8 * scale)
+        cv.circle((x - bw // 3, y + bh // 2), rad, (30, 30, 30), -1)
+        cv.circle((x + bw // 3, y + bh // 2), rad, (30, 30, 30), -1)
 
     def generate_vehicle(self, frame, x, y, scale=1.0, color=(0, 100, 200)):
-        bw, bh = int(60 * scale), int(40 * scale)
-        cv2.rectangle(frame, (x - bw // 2, y - bh // 2), (x + bw // 2, y + bh // 2), color, -1)
-        cv2.rectangle(frame, (x - bw // 2, y - bh // 2), (x + bw // 2, y + bh // 2), (0, 0, 0), 1)
-        cv2.rectangle(frame, (x - bw // 3, y - bh // 2), (x + bw // 3, y - bh // 4), (100, 100, 100), -1)
-        rad = int(8 * scale)
-        cv2.circle(frame, (x - bw // 3, y + bh // 2), rad, (30, 30, 30), -1)
-        cv2.circle(frame, (x + bw // 3, y + bh // 2), rad, (30, 30, 30), -1)
+        self._paint_vehicle(_Cv2Canvas(frame), x, y, scale, color)
         return frame
 
-    def generate_frame_with_vehicles(self) -> np.ndarray:
+    def _paint_frame_with_vehicles(self, cv):
+        """One frame of the stream through ``cv`` (host image or recorded list); advances ``frame_count``."""
         w, h = self.width, self.height
-        frame = self.generate_road_frame()
+        self._paint_road(cv)
         # The reference reseeds NumPy's legacy global RNG every frame; a private RandomState
         # with the same seed yields the same draws without clobbering global state.
         rs = np.random.RandomState(self.frame_count % 100)
@@ -100,8 +169,12 @@ class SyntheticDataGenerator:
             lane = rs.choice([-80, 0, 80])
             x = w // 2 + int(lane * t) + rs.randint(-20, 20)
             x += int(30 * np.sin(self.frame_count * 0.05 + i))
-            self.generate_vehicle(frame, x, y, 0.3 + 0.7 * t, _VEHICLE_COLORS[i % 4])
+            self._paint_vehicle(cv, x, y, 0.3 + 0.7 * t, _VEHICLE_COLORS[i % 4])
         self.frame_count += 1
+
+    def generate_frame_with_vehicles(self) -> np.ndarray:
+        frame = np.zeros((self.height, self.width, 3), dtype=np.uint8)
+        self._paint_frame_with_vehicles(_Cv2Canvas(frame))
         return frame
 
     def generate_video_stream(self, num_frames: int = 300) -> Iterator[np.ndarray]:
@@ -123,6 +196,29 @@ class SyntheticDataGenerator:
         for i in range(num_frames):
             out[i] = self.generate_frame_with_vehicles()
         return out
+
+
+    def generate_batch_device(self, num_frames: int, start_frame: Optional[int] = None, device=None, out=None,
+                              return_ms: bool = False):
+        """The same ``num_frames`` consecutive frames as :meth:`generate_batch`, rasterised ON THE GPU: the scene code
+        records its cv2 calls per frame and ``lane_draw_commands`` (csrc/k7_draw.cu) executes them for the whole batch on
+        a zeroed ``uint8[num_frames, H, W, 3]`` CUDA tensor -- bit-identical to the host frames (no
+        CPU rasterisation and no 6 MB-per-frame upload in a benchmark's set-up).  There is no CPU fallback."""
+        import torch
+        from ..visualization.draw_list import DrawList
+        if start_frame is not None:
+            self.frame_count = start_frame
+        dev = torch.device("cuda", torch.cuda.current_device() if device is None else int(device))
+        if out is None:
+            out = torch.zeros((num_frames, self.height, self.width, 3), dtype=torch.uint8, device=dev)
+        else:
+            out.zero_()
+        dl = DrawList(num_frames)
+        for i in range(num_frames):
+            self._paint_frame_with_vehicles(_ListCanvas(dl, i))
+        with torch.cuda.device(dev):
+            res = dl.execute(out, return_ms=return_ms)
+        return res
 
 
 def multi_camera_batch(num_streams: int, frames_per_stream: int, width: int = 1920, height: int = 1080,

@@ -283,8 +283,8 @@ class LaneDetector:
 
     def draw_lanes(self, frame: np.ndarray, left_lane: Optional[LaneLine], right_lane: Optional[LaneLine],
                    fill_lane: bool = True) -> np.ndarray:
-        """Overlay rendering, kept on the CPU with cv2 as in the reference (lane_detector.py:220-251):
-        translucent fill between the lanes, then the two polylines (blue left, red right)."""
+        """Overlay rendering of ONE host frame with cv2, as in the reference (lane_detector.py:220-251): translucent fill
+        between the lanes, then the two polylines (blue left, red right).  ``draw_lanes_batch`` is the device form."""
         if fill_lane and left_lane is not None and right_lane is not None:
             filled = frame.copy()
             outline = np.vstack([left_lane.points, right_lane.points[::-1]])
@@ -294,6 +294,14 @@ class LaneDetector:
             if lane is not None:
                 cv2.polylines(frame, [lane.points], False, colour, 3)
         return frame
+
+    def draw_lanes_batch(self, frames, lanes: Sequence[LanePair], fill_lane: bool = True):
+        """``draw_lanes`` for a whole batch on the GPU, IN PLACE: ``frames`` uint8 ``[N,H,W,3]`` (CUDA tensor: stays in
+        HBM; numpy: round trip inside the call), ``lanes`` as ``detect_batch`` returned them.  Pixels equal the
+        reference's ``draw_lanes(frame, left, right, fill_lane)`` (csrc/k7_draw.cu restates cv2's fillPoly / addWeighted
+        / thick polylines bit for bit).  No CPU fallback."""
+        from ..visualization.overlays import draw_lanes_batch
+        return draw_lanes_batch(frames, lanes, fill_lane, self._device if not _is_torch_cuda(frames) else None)
 
     def get_lane_center_offset(self, frame_width: int, left_lane: Optional[LaneLine],
                                right_lane: Optional[LaneLine]) -> Optional[float]:
