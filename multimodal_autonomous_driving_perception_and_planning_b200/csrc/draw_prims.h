@@ -372,7 +372,7 @@ struct Builder {
             x0 = std::max<int64_t>(x0, 0); x1 = std::min<int64_t>(x1, W - 1);
             if (y0 > y1 || x0 > x1) return;
         }
-        prims.push_back(Prim{P_MASK_BEGIN, 0, H - 1, 0, 0, 0, 0, 0});
+        prims.push_back(Prim{P_MASK_BEGIN, (int32_t)y0, (int32_t)y1, 0, 0, 0, 0, 0});
         fill_poly(v, count, color);
         uint32_t ab[3];
         memcpy(&ab[0], &alpha, 4); memcpy(&ab[1], &beta, 4); memcpy(&ab[2], &gamma, 4);
@@ -495,32 +495,36 @@ trunc:
 }
 
 
-// LaneDetector.draw_lanes (/root/reference/src/perception/lane_detector.py:220-251) for n frames
+// LaneDetector.draw_lanes (/root/reference/src/perception/lane_detector.py:220-251) for one frame: L, R = int32 [50][2]
+inline void build_draw_lanes_frame(Builder &b, const int32_t *L, int left_valid, const int32_t *R, int right_valid, int fill_lane)
+{
+    constexpr int NP = 50;
+    const uint32_t fill_color = 0u | 255u << 8 | 100u << 16;      // (0, 255, 100)   lane_detector.py:243
+    const uint32_t left_color = 255u, right_color = 255u << 16;   // (255, 0, 0) :248, (0, 0, 255) :251
+    Pt poly[2 * NP], side_pts[NP];
+    if (fill_lane && left_valid && right_valid) {                 // pts = vstack([left.points, right.points[::-1]])  :242
+        for (int i = 0; i < NP; i++) {
+            poly[i] = Pt{L[2 * i], L[2 * i + 1]};
+            poly[NP + i] = Pt{R[2 * (NP - 1 - i)], R[2 * (NP - 1 - i) + 1]};
+        }
+        b.fill_poly_weighted(poly, 2 * NP, fill_color, 0.7f, 0.3f, 0.0f);
+    }
+    if (left_valid) {
+        for (int i = 0; i < NP; i++) side_pts[i] = Pt{L[2 * i], L[2 * i + 1]};
+        b.polylines(side_pts, NP, false, left_color, 3);
+    }
+    if (right_valid) {
+        for (int i = 0; i < NP; i++) side_pts[i] = Pt{R[2 * i], R[2 * i + 1]};
+        b.polylines(side_pts, NP, false, right_color, 3);
+    }
+}
+
 inline void build_draw_lanes(Builder &b, int n, const int32_t *left_points, const uint8_t *left_valid,
                              const int32_t *right_points, const uint8_t *right_valid, int fill_lane)
 {
-    constexpr int LANE_NUM_POINTS = 50;
-    const uint32_t fill_color = 0u | 255u << 8 | 100u << 16;      // (0, 255, 100)   lane_detector.py:243
-    const uint32_t left_color = 255u, right_color = 255u << 16;   // (255, 0, 0) :248, (0, 0, 255) :251
-    Pt poly[2 * LANE_NUM_POINTS], side_pts[LANE_NUM_POINTS];
     for (int f = 0; f < n; f++) {
         b.begin.push_back((int64_t)b.prims.size());
-        const int32_t *L = left_points + (size_t)f * LANE_NUM_POINTS * 2, *R = right_points + (size_t)f * LANE_NUM_POINTS * 2;
-        if (fill_lane && left_valid[f] && right_valid[f]) {     // pts = vstack([left.points, right.points[::-1]])  :242
-            for (int i = 0; i < LANE_NUM_POINTS; i++) {
-                poly[i] = Pt{L[2 * i], L[2 * i + 1]};
-                poly[LANE_NUM_POINTS + i] = Pt{R[2 * (LANE_NUM_POINTS - 1 - i)], R[2 * (LANE_NUM_POINTS - 1 - i) + 1]};
-            }
-            b.fill_poly_weighted(poly, 2 * LANE_NUM_POINTS, fill_color, 0.7f, 0.3f, 0.0f);
-        }
-        if (left_valid[f]) {
-            for (int i = 0; i < LANE_NUM_POINTS; i++) side_pts[i] = Pt{L[2 * i], L[2 * i + 1]};
-            b.polylines(side_pts, LANE_NUM_POINTS, false, left_color, 3);
-        }
-        if (right_valid[f]) {
-            for (int i = 0; i < LANE_NUM_POINTS; i++) side_pts[i] = Pt{R[2 * i], R[2 * i + 1]};
-            b.polylines(side_pts, LANE_NUM_POINTS, false, right_color, 3);
-        }
+        build_draw_lanes_frame(b, left_points + (size_t)f * 100, left_valid[f], right_points + (size_t)f * 100, right_valid[f], fill_lane);
     }
 }
 

@@ -30,6 +30,7 @@
 
 #include <algorithm>
 #include <mutex>
+#include <thread>
 #include <vector>
 
 #include "draw_prims.h"
@@ -119,8 +120,8 @@ __device__ __forceinline__ void clipped_span(const Target &t, int y, long x1, lo
     }
 }
 
-__global__ void __launch_bounds__(DRAW_THREADS) k7_draw(uint8_t *frames, const Prim *prims, const int64_t *prim_begin,
-                                                       const int64_t *side, int H, int W)
+__global__ void __launch_bounds__(DRAW_THREADS) k7_draw(uint8_t *frames, const Prim *prims, const int64_t *band_begin,
+                                                       const int32_t *band_idx, const int64_t *side, int H, int W)
 {
     extern __shared__ uint32_t smem[];
     const int f = blockIdx.y, band = blockIdx.x;
@@ -134,9 +135,10 @@ __global__ void __launch_bounds__(DRAW_THREADS) k7_draw(uint8_t *frames, const P
     t.to_mask = false;
     int64_t *row_x = (int64_t *)(smem + (size_t)BAND_ROWS * t.WW + (((size_t)BAND_ROWS * t.WW) & 1)) + warp * MAX_ROW_EDGES;
 
-    const int64_t p_end = prim_begin[f + 1];
-    for (int64_t pi = prim_begin[f]; pi < p_end; pi++) {
-        const Prim p = prims[pi];
+    // the primitives of this frame that touch this band, in drawing order (binned on the host)
+    const int64_t p_end = band_begin[(size_t)f * gridDim.x + band + 1];
+    for (int64_t pi = band_begin[(size_t)f * gridDim.x + band]; pi < p_end; pi++) {
+        const Prim p = prims[band_idx[pi]];
         if (p.op == P_MASK_BEGIN) {              // band-uniform state: no row test
             __syncthreads();
             for (int i = tid; i < BAND_ROWS * t.WW; i += DRAW_THREADS) t.mask[i] = 0;
@@ -284,14 +286,73 @@ struct DrawCache {
 std::mutex g_draw_mutex;
 DrawCache g_draw_cache[LANE_MAX_DEVICES];
 
-int run_builder(Builder &b, uint8_t *frames, int on_device, int n, int device, cudaStream_t st, double *host_ms, float *device_ms)
+struct Chunk {
+    Builder b;
+    int f0 = 0, f1 = 0;
+    const char *err = nullptr;
+    std::vector<int32_t> counts;      // [frames of the chunk][bands]: primitives that touch the band
+    int64_t prim_base = 0, side_base = 0;
+};
+
+inline int band_lo(const Prim &p) { return p.y0 / BAND_ROWS; }
+inline int band_hi(const Prim &p) { return p.y1 / BAND_ROWS; }
+
+// The host half, frames in parallel: worker t expands the drawing calls of its frames into primitives and counts them per
+// band; the lists are then laid out in one pinned block (band offsets | primitives | side tables | per-band index lists),
+// filled by the same workers, and uploaded with one copy.  build_frame(Builder&, int f, const char **err) -> bool.
+template <class BuildFrame>
+int draw_driver(uint8_t *frames, int on_device, int n, int H, int W, int device, cudaStream_t st, float *device_ms,
+                BuildFrame build_frame)
 {
     auto fail = [](int code, const char *msg) { lane_set_global_error(msg); return code; };
-    const int H = b.H, W = b.W;
-    const size_t frame_bytes = (size_t)n * H * W * 3;
-    const size_t nb_begin = (size_t)(n + 1) * 8, nb_prims = b.prims.size() * sizeof(Prim), nb_side = std::max<size_t>(b.side.size(), 1) * 8;
-    const size_t off_prims = (nb_begin + 63) & ~(size_t)63, off_side = (off_prims + nb_prims + 63) & ~(size_t)63;
-    const size_t total = off_side + nb_side;
+    const int bands = (H + BAND_ROWS - 1) / BAND_ROWS;
+    const int T = std::max(1, std::min({n / 8, (int)std::thread::hardware_concurrency(), 16}));
+    std::vector<Chunk> chunks(T);
+    auto for_chunks = [&](auto fn) {
+        std::vector<std::thread> th;
+        for (int t = 1; t < T; t++) th.emplace_back([&, t] { fn(chunks[t]); });
+        fn(chunks[0]);
+        for (auto &x : th) x.join();
+    };
+    for (int t = 0; t < T; t++) {
+        chunks[t].f0 = (int)((int64_t)n * t / T);
+        chunks[t].f1 = (int)((int64_t)n * (t + 1) / T);
+        chunks[t].b.H = H;
+        chunks[t].b.W = W;
+    }
+    for_chunks([&](Chunk &c) {
+        c.counts.assign((size_t)(c.f1 - c.f0) * bands, 0);
+        for (int f = c.f0; f < c.f1; f++) {
+            c.b.begin.push_back((int64_t)c.b.prims.size());
+            if (!build_frame(c.b, f, &c.err)) return;
+            int32_t *cnt = c.counts.data() + (size_t)(f - c.f0) * bands;
+            for (size_t i = (size_t)c.b.begin.back(); i < c.b.prims.size(); i++)
+                for (int bd = band_lo(c.b.prims[i]); bd <= band_hi(c.b.prims[i]); bd++) cnt[bd]++;
+        }
+        c.b.begin.push_back((int64_t)c.b.prims.size());
+    });
+    for (const Chunk &c : chunks)
+        if (c.err) return fail(LANE_ERR_INVALID, c.err);
+    int64_t n_prims = 0, n_side = 0;
+    for (Chunk &c : chunks) {
+        c.prim_base = n_prims;
+        c.side_base = n_side;
+        n_prims += (int64_t)c.b.prims.size();
+        n_side += (int64_t)((c.b.side.size() + 1) & ~(size_t)1);
+    }
+    std::vector<int64_t> band_begin((size_t)n * bands + 1);
+    int64_t n_idx = 0;
+    for (const Chunk &c : chunks)
+        for (size_t k = 0; k < c.counts.size(); k++) {
+            band_begin[(size_t)c.f0 * bands + k] = n_idx;
+            n_idx += c.counts[k];
+        }
+    band_begin[(size_t)n * bands] = n_idx;
+    const size_t nb_begin = band_begin.size() * 8, nb_prims = (size_t)n_prims * sizeof(Prim), nb_side = (size_t)std::max<int64_t>(n_side, 1) * 8,
+                 nb_idx = (size_t)std::max<int64_t>(n_idx, 1) * 4;
+    const size_t off_prims = (nb_begin + 63) & ~(size_t)63, off_side = (off_prims + nb_prims + 63) & ~(size_t)63,
+                 off_idx = (off_side + nb_side + 63) & ~(size_t)63, total = off_idx + nb_idx;
+
     std::lock_guard<std::mutex> lk(g_draw_mutex);
     DrawCache &c = g_draw_cache[device & (LANE_MAX_DEVICES - 1)];
     if (c.cap < total) {
@@ -308,9 +369,25 @@ int run_builder(Builder &b, uint8_t *frames, int on_device, int n, int device, c
         c.cap = cap;
     }
     uint8_t *h = (uint8_t *)c.h, *d = (uint8_t *)c.d;
-    memcpy(h, b.begin.data(), nb_begin);
-    if (nb_prims) memcpy(h + off_prims, b.prims.data(), nb_prims);
-    if (!b.side.empty()) memcpy(h + off_side, b.side.data(), b.side.size() * 8);
+    memcpy(h, band_begin.data(), nb_begin);
+    for_chunks([&](Chunk &ck) {
+        Prim *hp = (Prim *)(h + off_prims) + ck.prim_base;
+        int64_t *hs = (int64_t *)(h + off_side) + ck.side_base;
+        int32_t *hi = (int32_t *)(h + off_idx);
+        if (!ck.b.side.empty()) memcpy(hs, ck.b.side.data(), ck.b.side.size() * 8);
+        std::vector<int64_t> cursor(bands);
+        for (int f = ck.f0; f < ck.f1; f++) {
+            for (int bd = 0; bd < bands; bd++) cursor[bd] = band_begin[(size_t)f * bands + bd];
+            for (int64_t i = ck.b.begin[f - ck.f0]; i < ck.b.begin[f - ck.f0 + 1]; i++) {
+                Prim p = ck.b.prims[i];
+                if (p.op == P_ROWS || p.op == P_POLYFILL || p.op == P_BITMAP) p.a += ck.side_base;
+                hp[i] = p;
+                for (int bd = band_lo(p); bd <= band_hi(p); bd++) hi[cursor[bd]++] = (int32_t)(ck.prim_base + i);
+            }
+        }
+    });
+
+    const size_t frame_bytes = (size_t)n * H * W * 3;
     uint8_t *d_frames = frames;
     if (!on_device) {
         if (cudaMalloc((void **)&d_frames, frame_bytes) != cudaSuccess) { cudaGetLastError(); return fail(LANE_ERR_CUDA, "lane_draw: device allocation failed"); }
@@ -319,7 +396,7 @@ int run_builder(Builder &b, uint8_t *frames, int on_device, int n, int device, c
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     if (device_ms) { cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventRecord(e0, st); }
     cudaMemcpyAsync(d, h, total, cudaMemcpyHostToDevice, st);
-    const int bands = (H + BAND_ROWS - 1) / BAND_ROWS, WW = (W + 31) >> 5;
+    const int WW = (W + 31) >> 5;
     const size_t mask_words = (size_t)BAND_ROWS * WW;
     const size_t smem = (mask_words + (mask_words & 1)) * 4 + (size_t)(DRAW_THREADS / 32) * MAX_ROW_EDGES * 8;
     static bool configured[LANE_MAX_DEVICES];
@@ -332,7 +409,7 @@ int run_builder(Builder &b, uint8_t *frames, int on_device, int n, int device, c
         return fail(LANE_ERR_UNSUPPORTED, "lane_draw: frame too wide for the band mask");
     }
     k7_draw<<<dim3(bands, n), DRAW_THREADS, smem, st>>>(d_frames, (const Prim *)(d + off_prims), (const int64_t *)d,
-                                                        (const int64_t *)(d + off_side), H, W);
+                                                        (const int32_t *)(d + off_idx), (const int64_t *)(d + off_side), H, W);
     cudaError_t e = cudaGetLastError();
     if (device_ms) cudaEventRecord(e1, st);
     if (e == cudaSuccess && !on_device) cudaMemcpyAsync(frames, d_frames, frame_bytes, cudaMemcpyDeviceToHost, st);
@@ -340,18 +417,17 @@ int run_builder(Builder &b, uint8_t *frames, int on_device, int n, int device, c
     if (e == cudaSuccess && device_ms) cudaEventElapsedTime(device_ms, e0, e1);
     if (e0) { cudaEventDestroy(e0); cudaEventDestroy(e1); }
     if (!on_device) cudaFree(d_frames);
-    (void)host_ms;
     if (e != cudaSuccess) return fail(LANE_ERR_CUDA, cudaGetErrorString(e));
     return LANE_OK;
 }
 
-int prepare_device(int device, const char *who)
+int prepare_device(int device)
 {
     auto fail = [](int code, const char *msg) { lane_set_global_error(msg); return code; };
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
         return fail(LANE_ERR_NO_DEVICE, "no CUDA device visible: this library has no CPU fallback");
-    if (device < 0 || device >= ndev) { (void)who; return fail(LANE_ERR_INVALID, "lane_draw: device out of range"); }
+    if (device < 0 || device >= ndev) return fail(LANE_ERR_INVALID, "lane_draw: device out of range");
     if (cudaSetDevice(device) != cudaSuccess) return fail(LANE_ERR_CUDA, "cudaSetDevice failed");
     return LANE_OK;
 }
@@ -365,18 +441,13 @@ extern "C" int lane_draw_commands(uint8_t *frames, int on_device, int n, int hei
     if (!frames || !commands || !command_begin || n < 1 || height < 1 || width < 1)
         return fail(LANE_ERR_INVALID, "lane_draw_commands: bad arguments");
     if (height > 32767 || width > 32767) return fail(LANE_ERR_UNSUPPORTED, "lane_draw_commands: frame larger than 32767 px");
-    if (int rc = prepare_device(device, "lane_draw_commands")) return rc;
-    Builder b;
-    b.H = height; b.W = width;
-    b.begin.reserve(n + 1);
-    for (int f = 0; f < n; f++) {
-        b.begin.push_back((int64_t)b.prims.size());
+    for (int f = 0; f < n; f++)
         if (command_begin[f + 1] < command_begin[f]) return fail(LANE_ERR_INVALID, "lane_draw_commands: command_begin must not decrease");
-        const char *err = nullptr;
-        if (!parse_commands(b, commands + command_begin[f], command_begin[f + 1] - command_begin[f], &err)) return fail(LANE_ERR_INVALID, err);
-    }
-    b.begin.push_back((int64_t)b.prims.size());
-    return run_builder(b, frames, on_device, n, device, (cudaStream_t)cuda_stream, nullptr, device_ms);
+    if (int rc = prepare_device(device)) return rc;
+    return draw_driver(frames, on_device, n, height, width, device, (cudaStream_t)cuda_stream, device_ms,
+                       [&](Builder &b, int f, const char **err) {
+                           return parse_commands(b, commands + command_begin[f], command_begin[f + 1] - command_begin[f], err);
+                       });
 }
 
 extern "C" int lane_draw_lanes_batch(uint8_t *frames, int on_device, int n, int height, int width, const int32_t *left_points,
@@ -387,11 +458,11 @@ extern "C" int lane_draw_lanes_batch(uint8_t *frames, int on_device, int n, int 
     if (!frames || !left_points || !right_points || !left_valid || !right_valid || n < 1 || height < 1 || width < 1)
         return fail(LANE_ERR_INVALID, "lane_draw_lanes_batch: bad arguments");
     if (height > 32767 || width > 32767) return fail(LANE_ERR_UNSUPPORTED, "lane_draw_lanes_batch: frame larger than 32767 px");
-    if (int rc = prepare_device(device, "lane_draw_lanes_batch")) return rc;
-    Builder b;
-    b.H = height; b.W = width;
-    b.begin.reserve(n + 1);
-    build_draw_lanes(b, n, left_points, left_valid, right_points, right_valid, fill_lane);
-    b.begin.push_back((int64_t)b.prims.size());
-    return run_builder(b, frames, on_device, n, device, (cudaStream_t)cuda_stream, nullptr, device_ms);
+    if (int rc = prepare_device(device)) return rc;
+    return draw_driver(frames, on_device, n, height, width, device, (cudaStream_t)cuda_stream, device_ms,
+                       [&](Builder &b, int f, const char **) {
+                           build_draw_lanes_frame(b, left_points + (size_t)f * LANE_NUM_POINTS * 2, left_valid[f],
+                                                  right_points + (size_t)f * LANE_NUM_POINTS * 2, right_valid[f], fill_lane);
+                           return true;
+                       });
 }

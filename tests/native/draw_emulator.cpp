@@ -154,3 +154,17 @@ extern "C" int emu_draw_lanes(uint8_t *frames, int n, int H, int W, const int32_
     }
     return 0;
 }
+
+// host expansion only (no pixels): how long the cv2 -> primitive step takes per batch
+extern "C" int emu_build_only(int n, int H, int W, const int32_t *commands, const int64_t *begin, int64_t *n_prims)
+{
+    Builder b;
+    b.H = H; b.W = W;
+    for (int f = 0; f < n; f++) {
+        b.begin.push_back((int64_t)b.prims.size());
+        const char *err = nullptr;
+        if (!parse_commands(b, commands + begin[f], begin[f + 1] - begin[f], &err)) return -1;
+    }
+    if (n_prims) *n_prims = (int64_t)b.prims.size();
+    return 0;
+}

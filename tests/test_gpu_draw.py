@@ -22,7 +22,7 @@ def test_random_command_mixes_equal_cv2_on_the_device():
     rng = np.random.default_rng(10)
     for t in range(400):
         img, ref, dl = random_mix(rng, lambda: DrawList(1))
-        mine = np.ascontiguousarray(img[None])
+        mine = img.copy()[None]
         dl.execute(mine)
         assert np.array_equal(ref, mine[0]), t
 
@@ -82,7 +82,7 @@ def test_draw_lanes_and_offset_indicator_equal_the_reference_goldens():
     for seed in range(N_RANDOM):
         frame, pts, valid, off = random_case(seed)
         for fill, col in ((True, 0), (False, 1)):
-            mine = np.ascontiguousarray(frame[None])
+            mine = frame.copy()[None]
             draw_lanes_arrays(mine, pts[None, 0], valid[None, 0], pts[None, 1], valid[None, 1], fill)
             assert h16(mine[0]) == g["random_hash"][seed][col], (seed, fill)
             if fill:
