@@ -575,7 +575,8 @@ __global__ void __launch_bounds__(416, 2) k4_ppht_v3(const uint32_t *__restrict_
                            const uint32_t *__restrict__ pmask_all, uint32_t *__restrict__ pmask_work,
                            uint32_t *__restrict__ over_all,
                            const int2 *__restrict__ win, int cells_max, int G, int nvw, int tpa,
-                           int32_t *__restrict__ lines_all, int *__restrict__ n_lines, LaneGeom g, LaneHoughParams hp, int prof)
+                           int32_t *__restrict__ lines_all, int *__restrict__ n_lines, LaneGeom g, LaneHoughParams hp, int prof,
+                           const int *__restrict__ order)
 {
     extern __shared__ __align__(16) unsigned char dyn[];
     uint32_t *cells32 = reinterpret_cast<uint32_t *>(dyn);
@@ -599,7 +600,9 @@ __global__ void __launch_bounds__(416, 2) k4_ppht_v3(const uint32_t *__restrict_
     unsigned rank;
     asm("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
     const int NVT = nvw * 32;                      // voter threads
-    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, f = blockIdx.x / G;
+    // clusters start in launch order as earlier ones retire: handing out the frames with the most points first keeps the
+    // longest sequential loops off the tail of the launch (order = k4_order's permutation; results do not depend on it)
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, f = order ? order[blockIdx.x / G] : blockIdx.x / G;
     const bool producer = wid == nvw;
     const int slot = tid / tpa, sub = tid - slot * tpa;
     const int angle = slot * G + (int)rank;
@@ -1051,6 +1054,21 @@ __global__ void __launch_bounds__(416, 2) k4_ppht_v3(const uint32_t *__restrict_
     asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 
+// order[k] = index of the frame with the k-th largest point count (ties by index): longest-processing-time-first for the
+// frame-per-cluster kernels.  n is a batch (hundreds of frames): a rank sort.
+__global__ void k4_order(const int *__restrict__ n_points, int *__restrict__ order, int n)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int mine = n_points[i];
+    int rank = 0;
+    for (int j = 0; j < n; j++) {
+        const int o = __ldg(&n_points[j]);
+        rank += (o > mine) || (o == mine && j < i);
+    }
+    order[rank] = i;
+}
+
 }  // namespace
 
 void launch_ppht_v2(uint32_t *points, const int *n_points, uint32_t *pmask, uint32_t *accum16, const int2 *win,
@@ -1066,9 +1084,13 @@ void launch_ppht_v2(uint32_t *points, const int *n_points, uint32_t *pmask, uint
 // v3 launch: false if the geometry does not fit (caller uses v2)
 bool launch_ppht_v3(const uint32_t *points, const int *n_points, const uint32_t *pmask, uint32_t *pmask_work,
                     uint32_t *list_over, const int2 *win3, int cells_max, int G, int32_t *lines, int *n_lines, LaneGeom g,
-                    LaneHoughParams hp, int n, cudaStream_t st, int *launches)
+                    LaneHoughParams hp, int n, cudaStream_t st, int *launches, int *order)
 {
     if (G < 1 || (g.bh * ((g.W + 31) / 32)) % 4 != 0 || ((uintptr_t)pmask % 16) != 0) return false;
+    if (order) {
+        k4_order<<<(n + 255) / 256, 256, 0, st>>>(n_points, order, n);
+        *launches += 1;
+    }
     const int angles = (LANE_NUM_ANGLES + G - 1) / G;
     int tpa = 384 / angles;                      // aim at ~12 voter warps per CTA
     tpa = tpa < 1 ? 1 : (tpa > 8 ? 8 : tpa);
@@ -1091,7 +1113,7 @@ bool launch_ppht_v3(const uint32_t *points, const int *n_points, const uint32_t 
     cfg.attrs = attr;
     cfg.numAttrs = 1;
     cudaError_t e = cudaLaunchKernelEx(&cfg, k4_ppht_v3, points, n_points, pmask, pmask_work, list_over, win3, cells_max, G, nvw, tpa,
-                                       lines, n_lines, g, hp, getenv("LANE_B200_PPHT_PROF") ? 1 : 0);
+                                       lines, n_lines, g, hp, getenv("LANE_B200_PPHT_PROF") ? 1 : 0, (const int *)order);
     if (e != cudaSuccess) { cudaGetLastError(); return false; }
     *launches += 1;
     return true;

@@ -69,6 +69,8 @@ struct lane_ctx {
     int2 *d_win = nullptr;            // [180] (rmin, first cell) per angle
     int cells_per_frame = 0;
     int ppht_v1 = 0, ppht_v2 = 0;     // LANE_B200_K4=v1|v2 pins an older PPHT kernel (A/B checks)
+    int k4_lpt = 1;                   // frames with the most points first (LANE_B200_K4_ORDER=0: launch order, A/B)
+    int *d_order = nullptr;
     int2 *d_win3 = nullptr;           // v3 layout: (rmin, first cell inside the owning CTA)
     uint32_t *d_pmask_work = nullptr; // [B][G3][bh][WW] private mask copies of the v3 cluster CTAs
     uint32_t *d_list_over = nullptr;  // [B][G3][over_cap] private extensions of the v3 point list (ROIs with many pixels)
@@ -148,7 +150,7 @@ void free_all(lane_ctx *c)
                     c->d_points, c->d_points_dbg, c->d_lut, c->d_thr, c->d_seedsA, c->d_seedsB, c->d_seed_count,
                     c->d_n_edges, c->d_n_points, c->d_rounds, c->d_n_lines, c->d_accum, c->d_lines, c->fit.raw, c->fit.big,
                     c->fit.side_n, c->fit.side_flags, c->d_stream_id, c->d_prev_fit, c->d_prev_valid,
-                    c->slots[0].d_records, c->slots[1].d_records, c->d_std_accum, c->d_hb_accum, c->d_hb_sorted, c->d_hb_tmp, c->d_hb_count, c->d_peaks, c->d_n_peaks, c->d_task_counter};
+                    c->slots[0].d_records, c->slots[1].d_records, c->d_std_accum, c->d_hb_accum, c->d_hb_sorted, c->d_hb_tmp, c->d_hb_count, c->d_peaks, c->d_n_peaks, c->d_task_counter, c->d_order};
     for (void *p : ptrs)
         if (p) cudaFree(p);
     free(c->h_roi);
@@ -338,7 +340,8 @@ int run_stages(lane_ctx *c, const uint8_t *frames_dev, int off, int m, const int
         // up the frames v3 flagged (point list larger than its shared-memory list), or runs alone if v3 cannot launch.
         bool v3 = !c->ppht_v2 && c->G3 > 0 &&
                   launch_ppht_v3(points, n_points, pmask_bits, c->d_pmask_work + o * c->G3 * std::max(g.bh, 1) * WW,
-                                 c->d_list_over ? c->d_list_over + o * c->G3 * lane_ppht_over_cap_v3() : nullptr, c->d_win3, c->cells_max3, c->G3, lines, n_lines, g, c->hp, m, c->st, &L[LANE_STAGE_PPHT]);
+                                 c->d_list_over ? c->d_list_over + o * c->G3 * lane_ppht_over_cap_v3() : nullptr, c->d_win3, c->cells_max3, c->G3, lines, n_lines, g, c->hp, m, c->st, &L[LANE_STAGE_PPHT],
+                                 c->k4_lpt ? c->d_order + o : nullptr);
         launch_ppht_v2(points, n_points, pmask_bits, c->d_accum16 + o * (c->cells_per_frame / 2), c->d_win,
                        c->cells_per_frame, lines, n_lines, g, c->hp, m, c->st, &L[LANE_STAGE_PPHT], v3 ? 1 : 0);
         if (v3) c->last_paths |= LANE_PATH_PPHT_DSMEM;
@@ -539,6 +542,7 @@ int lane_ctx_create(int device, int height, int width, int max_batch, int max_se
     CUB(dalloc(&ctx->d_n_points, B));
     CUB(dalloc(&ctx->d_rounds, B));
     CUB(dalloc(&ctx->d_n_lines, B));
+    CUB(dalloc(&ctx->d_order, B));
     CUB(dalloc(&ctx->d_win, LANE_NUM_ANGLES));
     CUB(dalloc(&ctx->d_win3, LANE_NUM_ANGLES));
     CUB(dalloc(&ctx->d_lines, B * g.max_segments * 4));
@@ -560,6 +564,8 @@ int lane_ctx_create(int device, int height, int width, int max_batch, int max_se
         e = getenv("LANE_B200_K4");
         ctx->ppht_v1 = e && !strcmp(e, "v1");
         ctx->ppht_v2 = e && !strcmp(e, "v2");
+        const char *ord = getenv("LANE_B200_K4_ORDER");
+        ctx->k4_lpt = !(ord && !strcmp(ord, "0"));
         e = getenv("LANE_B200_K2");
         ctx->force_generic_k2 = e && !strcmp(e, "generic");
     }
