@@ -36,6 +36,13 @@ struct lane_ctx {
     bool own_stream = true;
     int blur = 1;                     // 0: Canny runs on the plain grayscale plane (lane_set_preprocess)
     cudaStream_t st = nullptr, copy_st = nullptr;   // compute stream; H2D stream for chunked host batches
+    // Second compute stream for the back half of the path (PPHT + fit + record copies) of device-resident batches: the
+    // PPHT kernel runs in waves of whole frames (71 clusters at 1080p) and its last wave leaves 40 % of the SMs idle for a
+    // frame's latency; with the edge kernels of the NEXT queued batch on the first stream those SMs are used.  The buffers
+    // that cross from the edge half to the back half are kept per result slot (see `two`).
+    cudaStream_t st2 = nullptr;
+    cudaEvent_t edge_done[2] = {};
+    bool overlap_ok = true, overlap_now = false;    // LANE_B200_OVERLAP=0: one stream (A/B)
     cudaEvent_t copy_ev[LANE_COPY_EVENTS] = {}, start_ev = nullptr;
     std::string err;
 
@@ -174,6 +181,8 @@ void free_all(lane_ctx *c)
         if (e) cudaEventDestroy(e);
     if (c->copy_st) cudaStreamDestroy(c->copy_st);
     if (c->own_stream && c->st) cudaStreamDestroy(c->st);
+    if (c->st2) cudaStreamDestroy(c->st2);
+    for (auto &e : c->edge_done) if (e) cudaEventDestroy(e);
 }
 
 int ensure_streams(lane_ctx *c, int S)
@@ -246,10 +255,13 @@ int run_stages(lane_ctx *c, const uint8_t *frames_dev, int off, int m, const int
     int rc;
     const uint8_t *fr = frames_dev + o * P * 3;
     uint32_t *hist = c->d_hist + o * 256;
-    int4 *thr = c->d_thr + o;
-    int *n_edges = c->d_n_edges + o, *n_points = c->d_n_points + o, *rounds = c->d_rounds + o, *n_lines = c->d_n_lines + o;
-    uint32_t *points = c->d_points + o * g.max_points;
-    uint32_t *pmask_bits = c->d_pmask_bits + o * std::max(g.bh, 1) * WW;
+    // what the edge half hands to the back half lives in the batch's result slot: the edge kernels of the next batch may
+    // already be writing while PPHT / fit of this one still read
+    const size_t two = o + (size_t)c->cur * c->max_batch;
+    int4 *thr = c->d_thr + two;
+    int *n_edges = c->d_n_edges + two, *n_points = c->d_n_points + two, *rounds = c->d_rounds + two, *n_lines = c->d_n_lines + o;
+    uint32_t *points = c->d_points + two * g.max_points;
+    uint32_t *pmask_bits = c->d_pmask_bits + two * std::max(g.bh, 1) * WW;
     uint32_t *edge_bits = c->d_edge_bits + o * planes, *cb = c->d_dbg_c + o * planes, *sb = c->d_dbg_s + o * planes;
     int32_t *lines = c->d_lines + o * g.max_segments * 4;
 
@@ -331,19 +343,25 @@ int run_stages(lane_ctx *c, const uint8_t *frames_dev, int off, int m, const int
 
     rc = stage_check(c, "canny / compaction"); if (rc) return rc;
     if (timed) { rc = mark(c, LANE_STAGE_PPHT); if (rc) return rc; }
+    cudaStream_t hs = c->st;                       // stream of the back half
+    if (c->overlap_now) {
+        hs = c->st2;
+        CU(cudaEventRecord(c->edge_done[c->cur], c->st));
+        CU(cudaStreamWaitEvent(hs, c->edge_done[c->cur], 0));
+    }
     if (c->ppht_v1) {
         if (!c->d_accum) CU(dalloc(&c->d_accum, (size_t)c->max_batch * LANE_NUM_ANGLES * g.numrho));
         launch_ppht(points, n_points, pmask_bits, c->d_accum + o * LANE_NUM_ANGLES * g.numrho, lines, n_lines, g, c->hp, m,
-                    c->st, &L[LANE_STAGE_PPHT]);
+                    hs, &L[LANE_STAGE_PPHT]);
     } else {
         // v3 (cells in distributed shared memory) takes every frame it can; v2 (global 16-bit cells) then sweeps
         // up the frames v3 flagged (point list larger than its shared-memory list), or runs alone if v3 cannot launch.
         bool v3 = !c->ppht_v2 && c->G3 > 0 &&
                   launch_ppht_v3(points, n_points, pmask_bits, c->d_pmask_work + o * c->G3 * std::max(g.bh, 1) * WW,
-                                 c->d_list_over ? c->d_list_over + o * c->G3 * lane_ppht_over_cap_v3() : nullptr, c->d_win3, c->cells_max3, c->G3, lines, n_lines, g, c->hp, m, c->st, &L[LANE_STAGE_PPHT],
+                                 c->d_list_over ? c->d_list_over + o * c->G3 * lane_ppht_over_cap_v3() : nullptr, c->d_win3, c->cells_max3, c->G3, lines, n_lines, g, c->hp, m, hs, &L[LANE_STAGE_PPHT],
                                  c->k4_lpt ? c->d_order + o : nullptr);
         launch_ppht_v2(points, n_points, pmask_bits, c->d_accum16 + o * (c->cells_per_frame / 2), c->d_win,
-                       c->cells_per_frame, lines, n_lines, g, c->hp, m, c->st, &L[LANE_STAGE_PPHT], v3 ? 1 : 0);
+                       c->cells_per_frame, lines, n_lines, g, c->hp, m, hs, &L[LANE_STAGE_PPHT], v3 ? 1 : 0);
         if (v3) c->last_paths |= LANE_PATH_PPHT_DSMEM;
     }
 
@@ -352,7 +370,7 @@ int run_stages(lane_ctx *c, const uint8_t *frames_dev, int off, int m, const int
     LaneFitScratch fs{c->fit.raw + o * 6, c->fit.side_n + o * 2, c->fit.side_flags + o,
                       c->fit.big ? c->fit.big + o * 2 * 5 * 2 * (size_t)g.max_segments : nullptr};
     launch_fit(lines, n_lines, fs, stream_id_dev ? stream_id_dev + o : nullptr, S, c->d_prev_fit, c->d_prev_valid, c->smooth,
-               c->one_minus_smooth, thr, n_edges, n_points, rounds, c->slots[c->cur].d_records + o, g, m, c->st, &L[LANE_STAGE_FIT]);
+               c->one_minus_smooth, thr, n_edges, n_points, rounds, c->slots[c->cur].d_records + o, g, m, hs, &L[LANE_STAGE_FIT]);
     return stage_check(c, "fit");
 }
 
@@ -364,12 +382,21 @@ int enqueue(lane_ctx *c, const uint8_t *frames, bool on_device, int n, const int
 {
     int rc = LANE_OK;
     lane_ctx::slot_t &sl = c->slots[c->cur];
-    if (stream_id) CU(cudaMemcpyAsync(c->d_stream_id, stream_id, sizeof(int) * n, cudaMemcpyHostToDevice, c->st));
+    // back half on its own stream: device-resident batches outside profiling / debug mode (stage events and taps assume
+    // one stream).  Everything only the back half touches (stream ids, EMA state, records) is ordered on that stream.
+    const bool was_overlap = c->overlap_now;
+    c->overlap_now = c->overlap_ok && on_device && !c->profiling && !c->debug && c->st2 != nullptr;
+    if (was_overlap != c->overlap_now && c->q_count) {       // mode change with a batch in flight: order the two streams once
+        CU(cudaEventRecord(c->edge_done[c->cur ^ 1], was_overlap ? c->st2 : c->st));
+        CU(cudaStreamWaitEvent(was_overlap ? c->st : c->st2, c->edge_done[c->cur ^ 1], 0));
+    }
+    cudaStream_t hs = c->overlap_now ? c->st2 : c->st;
+    if (stream_id) CU(cudaMemcpyAsync(c->d_stream_id, stream_id, sizeof(int) * n, cudaMemcpyHostToDevice, hs));
     if (prev_fit) {                                  // explicit state: the caller's; otherwise what the last batch left on the device
         memcpy(sl.h_prev_fit, prev_fit, sizeof(double) * S * 6);
         memcpy(sl.h_prev_valid, prev_valid, (size_t)S * 2);
-        CU(cudaMemcpyAsync(c->d_prev_fit, sl.h_prev_fit, sizeof(double) * S * 6, cudaMemcpyHostToDevice, c->st));
-        CU(cudaMemcpyAsync(c->d_prev_valid, sl.h_prev_valid, (size_t)S * 2, cudaMemcpyHostToDevice, c->st));
+        CU(cudaMemcpyAsync(c->d_prev_fit, sl.h_prev_fit, sizeof(double) * S * 6, cudaMemcpyHostToDevice, hs));
+        CU(cudaMemcpyAsync(c->d_prev_valid, sl.h_prev_valid, (size_t)S * 2, cudaMemcpyHostToDevice, hs));
     }
     const int32_t *sid = stream_id ? c->d_stream_id : nullptr;
     const uint8_t *frames_dev = frames;
@@ -443,13 +470,13 @@ int enqueue(lane_ctx *c, const uint8_t *frames, bool on_device, int n, const int
         }
     }
     rc = mark(c, LANE_STAGE_D2H); if (rc) return rc;
-    CU(cudaMemcpyAsync(sl.h_records, sl.d_records, sizeof(lane_record) * n, cudaMemcpyDeviceToHost, c->st));
-    CU(cudaMemcpyAsync(sl.h_prev_fit, c->d_prev_fit, sizeof(double) * S * 6, cudaMemcpyDeviceToHost, c->st));
-    CU(cudaMemcpyAsync(sl.h_prev_valid, c->d_prev_valid, (size_t)S * 2, cudaMemcpyDeviceToHost, c->st));
+    CU(cudaMemcpyAsync(sl.h_records, sl.d_records, sizeof(lane_record) * n, cudaMemcpyDeviceToHost, hs));
+    CU(cudaMemcpyAsync(sl.h_prev_fit, c->d_prev_fit, sizeof(double) * S * 6, cudaMemcpyDeviceToHost, hs));
+    CU(cudaMemcpyAsync(sl.h_prev_valid, c->d_prev_valid, (size_t)S * 2, cudaMemcpyDeviceToHost, hs));
     rc = mark(c, LANE_NUM_STAGES); if (rc) return rc;
     CU(cudaGetLastError());
     c->last_frames_dev = frames_dev;
-    CU(cudaEventRecord(sl.done, c->st));
+    CU(cudaEventRecord(sl.done, hs));
     sl.n = n;
     sl.S = S;
     sl.timed = c->profiling && on_device;
@@ -526,6 +553,14 @@ int lane_ctx_create(int device, int height, int width, int max_batch, int max_se
         }                                                                                               \
     } while (0)
     CUB(cudaStreamCreateWithFlags(&ctx->st, cudaStreamNonBlocking));
+    {
+        int lo = 0, hi = 0;                          // the back half first: its clusters keep their slots, the edge kernels fill in
+        cudaDeviceGetStreamPriorityRange(&lo, &hi);
+        CUB(cudaStreamCreateWithPriority(&ctx->st2, cudaStreamNonBlocking, hi));
+        for (auto &e : ctx->edge_done) CUB(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        const char *ov = getenv("LANE_B200_OVERLAP");
+        ctx->overlap_ok = !(ov && !strcmp(ov, "0"));
+    }
     for (auto &sl : ctx->slots) {
         for (auto &e : sl.ev) CUB(cudaEventCreate(&e));
         CUB(cudaEventCreateWithFlags(&sl.done, cudaEventDisableTiming));
@@ -537,10 +572,10 @@ int lane_ctx_create(int device, int height, int width, int max_batch, int max_se
     CUB(dalloc(&ctx->d_dbg_s, B * height * WW));
     CUB(dalloc(&ctx->d_hist, B * 256));
     CUB(dalloc(&ctx->d_lut, 1022));
-    CUB(dalloc(&ctx->d_thr, B));
-    CUB(dalloc(&ctx->d_n_edges, B));
-    CUB(dalloc(&ctx->d_n_points, B));
-    CUB(dalloc(&ctx->d_rounds, B));
+    CUB(dalloc(&ctx->d_thr, 2 * B));
+    CUB(dalloc(&ctx->d_n_edges, 2 * B));
+    CUB(dalloc(&ctx->d_n_points, 2 * B));
+    CUB(dalloc(&ctx->d_rounds, 2 * B));
     CUB(dalloc(&ctx->d_n_lines, B));
     CUB(dalloc(&ctx->d_order, B));
     CUB(dalloc(&ctx->d_win, LANE_NUM_ANGLES));
@@ -654,8 +689,8 @@ int lane_set_roi_mask(lane_ctx *c, const uint8_t *mask)
                 CU(dalloc(&c->d_list_over, (size_t)c->max_batch * c->G3 * lane_ppht_over_cap_v3()));
         }
     }
-    CU(dalloc(&c->d_pmask_bits, (size_t)c->max_batch * std::max(g.bh, 1) * WW));
-    CU(dalloc(&c->d_points, (size_t)c->max_batch * g.max_points));
+    CU(dalloc(&c->d_pmask_bits, 2 * (size_t)c->max_batch * std::max(g.bh, 1) * WW));      // per result slot
+    CU(dalloc(&c->d_points, 2 * (size_t)c->max_batch * g.max_points));
     if (c->debug) CU(dalloc(&c->d_points_dbg, (size_t)c->max_batch * g.max_points));
     c->have_roi = true;
     return LANE_OK;
@@ -894,7 +929,7 @@ int lane_hough_accumulator(lane_ctx *c, int fi, int32_t *accum_host, int thresho
     const LaneGeom &g = c->g;
     const size_t cells = (size_t)(LANE_NUM_ANGLES + 2) * (g.numrho + 2);
     if (!c->d_std_accum) CU(dalloc(&c->d_std_accum, cells));
-    launch_hough_accum(c->d_points_dbg + (size_t)fi * g.max_points, c->d_n_points + fi, c->d_std_accum, g, c->st);
+    launch_hough_accum(c->d_points_dbg + (size_t)fi * g.max_points, c->d_n_points + (size_t)c->cur * c->max_batch + fi, c->d_std_accum, g, c->st);
     CU(cudaGetLastError());
     if (accum_host) CU(cudaMemcpyAsync(accum_host, c->d_std_accum, sizeof(int32_t) * cells, cudaMemcpyDeviceToHost, c->st));
     int found = 0;
