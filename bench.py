@@ -141,6 +141,52 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+class NvmlSampler:
+    """SM clock and clock-event reasons straight from NVML every ~2 ms (nvidia-smi's loop cannot go below ~20 ms, which is
+    as long as the whole timed region): the samples that fall inside the timed region itself."""
+
+    def __init__(self, index):
+        self.samples, self.stop_flag, self.ok = [], False, False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_sm = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+            self.thread = threading.Thread(target=self._loop, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.ok = False
+
+    def _loop(self):
+        nv = self.nv
+        while not self.stop_flag:
+            try:
+                t = time.perf_counter()
+                sm = nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)
+                rs = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                self.samples.append((t, sm, rs))
+            except Exception:
+                pass
+            time.sleep(0.002)
+
+    def window(self, t0, t1):
+        self.stop_flag = True
+        if not self.ok:
+            return None
+        nv = self.nv
+        rows = [(sm, rs) for (t, sm, rs) in self.samples if t0 <= t <= t1]
+        names = {"hw_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8),
+                 "hw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40),
+                 "sw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20),
+                 "sw_power_cap": getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4)}
+        reasons = sorted(k for k, bit in names.items() if any(rs & bit for _, rs in rows))
+        return {"samples": len(rows), "sm_mhz": float(np.median([sm for sm, _ in rows])) if rows else None,
+                "sm_min_mhz": min((sm for sm, _ in rows), default=None), "sm_max_mhz": self.max_sm, "reasons": reasons,
+                "source": "NVML polled every ~2 ms"}
+
+
 # ------------------------------------------------------------------------------------ main
 def main():
     ap = argparse.ArgumentParser()
@@ -276,14 +322,11 @@ def main():
             state["last_recs"] = recs
             if on_collect:
                 on_collect()
-            ev = None
             if gatherer is not None:
                 state["last_bufs"] = gatherer.gather_device(ctx.records_device_ptr(), to_host=False)
-                ev = torch.cuda.Event()
-                ev.record(torch.cuda.current_stream(dev))
+                # only the fit kernel that next writes this result slot waits for the collective (not the edge kernels)
+                ctx.fence_records(torch.cuda.current_stream(dev).cuda_stream)
             if issued < total:
-                if ev is not None:
-                    stream.wait_event(ev)                    # the slot's records are still being read by the collective
                 enqueue_next(); issued += 1
         if gatherer is not None:
             stream.wait_stream(torch.cuda.current_stream(dev))   # timing events on the context's stream see the gathers
@@ -295,6 +338,7 @@ def main():
         torch.cuda.synchronize()
 
     sampler = ClockSampler(local) if rank == 0 else None
+    nvml_sampler = NvmlSampler(local) if rank == 0 else None
     t_load0 = time.perf_counter()
     run_batches(max(args.warmup, 3) * S)
     found = int(state["last_recs"]["side"]["valid"].sum())
@@ -443,6 +487,8 @@ def main():
         clocks = sampler.stop(t_load0, time.perf_counter())
         clocks["window"] = "warm-up + timed region + e2e legs"
         clocks["samples_in_timed_region"] = sum(1 for (t, _) in sampler.lines if timed_window[0] <= t <= timed_window[1])
+        if nvml_sampler is not None:
+            clocks["timed_region"] = nvml_sampler.window(*timed_window)
 
     if rank == 0:
         peaks = {}

@@ -138,9 +138,14 @@ LANE_API int lane_detect_collect(lane_ctx *ctx, double *prev_fit, uint8_t *prev_
 LANE_API void *lane_ctx_stream(lane_ctx *ctx);
 /* Device copy of the records lane_detect_collect / lane_detect_batch returned last (lane_record[n]).  It stays valid
  * until the batch AFTER the next one is enqueued (two result slots alternate), so a multi-GPU caller can hand it to
- * NCCL without a host round trip (the path's only collective is the gather of these records); the
- * context's stream must be made to wait for that read before the slot's next enqueue. */
+ * NCCL without a host round trip (the path's only collective is the gather of these records); the slot's next
+ * writer must be ordered behind that read: lane_ctx_fence_records. */
 LANE_API const lane_record *lane_ctx_records_device(lane_ctx *ctx);
+/* Tell the context that work already enqueued on `reader_stream` (a cudaStream_t: the collective that gathers the records
+ * of the batch collected last) reads lane_ctx_records_device: only the kernel that next WRITES that result slot
+ * (the fit of the batch after next) waits for it -- the edge kernels of the following batches do not.  Call it right after
+ * enqueuing the reader. */
+LANE_API int lane_ctx_fence_records(lane_ctx *ctx, void *reader_stream);
 /* Use a caller-owned stream (cudaStream_t) instead of the context's own. */
 LANE_API int lane_ctx_set_stream(lane_ctx *ctx, void *cuda_stream);
 

@@ -90,6 +90,7 @@ _PROTOS = {
     "lane_ctx_stream": (C.c_void_p, [C.c_void_p]),
     "lane_ctx_set_stream": (C.c_int, [C.c_void_p, C.c_void_p]),
     "lane_ctx_records_device": (C.c_void_p, [C.c_void_p]),
+    "lane_ctx_fence_records": (C.c_int, [C.c_void_p, C.c_void_p]),
     "lane_ctx_last_paths": (C.c_int, [C.c_void_p]),
     "lane_set_profiling": (C.c_int, [C.c_void_p, C.c_int]),
     "lane_get_stage_ms": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
@@ -223,6 +224,11 @@ class LaneContext:
     def records_device_ptr(self) -> int:
         """Device address of the records of the batch enqueued last (see lane_ctx_records_device)."""
         return int(lib().lane_ctx_records_device(self._h) or 0)
+
+    def fence_records(self, reader_stream: int):
+        """Work already enqueued on ``reader_stream`` (a cudaStream_t value) reads ``records_device_ptr()`` of the batch
+        collected last; the kernel that next writes that result slot waits for it (see lane_ctx_fence_records)."""
+        self._check(lib().lane_ctx_fence_records(self._h, C.c_void_p(reader_stream)))
 
     # ---- hot path
     def detect(self, frames, n: int, on_device: bool, stream_id, n_streams: int, prev_fit: np.ndarray,

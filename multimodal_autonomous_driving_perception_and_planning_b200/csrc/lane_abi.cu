@@ -110,6 +110,8 @@ struct lane_ctx {
         uint8_t *h_prev_valid = nullptr;
         cudaEvent_t ev[LANE_NUM_STAGES + 1] = {};
         cudaEvent_t done = nullptr;
+        cudaEvent_t reader_done = nullptr;           // lane_ctx_fence_records: an outside reader of d_records ends here
+        bool has_reader = false;
         int n = 0, S = 0;
         bool timed = false;
         int32_t launches[LANE_NUM_STAGES] = {};
@@ -168,6 +170,7 @@ void free_all(lane_ctx *c)
         for (auto &e : sl.ev)
             if (e) cudaEventDestroy(e);
         if (sl.done) cudaEventDestroy(sl.done);
+        if (sl.reader_done) cudaEventDestroy(sl.reader_done);
     }
     for (auto &e : c->copy_ev)
         if (e) cudaEventDestroy(e);
@@ -367,6 +370,10 @@ int run_stages(lane_ctx *c, const uint8_t *frames_dev, int off, int m, const int
 
     rc = stage_check(c, "ppht"); if (rc) return rc;
     if (timed) { rc = mark(c, LANE_STAGE_FIT); if (rc) return rc; }
+    if (c->slots[c->cur].has_reader) {             // an outside reader (the NCCL gather) may still be on this slot's records
+        CU(cudaStreamWaitEvent(hs, c->slots[c->cur].reader_done, 0));
+        c->slots[c->cur].has_reader = false;
+    }
     LaneFitScratch fs{c->fit.raw + o * 6, c->fit.side_n + o * 2, c->fit.side_flags + o,
                       c->fit.big ? c->fit.big + o * 2 * 5 * 2 * (size_t)g.max_segments : nullptr};
     launch_fit(lines, n_lines, fs, stream_id_dev ? stream_id_dev + o : nullptr, S, c->d_prev_fit, c->d_prev_valid, c->smooth,
@@ -564,6 +571,7 @@ int lane_ctx_create(int device, int height, int width, int max_batch, int max_se
     for (auto &sl : ctx->slots) {
         for (auto &e : sl.ev) CUB(cudaEventCreate(&e));
         CUB(cudaEventCreateWithFlags(&sl.done, cudaEventDisableTiming));
+        CUB(cudaEventCreateWithFlags(&sl.reader_done, cudaEventDisableTiming));
     }
     const size_t WW = (width + 31) / 32;
     CUB(dalloc(&ctx->d_roi_bits, (size_t)height * WW));
@@ -757,6 +765,16 @@ void *lane_ctx_stream(lane_ctx *c) { return c ? (void *)c->st : nullptr; }
 int lane_ctx_last_paths(lane_ctx *c) { return c ? c->last_paths : 0; }
 
 const lane_record *lane_ctx_records_device(lane_ctx *c) { return c ? c->slots[c->last_collected].d_records : nullptr; }
+
+int lane_ctx_fence_records(lane_ctx *c, void *reader_stream)
+{
+    if (!c) return LANE_ERR_INVALID;
+    CU(cudaSetDevice(c->device));
+    lane_ctx::slot_t &sl = c->slots[c->last_collected];
+    CU(cudaEventRecord(sl.reader_done, (cudaStream_t)reader_stream));
+    sl.has_reader = true;
+    return LANE_OK;
+}
 
 int lane_ctx_set_stream(lane_ctx *c, void *cuda_stream)
 {
