@@ -279,6 +279,13 @@ LANE_API int lane_frame_stats(const uint8_t *frames, int on_device, int n, int h
 LANE_API int lane_draw_commands(uint8_t *frames, int on_device, int n, int height, int width, const int32_t *commands,
                                 const int64_t *command_begin, int device, void *cuda_stream, float *device_ms);
 
+/* SyntheticDataGenerator.generate_frame_with_vehicles (the reference's data/generators/__pycache__/synthetic_data.cpython-312.pyc,
+ * SURVEY.md Appendix B) for frame_count = frame_count0 .. frame_count0 + n - 1: the scene (sky gradient, ground, road triangle,
+ * lane dashes, trees, 2-4 vehicles drawn from NumPy's legacy RandomState(frame_count % 100)) is laid out by the library's host
+ * code and rasterised by the same kernel; frames are overwritten (zeroed first), bit-identical to the Python / cv2 generator. */
+LANE_API int lane_generate_frames(uint8_t *frames, int on_device, int n, int height, int width, int64_t frame_count0,
+                                  int device, void *cuda_stream, float *device_ms);
+
 /* LaneDetector.draw_lanes (lane_detector.py:220-251) for a batch: the lane area between the two 50-point polylines
  * filled with (0, 255, 100) at weight 0.3 (only when fill_lane and both sides are valid), then the left polyline in
  * (255, 0, 0) and the right one in (0, 0, 255), thickness 3.

@@ -527,5 +527,120 @@ inline void build_draw_lanes(Builder &b, int n, const int32_t *left_points, cons
         build_draw_lanes_frame(b, left_points + (size_t)f * 100, left_valid[f], right_points + (size_t)f * 100, right_valid[f], fill_lane);
     }
 }
+// ---- the synthetic generator's scene (reference: data/generators/__pycache__/synthetic_data.cpython-312.pyc, SURVEY.md
+// Appendix B; Python form: generators/synthetic_data.py) -----------------------------------------------------------------
+// NumPy's legacy RandomState(seed) as the generator uses it: MT19937 seeded by init_genrand, randint by masked rejection on
+// 32-bit draws, uniform = low + (high - low) * the 53-bit double of two draws, choice(seq) = randint(0, len(seq)).
+struct LegacyRandomState {
+    uint32_t mt[624];
+    int idx = 624;
+    explicit LegacyRandomState(uint32_t seed)
+    {
+        mt[0] = seed;
+        for (int i = 1; i < 624; i++) mt[i] = 1812433253u * (mt[i - 1] ^ (mt[i - 1] >> 30)) + (uint32_t)i;
+    }
+    uint32_t next32()
+    {
+        if (idx >= 624) {
+            for (int k = 0; k < 624; k++) {
+                const uint32_t y = (mt[k] & 0x80000000u) | (mt[(k + 1) % 624] & 0x7fffffffu);
+                mt[k] = mt[(k + 397) % 624] ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
+            }
+            idx = 0;
+        }
+        uint32_t y = mt[idx++];
+        y ^= y >> 11;
+        y ^= (y << 7) & 0x9d2c5680u;
+        y ^= (y << 15) & 0xefc60000u;
+        y ^= y >> 18;
+        return y;
+    }
+    double next_double()
+    {
+        const uint32_t a = next32() >> 5, b = next32() >> 6;
+        return ((double)a * 67108864.0 + (double)b) / 9007199254740992.0;
+    }
+    int64_t randint(int64_t low, int64_t high)      // [low, high)
+    {
+        const uint32_t rng = (uint32_t)(high - 1 - low);
+        if (rng == 0) return low;
+        uint32_t mask = rng;
+        mask |= mask >> 1; mask |= mask >> 2; mask |= mask >> 4; mask |= mask >> 8; mask |= mask >> 16;
+        uint32_t v;
+        do { v = next32() & mask; } while (v > rng);
+        return low + (int64_t)v;
+    }
+    double uniform(double low, double high) { return low + (high - low) * next_double(); }
+};
+
+// One frame of SyntheticDataGenerator.generate_frame_with_vehicles at `frame_count`, on a zeroed image
+inline void build_generator_frame(Builder &b, int64_t frame_count)
+{
+    const int w = b.W, h = b.H, half = h / 2;
+    auto color = [](int c0, int c1, int c2) { return (uint32_t)(c0 | c1 << 8 | c2 << 16); };
+    auto line = [&](int64_t x1, int64_t y1, int64_t x2, int64_t y2, uint32_t c, int th) { b.thick_line(Pt{x1, y1}, Pt{x2, y2}, c, th, 3); };
+    // sky gradient: cv2.line((0, y), (w, y), (int(200 - 80 r), int(180 - 60 r), int(255 - 55 r)), 1), r = y / half
+    if (half > 0) {
+        std::vector<int32_t> sky(half);
+        for (int y = 0; y < half; y++) {
+            const double r = (double)y / (double)half;
+            sky[y] = (int32_t)color((int)(200 - 80 * r), (int)(180 - 60 * r), (int)(255 - 55 * r));
+        }
+        b.rows(0, half, 0, w, sky.data());
+    }
+    b.rectangle(Pt{0, half}, Pt{w, h}, color(60, 60, 60), -1);
+    const int64_t vp_x = w / 2 + (int64_t)(20 * sin((double)frame_count * 0.02)), vp_y = half;
+    const Pt road[3] = {{vp_x, vp_y}, {50, h}, {w - 50, h}};
+    b.fill_poly(road, 3, color(80, 80, 80));
+    // lane markings
+    const int n = 10;
+    const int64_t scroll = (h / n) > 0 ? (frame_count * 5) % (h / n) : 0;
+    auto row = [&](double t) { return std::min<int64_t>((int64_t)((double)vp_y + (double)(h - vp_y) * t) + scroll, h); };
+    for (int i = 0; i < n; i++) {
+        const int64_t ya = row((double)i / n), yb = row(((double)i + 0.5) / n);
+        if (ya >= vp_y && yb >= vp_y) line(vp_x, ya, vp_x, yb, color(255, 255, 200), 2);
+    }
+    for (int side = -1; side <= 1; side += 2) {
+        const double spread = side * 150;
+        for (int i = 0; i < n; i++) {
+            const double t1 = (double)i / n, t2 = ((double)i + 0.6) / n;
+            line((int64_t)((double)vp_x + spread * t1), row(t1), (int64_t)((double)vp_x + spread * t2), row(t2), color(255, 255, 255), 2);
+        }
+    }
+    // environment: trees
+    for (int i = 0; i < 5; i++) {
+        const double t = ((double)i + 0.5) / 5;
+        const int64_t base = (int64_t)((double)half + (double)(h - half) * t * 0.8);
+        const int64_t inset = (int64_t)(30 + 50 * t), tall = (int64_t)(30 + 40 * t);
+        for (int k = 0; k < 2; k++) {
+            const int64_t x = k == 0 ? inset : w - inset;
+            line(x, base, x, base - tall, color(80, 50, 30), 2);
+            b.circle_filled(x, base - tall - 10, (int)(15 * t + 5), color(50, 120, 50));
+        }
+    }
+    // vehicles: RandomState(frame_count % 100)
+    static const int vc[4][3] = {{0, 100, 200}, {200, 50, 50}, {50, 200, 50}, {200, 200, 50}};
+    static const int lanes[3] = {-80, 0, 80};
+    LegacyRandomState rs((uint32_t)(frame_count % 100));
+    const int64_t nv = rs.randint(2, 5);
+    for (int64_t i = 0; i < nv; i++) {
+        const double t = rs.uniform(0.2, 0.9);
+        const int64_t y = (int64_t)((double)(h / 2) + (double)(h / 2) * t);
+        const int lane = lanes[rs.randint(0, 3)];
+        int64_t x = w / 2 + (int64_t)((double)lane * t) + rs.randint(-20, 20);
+        x += (int64_t)(30 * sin((double)frame_count * 0.05 + (double)i));
+        const double scale = 0.3 + 0.7 * t;
+        const int64_t bw = (int64_t)(60 * scale), bh = (int64_t)(40 * scale);
+        auto fdiv = [](int64_t a, int64_t d) { return a >= 0 ? a / d : -((-a + d - 1) / d); };   // Python's // for d > 0
+        const uint32_t c = color(vc[i % 4][0], vc[i % 4][1], vc[i % 4][2]);
+        b.rectangle(Pt{x - fdiv(bw, 2), y - fdiv(bh, 2)}, Pt{x + fdiv(bw, 2), y + fdiv(bh, 2)}, c, -1);
+        b.rectangle(Pt{x - fdiv(bw, 2), y - fdiv(bh, 2)}, Pt{x + fdiv(bw, 2), y + fdiv(bh, 2)}, color(0, 0, 0), 1);
+        b.rectangle(Pt{x - fdiv(bw, 3), y - fdiv(bh, 2)}, Pt{x + fdiv(bw, 3), y - fdiv(bh, 4)}, color(100, 100, 100), -1);
+        const int rad = (int)(8 * scale);
+        b.circle_filled(x - fdiv(bw, 3), y + fdiv(bh, 2), rad, color(30, 30, 30));
+        b.circle_filled(x + fdiv(bw, 3), y + fdiv(bh, 2), rad, color(30, 30, 30));
+    }
+}
+
 
 }  // namespace lane_draw

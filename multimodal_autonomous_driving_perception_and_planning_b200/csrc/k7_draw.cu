@@ -302,7 +302,7 @@ inline int band_hi(const Prim &p) { return p.y1 / BAND_ROWS; }
 // filled by the same workers, and uploaded with one copy.  build_frame(Builder&, int f, const char **err) -> bool.
 template <class BuildFrame>
 int draw_driver(uint8_t *frames, int on_device, int n, int H, int W, int device, cudaStream_t st, float *device_ms,
-                BuildFrame build_frame)
+                BuildFrame build_frame, bool clear_first = false)
 {
     auto fail = [](int code, const char *msg) { lane_set_global_error(msg); return code; };
     const int bands = (H + BAND_ROWS - 1) / BAND_ROWS;
@@ -391,10 +391,11 @@ int draw_driver(uint8_t *frames, int on_device, int n, int H, int W, int device,
     uint8_t *d_frames = frames;
     if (!on_device) {
         if (cudaMalloc((void **)&d_frames, frame_bytes) != cudaSuccess) { cudaGetLastError(); return fail(LANE_ERR_CUDA, "lane_draw: device allocation failed"); }
-        cudaMemcpyAsync(d_frames, frames, frame_bytes, cudaMemcpyHostToDevice, st);
+        if (!clear_first) cudaMemcpyAsync(d_frames, frames, frame_bytes, cudaMemcpyHostToDevice, st);
     }
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     if (device_ms) { cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventRecord(e0, st); }
+    if (clear_first) cudaMemsetAsync(d_frames, 0, frame_bytes, st);
     cudaMemcpyAsync(d, h, total, cudaMemcpyHostToDevice, st);
     const int WW = (W + 31) >> 5;
     const size_t mask_words = (size_t)BAND_ROWS * WW;
@@ -465,4 +466,19 @@ extern "C" int lane_draw_lanes_batch(uint8_t *frames, int on_device, int n, int 
                                                   right_points + (size_t)f * LANE_NUM_POINTS * 2, right_valid[f], fill_lane);
                            return true;
                        });
+}
+
+extern "C" int lane_generate_frames(uint8_t *frames, int on_device, int n, int height, int width, int64_t frame_count0,
+                                    int device, void *cuda_stream, float *device_ms)
+{
+    auto fail = [](int code, const char *msg) { lane_set_global_error(msg); return code; };
+    if (!frames || n < 1 || height < 1 || width < 1 || frame_count0 < 0) return fail(LANE_ERR_INVALID, "lane_generate_frames: bad arguments");
+    if (height > 32767 || width > 32767) return fail(LANE_ERR_UNSUPPORTED, "lane_generate_frames: frame larger than 32767 px");
+    if (int rc = prepare_device(device)) return rc;
+    return draw_driver(frames, on_device, n, height, width, device, (cudaStream_t)cuda_stream, device_ms,
+                       [&](Builder &b, int f, const char **) {
+                           build_generator_frame(b, frame_count0 + f);
+                           return true;
+                       },
+                       true);
 }

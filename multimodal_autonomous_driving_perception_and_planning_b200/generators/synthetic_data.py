@@ -199,26 +199,42 @@ class SyntheticDataGenerator:
 
 
     def generate_batch_device(self, num_frames: int, start_frame: Optional[int] = None, device=None, out=None,
-                              return_ms: bool = False):
-        """The same ``num_frames`` consecutive frames as :meth:`generate_batch`, rasterised ON THE GPU: the scene code
-        records its cv2 calls per frame and ``lane_draw_commands`` (csrc/k7_draw.cu) executes them for the whole batch on
-        a zeroed ``uint8[num_frames, H, W, 3]`` CUDA tensor -- bit-identical to the host frames (no
-        CPU rasterisation and no 6 MB-per-frame upload in a benchmark's set-up).  There is no CPU fallback."""
+                              return_ms: bool = False, recorded: bool = False):
+        """The same ``num_frames`` consecutive frames as :meth:`generate_batch`, rasterised ON THE GPU into a
+        ``uint8[num_frames, H, W, 3]`` CUDA tensor, bit-identical to the host frames (no CPU
+        rasterisation and no 6 MB-per-frame upload in a benchmark's set-up).  ``lane_generate_frames`` lays the scene out
+        in the library's C++ host code (NumPy's legacy ``RandomState`` draws included) and ``k7_draw`` draws it;
+        ``recorded=True`` records the scene with this class's own Python code into a ``DrawList`` instead (the two must
+        agree; tests compare both with the cv2 generator).  There is no CPU fallback."""
+        import ctypes as C
         import torch
-        from ..visualization.draw_list import DrawList
+        from .. import _native
         if start_frame is not None:
             self.frame_count = start_frame
         dev = torch.device("cuda", torch.cuda.current_device() if device is None else int(device))
         if out is None:
-            out = torch.zeros((num_frames, self.height, self.width, 3), dtype=torch.uint8, device=dev)
-        else:
+            out = torch.empty((num_frames, self.height, self.width, 3), dtype=torch.uint8, device=dev)
+        elif tuple(out.shape) != (num_frames, self.height, self.width, 3) or out.dtype != torch.uint8 or not out.is_cuda \
+                or not out.is_contiguous():
+            raise ValueError("out must be a contiguous CUDA uint8 tensor [num_frames, H, W, 3]")
+        if recorded:
+            from ..visualization.draw_list import DrawList
             out.zero_()
-        dl = DrawList(num_frames)
-        for i in range(num_frames):
-            self._paint_frame_with_vehicles(_ListCanvas(dl, i))
-        with torch.cuda.device(dev):
-            res = dl.execute(out, return_ms=return_ms)
-        return res
+            dl = DrawList(num_frames)
+            for i in range(num_frames):
+                self._paint_frame_with_vehicles(_ListCanvas(dl, i))
+            with torch.cuda.device(out.device):
+                return dl.execute(out, return_ms=return_ms)
+        lib = _native.lib()
+        ms = C.c_float(0.0)
+        with torch.cuda.device(out.device):
+            stream = torch.cuda.current_stream(out.device).cuda_stream
+            rc = lib.lane_generate_frames(C.c_void_p(out.data_ptr()), 1, num_frames, self.height, self.width,
+                                          int(self.frame_count), out.device.index, C.c_void_p(stream), C.byref(ms))
+        if rc:
+            raise _native.LaneError(rc, (lib.lane_last_error(None) or b"").decode())
+        self.frame_count += num_frames
+        return (out, ms.value) if return_ms else out
 
 
 def multi_camera_batch(num_streams: int, frames_per_stream: int, width: int = 1920, height: int = 1080,

@@ -168,3 +168,20 @@ extern "C" int emu_build_only(int n, int H, int W, const int32_t *commands, cons
     if (n_prims) *n_prims = (int64_t)b.prims.size();
     return 0;
 }
+
+// SyntheticDataGenerator frames frame_count0 .. frame_count0 + n - 1 through the product's C++ scene code, on zeroed images
+extern "C" int emu_generate(uint8_t *frames, int n, int H, int W, int64_t frame_count0)
+{
+    Builder b;
+    b.H = H; b.W = W;
+    for (int f = 0; f < n; f++) {
+        b.begin.push_back((int64_t)b.prims.size());
+        build_generator_frame(b, frame_count0 + f);
+    }
+    b.begin.push_back((int64_t)b.prims.size());
+    for (int f = 0; f < n; f++) {
+        Canvas c{frames + (size_t)f * H * W * 3, H, W};
+        replay(c, b, f);
+    }
+    return 0;
+}

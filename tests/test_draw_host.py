@@ -35,6 +35,23 @@ def test_generator_frames_recorded_and_replayed_equal_the_host_generator():
         assert gen.frame_count == start + n
 
 
+def test_generator_scene_in_the_library_equals_the_host_generator():
+    """lane_generate_frames' host half (C++ scene code with NumPy's legacy RandomState) on the CPU: every seed
+    (frame_count % 100) and the sha256 fixtures of SURVEY.md 8(c)."""
+    import ctypes as C
+    import hashlib
+    from draw_util import emulator
+    emu = emulator()
+    emu.emu_generate.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int64]
+    for w, h, n, start in [(640, 480, 300, 0), (320, 240, 220, 950), (321, 203, 60, 7), (64, 48, 30, 0)]:
+        ref = SyntheticDataGenerator(w, h).generate_batch(n, start_frame=start)
+        mine = np.full_like(ref, 9)[:, :, :, :] * 0
+        assert emu.emu_generate(mine.ctypes.data_as(C.c_void_p), n, h, w, start) == 0
+        assert np.array_equal(ref, mine), (w, h)
+        if (w, h, start) == (640, 480, 0):
+            assert hashlib.sha256(mine.tobytes()).hexdigest()[:16] == "701c6dd0c4e8d707"
+
+
 def test_draw_lanes_and_offset_indicator_equal_the_reference_goldens():
     g = draw_golden()
     ov = OverlayRenderer()

@@ -142,12 +142,19 @@ def test_degenerate_and_far_outside_lanes():
 
 
 def test_generator_on_the_device_equals_the_host_generator():
-    for w, h, n, start in [(640, 480, 40, 0), (1920, 1080, 6, 95), (1280, 720, 4, 1000), (3840, 2160, 2, 3), (321, 203, 5, 7)]:
+    for w, h, n, start in [(640, 480, 120, 0), (1920, 1080, 6, 95), (1280, 720, 4, 1000), (3840, 2160, 2, 3), (321, 203, 105, 7)]:
         ref = SyntheticDataGenerator(w, h).generate_batch(n, start_frame=start)
-        gen = SyntheticDataGenerator(w, h)
-        dev = gen.generate_batch_device(n, start_frame=start)
-        assert gen.frame_count == start + n
-        assert np.array_equal(ref, dev.cpu().numpy()), (w, h)
+        for recorded in (False, True):       # scene laid out by the library's C++ code / recorded by the Python class
+            gen = SyntheticDataGenerator(w, h)
+            dev = gen.generate_batch_device(n, start_frame=start, recorded=recorded)
+            assert gen.frame_count == start + n
+            assert np.array_equal(ref, dev.cpu().numpy()), (w, h, recorded)
+    # host buffers through the raw ABI
+    import ctypes as C
+    from multimodal_autonomous_driving_perception_and_planning_b200 import _native
+    out = np.full((3, 120, 160, 3), 7, np.uint8)
+    assert _native.lib().lane_generate_frames(out.ctypes.data_as(C.c_void_p), 0, 3, 120, 160, 41, 0, None, None) == 0
+    assert np.array_equal(out, SyntheticDataGenerator(160, 120).generate_batch(3, start_frame=41))
 
 
 def test_generator_fixtures_of_the_survey_on_the_device():
