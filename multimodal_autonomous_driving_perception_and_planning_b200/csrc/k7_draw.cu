@@ -26,6 +26,8 @@
 //   BITMAP    1-bit mask blit (text)
 // HBM-bound byte work: no tensor cores, no GEMM shapes.
 #include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -360,7 +362,11 @@ int draw_driver(uint8_t *frames, int on_device, int n, int H, int W, int device,
         if (c.h) cudaFreeHost(c.h);
         c = DrawCache{};
         const size_t cap = std::max(total + total / 2, (size_t)1 << 20);
-        if (cudaMalloc(&c.d, cap) != cudaSuccess || cudaMallocHost(&c.h, cap) != cudaSuccess) {
+        // write-combined: the block is written once, front to back, by up to 16 host threads and then read by the copy
+        // engine only.  (Measured on the B200 box: the upload that follows the fill runs at ~11 GB/s with write-combined
+        // and with ordinary pinned memory alike, a repeated upload of the same block at 46 GB/s -- the hand-over from the
+        // CPU's writes to the DMA reads is what costs, 2 ms per 22 MB; LANE_B200_DRAW_DEBUG=1 prints it.)
+        if (cudaMalloc(&c.d, cap) != cudaSuccess || cudaHostAlloc(&c.h, cap, cudaHostAllocWriteCombined) != cudaSuccess) {
             if (c.d) cudaFree(c.d);
             c = DrawCache{};
             cudaGetLastError();
@@ -375,16 +381,21 @@ int draw_driver(uint8_t *frames, int on_device, int n, int H, int W, int device,
         int64_t *hs = (int64_t *)(h + off_side) + ck.side_base;
         int32_t *hi = (int32_t *)(h + off_idx);
         if (!ck.b.side.empty()) memcpy(hs, ck.b.side.data(), ck.b.side.size() * 8);
+        // the chunk's index lists are one contiguous stretch of the block: filled in ordinary memory (scattered 4-byte
+        // writes), then copied out in one sweep
+        const int64_t idx0 = band_begin[(size_t)ck.f0 * bands], idx1 = band_begin[(size_t)ck.f1 * bands];
+        std::vector<int32_t> local((size_t)(idx1 - idx0));
         std::vector<int64_t> cursor(bands);
         for (int f = ck.f0; f < ck.f1; f++) {
-            for (int bd = 0; bd < bands; bd++) cursor[bd] = band_begin[(size_t)f * bands + bd];
+            for (int bd = 0; bd < bands; bd++) cursor[bd] = band_begin[(size_t)f * bands + bd] - idx0;
             for (int64_t i = ck.b.begin[f - ck.f0]; i < ck.b.begin[f - ck.f0 + 1]; i++) {
                 Prim p = ck.b.prims[i];
                 if (p.op == P_ROWS || p.op == P_POLYFILL || p.op == P_BITMAP) p.a += ck.side_base;
                 hp[i] = p;
-                for (int bd = band_lo(p); bd <= band_hi(p); bd++) hi[cursor[bd]++] = (int32_t)(ck.prim_base + i);
+                for (int bd = band_lo(p); bd <= band_hi(p); bd++) local[cursor[bd]++] = (int32_t)(ck.prim_base + i);
             }
         }
+        if (!local.empty()) memcpy(hi + idx0, local.data(), local.size() * 4);
     });
 
     const size_t frame_bytes = (size_t)n * H * W * 3;
@@ -397,6 +408,9 @@ int draw_driver(uint8_t *frames, int on_device, int n, int H, int W, int device,
     if (device_ms) { cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventRecord(e0, st); }
     if (clear_first) cudaMemsetAsync(d_frames, 0, frame_bytes, st);
     cudaMemcpyAsync(d, h, total, cudaMemcpyHostToDevice, st);
+    static const bool dbg = getenv("LANE_B200_DRAW_DEBUG") != nullptr;
+    cudaEvent_t ec = nullptr;
+    if (dbg && device_ms) { cudaEventCreate(&ec); cudaEventRecord(ec, st); }
     const int WW = (W + 31) >> 5;
     const size_t mask_words = (size_t)BAND_ROWS * WW;
     const size_t smem = (mask_words + (mask_words & 1)) * 4 + (size_t)(DRAW_THREADS / 32) * MAX_ROW_EDGES * 8;
@@ -416,6 +430,13 @@ int draw_driver(uint8_t *frames, int on_device, int n, int H, int W, int device,
     if (e == cudaSuccess && !on_device) cudaMemcpyAsync(frames, d_frames, frame_bytes, cudaMemcpyDeviceToHost, st);
     if (e == cudaSuccess) e = cudaStreamSynchronize(st);
     if (e == cudaSuccess && device_ms) cudaEventElapsedTime(device_ms, e0, e1);
+    if (ec) {
+        float cms = 0;
+        if (e == cudaSuccess) cudaEventElapsedTime(&cms, e0, ec);
+        fprintf(stderr, "lane_draw: %lld primitives, %lld band entries, %.2f MB uploaded in %.3f ms, upload + kernel %.3f ms, %d host threads\n",
+                (long long)n_prims, (long long)n_idx, total / 1e6, cms, device_ms ? *device_ms : 0.f, T);
+        cudaEventDestroy(ec);
+    }
     if (e0) { cudaEventDestroy(e0); cudaEventDestroy(e1); }
     if (!on_device) cudaFree(d_frames);
     if (e != cudaSuccess) return fail(LANE_ERR_CUDA, cudaGetErrorString(e));
