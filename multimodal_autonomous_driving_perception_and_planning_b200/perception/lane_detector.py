@@ -223,6 +223,85 @@ class LaneDetector:
         self._adopt_state(lanes)
         return lanes
 
+    def detect_batches(self, batches):
+        """Pipelined ``detect_batch`` over a sequence of device-resident batches: a generator that yields, for every CUDA
+        tensor ``[N,H,W,3]`` of ``batches`` in order, what ``detect_batch`` would return for it.
+
+        Two batches are kept in flight on the native context with the temporal-smoothing state carried on the device (the
+        streaming form of the C ABI: ``lane_detect_enqueue`` twice, then collect / enqueue alternately), so the GPU never
+        waits for the host between batches and the Hough half of batch i runs under the edge kernels of batch i+1.
+        Results, state chain and ``prev_*_fit`` are exactly those of calling ``detect_batch`` batch after batch; a batch whose
+        segment lists overflow is re-run on the dense context like there (the queue is drained and restarted around it).
+        Batches that are not CUDA tensors of one common shape on one device simply go through ``detect_batch``."""
+        import torch
+        it = iter(batches)
+        queue = []                                   # [tensor, state_before (fit, valid)] of the batches in flight
+        ctx = None
+        fit, valid = self._state_arrays()
+        s, oms = self.smoothing_factor, 1 - self.smoothing_factor
+
+        def streamable(fr):
+            return (_is_torch_cuda(fr) and len(fr.shape) == 4 and fr.shape[0] > 0 and ctx is not None and
+                    fr.shape[0] <= ctx.max_batch and (int(fr.shape[1]), int(fr.shape[2])) == (ctx.height, ctx.width) and
+                    fr.device.index == ctx.device)
+
+        def enqueue(fr, explicit):
+            fr = fr.contiguous()
+            torch.cuda.ExternalStream(ctx.stream(), device=fr.device).wait_stream(torch.cuda.current_stream(fr.device))
+            if explicit:
+                ctx.enqueue(fr.data_ptr(), int(fr.shape[0]), None, 1, fit, valid, s, oms)
+            else:
+                ctx.enqueue(fr.data_ptr(), int(fr.shape[0]), None, 1, None, None, s, oms)
+            queue.append([fr, None])
+
+        def drain():
+            while ctx is not None and ctx._inflight:
+                ctx.collect(np.zeros((1, 2, 3)), np.zeros((1, 2), np.uint8))
+            queue.clear()
+
+        try:
+            nxt = next(it, None)
+            while nxt is not None or queue:
+                if not queue:                        # (re)start the pipeline with the detector's current state
+                    cur = nxt
+                    nxt = next(it, None)
+                    self._check_frames(cur, batched=True)
+                    if _is_torch_cuda(cur) and cur.shape[0] > 0:
+                        ctx = self._context(int(cur.shape[1]), int(cur.shape[2]), int(cur.shape[0]), cur)
+                    if not streamable(cur):
+                        yield self.detect_batch(cur)
+                        continue
+                    fit, valid = self._state_arrays()
+                    enqueue(cur, explicit=True)
+                if nxt is not None and len(queue) < 2:
+                    self._check_frames(nxt, batched=True)
+                    if streamable(nxt):
+                        enqueue(nxt, explicit=False)
+                        nxt = next(it, None)
+                head = queue[0][0]
+                state_before = (fit.copy(), valid.copy())
+                recs = ctx.collect(fit, valid)       # fit / valid now hold the state after `head`
+                queue.pop(0)
+                if recs["flags"].any():
+                    # truncated segment lists: the batches behind it started from a wrong state; drain, redo this batch
+                    # the blocking way (dense context) from the state it started with, and restart the pipeline
+                    requeue = [q[0] for q in queue]
+                    drain()
+                    for side, p in enumerate(("prev_left_fit", "prev_right_fit")):
+                        setattr(self, p, state_before[0][0, side].copy() if state_before[1][0, side] else None)
+                    lanes = self.detect_batch(head)
+                    yield lanes
+                    fit, valid = self._state_arrays()
+                    for k, fr in enumerate(requeue):
+                        enqueue(fr, explicit=(k == 0))
+                    continue
+                self.last_records = recs
+                lanes = self._lanes_from_records(recs)
+                self._adopt_state(lanes)
+                yield lanes
+        finally:
+            drain()
+
     def _adopt_state(self, lanes: List[LanePair]):
         """Like the reference (:210-216), prev_*_fit aliases the last returned polynomial of that side."""
         for left, _ in reversed(lanes):

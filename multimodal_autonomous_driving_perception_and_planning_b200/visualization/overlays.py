@@ -175,16 +175,31 @@ class OverlayRenderer:
             self.put_text(dl, frame, f"Offset: {offset:.0f}px", (x_start + 5, y_start - 5), 0.4, (255, 255, 255), 1,
                           frame_size=(w, h))
 
+    def _indicator_words(self, width: int, height: int, offset: Optional[float]) -> np.ndarray:
+        """Encoded command stream of one frame's indicator; cached per (size, offset) -- a batch has few distinct offsets."""
+        key = ("indicator", width, height, offset)
+        words = self._text_cache.get(key)
+        if words is None:
+            tmp = DrawList(1)
+            self.record_lane_offset_indicator(tmp, 0, width, height, offset)
+            words = self._text_cache[key] = tmp.encoded(0)
+            if len(self._text_cache) > 65536:
+                self._text_cache.clear()
+        return words
+
     def draw_lane_offset_indicator_batch(self, frames, offsets: Sequence[Optional[float]], device: Optional[int] = None):
         """``draw_lane_offset_indicator(frame, offset)`` for every frame of a batch, IN PLACE (uint8 ``[N, H, W, 3]``, CUDA
         tensor or numpy); ``offsets[i]`` is what ``get_lane_center_offset`` returned for frame ``i`` (``None`` allowed)."""
+        from .draw_list import run_commands
         n, h, w = int(frames.shape[0]), int(frames.shape[1]), int(frames.shape[2])
         if len(offsets) != n:
             raise ValueError("one offset per frame")
-        dl = DrawList(n)
-        for i, off in enumerate(offsets):
-            self.record_lane_offset_indicator(dl, i, w, h, None if off is None else float(off))
-        return dl.execute(frames, device)
+        if len(frames.shape) != 4 or frames.shape[3] != 3:
+            raise ValueError(f"expected uint8 frames [N, H, W, 3], got {tuple(frames.shape)}")
+        parts = [self._indicator_words(w, h, None if off is None else float(off)) for off in offsets]
+        begin = np.zeros(n + 1, np.int64)
+        np.cumsum([len(p) for p in parts], out=begin[1:])
+        return run_commands(frames, np.ascontiguousarray(np.concatenate(parts), np.int32), begin, device)
 
     def draw_lanes_batch(self, frames, lanes, fill_lane: bool = True, device: Optional[int] = None):
         return draw_lanes_batch(frames, lanes, fill_lane, device)

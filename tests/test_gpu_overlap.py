@@ -64,3 +64,37 @@ def test_streaming_with_overlap_equals_batch_after_batch(w, h, n):
     ms, _ = ctx.stage_ms()
     assert ms["ppht"] > 0
     det.close()
+
+
+def test_detect_batches_generator_equals_detect_batch_batch_after_batch():
+    """The public pipelined form: same lanes, same state chain, dense batches re-run, odd batches passed through."""
+    import torch
+    w, h, n = 1920, 1080, 48
+    batches = _batches(w, h, n, 6)
+    batches.insert(3, batches[1][:17].contiguous())                    # a shorter batch in the middle
+    host_batch = batches[0][:5].cpu().numpy()                          # a host batch: goes through detect_batch
+    seq = batches[:5] + [host_batch] + batches[5:]
+    ref_det = LaneDetector(max_batch=n, max_segments=256)              # small cap: the noise batch overflows it
+    want = [ref_det.detect_batch(b) for b in seq]
+    assert ref_det.dense_reruns >= 1
+    det = LaneDetector(max_batch=n, max_segments=256)
+    got = list(det.detect_batches(seq))
+    assert len(got) == len(want)
+    for k, (a, b) in enumerate(zip(got, want)):
+        assert len(a) == len(b)
+        for (la, ra), (lb, rb) in zip(a, b):
+            for x, y in ((la, lb), (ra, rb)):
+                assert (x is None) == (y is None), k
+                if x is not None:
+                    assert np.array_equal(x.points, y.points) and np.array_equal(x.polynomial, y.polynomial), k
+                    assert x.confidence == y.confidence and x.side == y.side
+    assert np.array_equal(det.prev_left_fit, ref_det.prev_left_fit) and np.array_equal(det.prev_right_fit, ref_det.prev_right_fit)
+    assert det.dense_reruns == ref_det.dense_reruns
+    # stopping early leaves nothing in flight
+    g = det.detect_batches(batches)
+    next(g)
+    g.close()
+    assert not det._ctx._inflight
+    det.detect_batch(batches[0])
+    det.close()
+    ref_det.close()
