@@ -40,6 +40,22 @@ def build(force: bool = False) -> str:
     return _LIB
 
 
+_EMU_SRC = os.path.join(os.path.dirname(_HERE), "tests", "native", "draw_emulator.cpp")
+_EMU_HDR = os.path.join(os.path.dirname(_HERE), "multimodal_autonomous_driving_perception_and_planning_b200", "csrc",
+                        "draw_prims.h")
+_EMU_LIB = os.path.join(_HERE, "_build", "libdraw_emulator.so")
+
+
+def build_draw_emulator(force: bool = False) -> str:
+    """Compile tests/native/draw_emulator.cpp (the CPU replay of K7's device primitives: test infrastructure that lets
+    the drawing path's HOST half be checked against cv2 without a GPU) and return the .so path."""
+    os.makedirs(os.path.dirname(_EMU_LIB), exist_ok=True)
+    newest = max(os.path.getmtime(_EMU_SRC), os.path.getmtime(_EMU_HDR))
+    if force or not os.path.exists(_EMU_LIB) or os.path.getmtime(_EMU_LIB) < newest:
+        subprocess.check_call(["g++", "-O2", "-std=c++20", "-ffp-contract=off", "-shared", "-fPIC", "-o", _EMU_LIB, _EMU_SRC])
+    return _EMU_LIB
+
+
 _lib = None
 
 

@@ -111,13 +111,8 @@ _EMU = None
 def emulator():
     global _EMU
     if _EMU is None:
-        src = os.path.join(ROOT, "tests", "native", "draw_emulator.cpp")
-        hdr = os.path.join(ROOT, "multimodal_autonomous_driving_perception_and_planning_b200", "csrc", "draw_prims.h")
-        out = os.path.join(ROOT, "oracle", "_build", "libdraw_emulator.so")
-        os.makedirs(os.path.dirname(out), exist_ok=True)
-        if not os.path.exists(out) or os.path.getmtime(out) < max(os.path.getmtime(src), os.path.getmtime(hdr)):
-            subprocess.run(["g++", "-O2", "-std=c++20", "-shared", "-fPIC", "-o", out, src], check=True)
-        _EMU = C.CDLL(out)
+        import oracle
+        _EMU = C.CDLL(oracle.build_draw_emulator())
     return _EMU
 
 
