@@ -134,3 +134,29 @@ def test_malformed_command_streams_are_rejected():
                                    begin.ctypes.data_as(C.c_void_p), None)
         assert rc == -1, words
     assert not frames.any()
+
+
+def test_polygons_with_more_edges_than_a_warp_orders_and_far_away_vertices():
+    import cv2
+    rng = np.random.default_rng(9)
+    for t in range(30):
+        w, h = int(rng.integers(40, 200)), int(rng.integers(40, 160))
+        img = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+        nv = int(rng.integers(130, 400))                      # > 128 edges: scan-converted by the host half
+        pts = np.column_stack([rng.integers(-30, w + 30, nv), rng.integers(-30, h + 30, nv)]).astype(np.int32)
+        far = np.array([[int(rng.integers(-10**6, 10**6)), int(rng.integers(-10**6, 10**6))] for _ in range(5)], np.int32)
+        ref = img.copy()
+        dl = DrawList(1)
+        cv2.fillPoly(ref, [pts], (9, 8, 7))
+        dl.fillPoly(0, pts, (9, 8, 7))
+        cv2.fillPoly(ref, [far], (1, 2, 3))
+        dl.fillPoly(0, far, (1, 2, 3))
+        cv2.polylines(ref, [far], True, (4, 5, 6), 3)
+        dl.polylines(0, far, True, (4, 5, 6), 3)
+        cv2.line(ref, tuple(int(v) for v in far[0]), tuple(int(v) for v in far[1]), (7, 7, 7), 1)
+        dl.line(0, far[0], far[1], (7, 7, 7), 1)
+        cv2.circle(ref, (int(far[2][0]) % w, int(far[2][1]) % h), 30, (0, 9, 0), -1)
+        dl.circle(0, (int(far[2][0]) % w, int(far[2][1]) % h), 30, (0, 9, 0), -1)
+        mine = img.copy()[None]
+        emu_commands(dl, mine)
+        assert np.array_equal(ref, mine[0]), t

@@ -214,3 +214,28 @@ def test_bad_arguments():
         dl.execute(np.zeros((1, 8, 8, 3), np.uint8))
     with pytest.raises(ValueError):
         draw_lanes_batch(torch.zeros((2, 8, 8, 3), dtype=torch.uint8, device="cuda"), [(None, None)])
+
+
+def test_polygons_with_more_edges_than_a_warp_orders_and_far_away_vertices():
+    rng = np.random.default_rng(9)
+    for t in range(12):
+        w, h = int(rng.integers(40, 200)), int(rng.integers(40, 160))
+        img = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+        nv = int(rng.integers(100, 400))
+        pts = np.column_stack([rng.integers(-30, w + 30, nv), rng.integers(-30, h + 30, nv)]).astype(np.int32)
+        far = np.array([[int(rng.integers(-10**6, 10**6)), int(rng.integers(-10**6, 10**6))] for _ in range(5)], np.int32)
+        ref = img.copy()
+        dl = DrawList(1)
+        cv2.fillPoly(ref, [pts], (9, 8, 7))
+        dl.fillPoly(0, pts, (9, 8, 7))
+        o = ref.copy()
+        cv2.fillPoly(o, [pts[:120]], (50, 60, 70))              # 120 edges: ordered per row by a warp, many crossings
+        ref = cv2.addWeighted(ref, 0.7, o, 0.3, 0)
+        dl.fillPoly_weighted(0, pts[:120], (50, 60, 70), 0.7, 0.3)
+        cv2.fillPoly(ref, [far], (1, 2, 3))
+        dl.fillPoly(0, far, (1, 2, 3))
+        cv2.polylines(ref, [far], True, (4, 5, 6), 3)
+        dl.polylines(0, far, True, (4, 5, 6), 3)
+        mine = img.copy()[None]
+        dl.execute(mine)
+        assert np.array_equal(ref, mine[0]), t
