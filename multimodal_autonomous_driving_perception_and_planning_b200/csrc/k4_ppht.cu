@@ -571,6 +571,19 @@ __device__ __forceinline__ int scell_get(const uint32_t *cells32, int cell)
 // shared-memory atomics (order-free); a vote that sees its bin at or above the threshold flags the
 // bin, and the exact first triggering point is then recovered per flagged bin by replaying only that
 // bin over the batch (counts inside a batch are monotone, so no other bin can trigger earlier).
+#ifdef LANE_PPHT_PROF
+// schedule probe (make prof; LANE_B200_PPHT_PROF=1): per frame the SM of rank 0, %globaltimer at the start and the end of the
+// cluster and thread 0's cycle accounting, written to a global array (printf inside the kernel would distort the schedule)
+// and printed by a one-thread kernel behind the launch.  tools/ppht_prof.py drives it; profiles/r2_ppht_schedule.txt.
+__device__ unsigned long long g_ppht_prof[8192][8];
+__global__ void k4_prof_dump(int n)
+{
+    for (int f = 0; f < n && f < 8192; f++)
+        printf("GT f=%d sm=%llu start=%llu end=%llu vote=%llu xchg=%llu walk=%llu total=%llu\n", f, g_ppht_prof[f][2],
+               g_ppht_prof[f][0], g_ppht_prof[f][1], g_ppht_prof[f][3], g_ppht_prof[f][4], g_ppht_prof[f][5], g_ppht_prof[f][6]);
+}
+#endif
+
 __global__ void __launch_bounds__(416, 2) k4_ppht_v3(const uint32_t *__restrict__ points_all, const int *__restrict__ n_points,
                            const uint32_t *__restrict__ pmask_all, uint32_t *__restrict__ pmask_work,
                            uint32_t *__restrict__ over_all,
@@ -645,6 +658,10 @@ __global__ void __launch_bounds__(416, 2) k4_ppht_v3(const uint32_t *__restrict_
     unsigned seq = 0;
 #ifdef LANE_PPHT_PROF   // cycle accounting of thread 0 (build with -DLANE_PPHT_PROF, run with LANE_B200_PPHT_PROF=1)
     long long tA = 0, tB = 0, tC = 0, tD = 0, tE = 0, tG = 0, tH = 0, tI = 0, t0 = 0, tStart = clock64();
+    unsigned long long gt_start;
+    unsigned prof_sm;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt_start));
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(prof_sm));
     int nTrig = 0, nIter = 0;
 #define TICK(acc) do { if (prof && tid == 0) { long long now_ = clock64(); acc += now_ - t0; t0 = now_; } } while (0)
 #define PROF(x) x
@@ -1046,9 +1063,12 @@ __global__ void __launch_bounds__(416, 2) k4_ppht_v3(const uint32_t *__restrict_
         TICK(tI);
     }
 #ifdef LANE_PPHT_PROF
-    if (prof && tid == 0 && rank == 0 && f < 2)
-        printf("ppht f=%d pts=%d iters=%d trig=%d total=%lld | maskchk=%lld vote=%lld replay=%lld xchg=%lld rollback+argmax+xchg2=%lld pass1=%lld pass2=%lld syncwait=%lld\n",
-               f, count0, nIter, nTrig, clock64() - tStart, tA, tB, tC, tD, tE, tG, tH, tI);
+    if (prof && tid == 0 && rank == 0 && f < 8192) {
+        unsigned long long gt_end;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt_end));
+        g_ppht_prof[f][0] = gt_start; g_ppht_prof[f][1] = gt_end; g_ppht_prof[f][2] = prof_sm;
+        g_ppht_prof[f][3] = tB; g_ppht_prof[f][4] = tD + tE; g_ppht_prof[f][5] = tG + tH; g_ppht_prof[f][6] = clock64() - tStart;
+    }
 #endif
     if (tid == 0 && rank == 0) n_lines[f] = nl;
     asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
@@ -1115,6 +1135,9 @@ bool launch_ppht_v3(const uint32_t *points, const int *n_points, const uint32_t 
     cudaError_t e = cudaLaunchKernelEx(&cfg, k4_ppht_v3, points, n_points, pmask, pmask_work, list_over, win3, cells_max, G, nvw, tpa,
                                        lines, n_lines, g, hp, getenv("LANE_B200_PPHT_PROF") ? 1 : 0, (const int *)order);
     if (e != cudaSuccess) { cudaGetLastError(); return false; }
+#ifdef LANE_PPHT_PROF
+    if (getenv("LANE_B200_PPHT_PROF")) k4_prof_dump<<<1, 1, 0, st>>>(n);
+#endif
     *launches += 1;
     return true;
 }

@@ -1,5 +1,11 @@
-"""GPU-box probe: schedule of k4_ppht_v3 (a -DLANE_PPHT_PROF build selected with LANE_B200_LIB, run with
-LANE_B200_PPHT_PROF=1): the bench's 256-frame batch, the kernel prints start / end (globaltimer) per frame."""
+"""GPU-box probe: schedule of k4_ppht_v3 over the bench's 256-frame batch.
+
+    make -C multimodal_autonomous_driving_perception_and_planning_b200/csrc prof          # -DLANE_PPHT_PROF build -> tools/_alt/
+    LANE_B200_LIB=$PWD/tools/_alt/liblane_prof.so LANE_B200_PPHT_PROF=1 python tools/ppht_prof.py 256
+
+Every frame's cluster records %globaltimer at its start and end, its SM and thread 0's cycle accounting in a global array;
+a one-thread kernel prints the lines after the launch ("GT f=.. sm=.. start=.. end=.. vote=.. xchg=.. walk=.. total=..").
+profiles/r2_ppht_schedule.txt is the output for the second (warm) call."""
 import sys
 sys.path.insert(0, '.')
 import torch
