@@ -294,6 +294,11 @@ LANE_API int lane_generate_frames(uint8_t *frames, int on_device, int n, int hei
 LANE_API int lane_draw_lanes_batch(uint8_t *frames, int on_device, int n, int height, int width, const int32_t *left_points,
                                    const uint8_t *left_valid, const int32_t *right_points, const uint8_t *right_valid,
                                    int fill_lane, int device, void *cuda_stream, float *device_ms);
+/* The same straight from the lane records on the device (lane_ctx_records_device of the batch collected last, or any
+ * device copy of lane_record[n]): no lane data touches the host.  frames_dev: device pointer, drawn in place; the kernel is
+ * enqueued on `cuda_stream` and the call returns without synchronising. */
+LANE_API int lane_draw_lanes_records(uint8_t *frames_dev, int n, int height, int width, const lane_record *records_dev,
+                                     int fill_lane, int device, void *cuda_stream);
 
 #ifdef __cplusplus
 }

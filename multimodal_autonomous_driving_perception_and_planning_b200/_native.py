@@ -104,6 +104,7 @@ _PROTOS = {
                                        C.POINTER(C.c_float)]),
     "lane_draw_lanes_batch": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
                                         C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.POINTER(C.c_float)]),
+    "lane_draw_lanes_records": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
     "lane_hough_accumulator": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int,
                                          C.POINTER(C.c_int)]),
 }

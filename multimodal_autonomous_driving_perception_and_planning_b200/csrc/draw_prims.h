@@ -30,11 +30,31 @@ constexpr int BAND_ROWS = 32;
 constexpr int DRAW_THREADS = 256;
 constexpr int MAX_ROW_EDGES = 128;   // active edges per row the POLYFILL primitive orders (more: host falls back to spans)
 
-// ------------------------------------------------------------------------------------------------ host side: cv2 -> primitives
+// ------------------------------------------------------------------------------------------------ geometry core
+// OpenCV's arithmetic, written once for both halves: the host half emits device primitives from it (Builder below), the
+// lane-overlay kernel (k7_lanes) runs the same functions on the device with an emitter that rasterises directly.
+// An emitter E provides
+//   int W, H
+//   void span(int64_t y, int64_t x1, int64_t x2)                 pixels x1..x2 of row y (any values: the emitter clips)
+//   void line8(int64_t x1, int64_t y1, int64_t dmaj, int64_t dmin, bool vert, int sy)   Bresenham, clipped, left to right
+//   void line2(bool xmajor, int64_t major0, int64_t count, int64_t minor0, int64_t step) 16.16 DDA, points checked one by one
+//   void trap(int64_t y0, int64_t y1, int64_t xl0, int64_t dxl, int64_t xr0, int64_t dxr) rows 0 <= y0..y1 < H of a trapezoid
+#ifdef __CUDACC__
+#define LANE_HD __host__ __device__
+#define LANE_NO_EXEC_CHECK _Pragma("nv_exec_check_disable")      // the emitter decides which side a template instance runs on
+#else
+#define LANE_HD
+#define LANE_NO_EXEC_CHECK
+#endif
+
 struct Pt { int64_t x, y; };
 
+template <class T> LANE_HD inline T lane_min(T a, T b) { return a < b ? a : b; }
+template <class T> LANE_HD inline T lane_max(T a, T b) { return a > b ? a : b; }
+template <class T> LANE_HD inline void lane_swap(T &a, T &b) { T t = a; a = b; b = t; }
+
 // cv::clipLine(Size2l, Point2l&, Point2l&)
-bool clip_line(int64_t width, int64_t height, Pt &p1, Pt &p2)
+LANE_HD inline bool clip_line(int64_t width, int64_t height, Pt &p1, Pt &p2)
 {
     const int64_t right = width - 1, bottom = height - 1;
     if (width <= 0 || height <= 0) return false;
@@ -73,10 +93,225 @@ bool clip_line(int64_t width, int64_t height, Pt &p1, Pt &p2)
     return (c1 | c2) == 0;
 }
 
-inline int64_t pack2(int64_t hi, int64_t lo) { return (int64_t)(((uint64_t)hi << 32) | (uint32_t)lo); }
+LANE_HD inline int64_t pack2(int64_t hi, int64_t lo) { return (int64_t)(((uint64_t)hi << 32) | (uint32_t)lo); }
 
+// dx*dx + dy*dy with two separately rounded products (the OpenCV build has no FMA contraction in this code)
+LANE_HD inline double sum_sq(double dx, double dy)
+{
+#ifdef __CUDA_ARCH__
+    return __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy));
+#else
+    volatile double a = dx * dx, b = dy * dy;
+    return a + b;
+#endif
+}
+
+// Line(img, p1, p2, color, 8): LineIterator, left to right
+LANE_NO_EXEC_CHECK
+template <class E> LANE_HD inline void geo_line8(E &e, Pt p1, Pt p2)
+{
+    const int W = e.W, H = e.H;
+    if ((uint64_t)p1.x >= (uint64_t)W || (uint64_t)p2.x >= (uint64_t)W || (uint64_t)p1.y >= (uint64_t)H ||
+        (uint64_t)p2.y >= (uint64_t)H)
+        if (!clip_line(W, H, p1, p2)) return;
+    int64_t dx = p2.x - p1.x, dy = p2.y - p1.y;
+    if (dx < 0) { dx = -dx; dy = -dy; p1 = p2; }
+    int sy = 1;
+    if (dy < 0) { dy = -dy; sy = -1; }
+    const bool vert = dy > dx;
+    if (vert) lane_swap(dx, dy);
+    if (!vert && dy == 0) { e.span(p1.y, p1.x, p1.x + dx); return; }
+    e.line8(p1.x, p1.y, dx, dy, vert, sy);
+}
+
+// Line2(img, p1, p2, color): 16.16 end points (the outline FillConvexPoly draws when shift != 0)
+LANE_NO_EXEC_CHECK
+template <class E> LANE_HD inline void geo_line2(E &e, Pt p1, Pt p2)
+{
+    if (!clip_line((int64_t)e.W << XY_SHIFT, (int64_t)e.H << XY_SHIFT, p1, p2)) return;
+    int64_t dx = p2.x - p1.x, dy = p2.y - p1.y;
+    const int64_t ax = dx < 0 ? -dx : dx, ay = dy < 0 ? -dy : dy;
+    int64_t step, ecount;
+    const bool xmajor = ax > ay;
+    if (xmajor) {
+        if (dx < 0) { dy = -dy; lane_swap(p1, p2); }
+        step = dy * XY_ONE / (ax | 1);
+        ecount = (p2.x - p1.x) >> XY_SHIFT;
+    } else {
+        if (dy < 0) { dx = -dx; lane_swap(p1, p2); }
+        step = dx * XY_ONE / (ay | 1);
+        ecount = (p2.y - p1.y) >> XY_SHIFT;
+    }
+    p1.x += HALF;
+    p1.y += HALF;
+    e.span((p2.y + HALF) >> XY_SHIFT, (p2.x + HALF) >> XY_SHIFT, (p2.x + HALF) >> XY_SHIFT);
+    if (ecount < 0) return;
+    if (xmajor) e.line2(true, p1.x >> XY_SHIFT, ecount + 1, p1.y, step);
+    else e.line2(false, p1.y >> XY_SHIFT, ecount + 1, p1.x, step);
+}
+
+// FillConvexPoly(img, v, npts, color, LINE_8, shift): outline, then the scan conversion as maximal runs of rows between
+// edge changes (a run is a trapezoid: both edges advance by a constant per row)
+LANE_NO_EXEC_CHECK
+template <class E> LANE_HD inline void geo_fill_convex(E &e, const Pt *v, int npts, int shift)
+{
+    const int W = e.W, H = e.H;
+    const int64_t delta = ((int64_t)1 << shift) >> 1;
+    Pt p0{v[npts - 1].x << (XY_SHIFT - shift), v[npts - 1].y << (XY_SHIFT - shift)};
+    int64_t xmin = v[0].x, xmax = v[0].x, ymin = v[0].y, ymax = v[0].y;
+    int imin = 0;
+    for (int i = 0; i < npts; i++) {
+        Pt p = v[i];
+        if (p.y < ymin) { ymin = p.y; imin = i; }
+        ymax = lane_max(ymax, p.y);
+        xmax = lane_max(xmax, p.x);
+        xmin = lane_min(xmin, p.x);
+        p.x <<= XY_SHIFT - shift;
+        p.y <<= XY_SHIFT - shift;
+        if (shift == 0) geo_line8(e, Pt{p0.x >> XY_SHIFT, p0.y >> XY_SHIFT}, Pt{p.x >> XY_SHIFT, p.y >> XY_SHIFT});
+        else geo_line2(e, p0, p);
+        p0 = p;
+    }
+    xmin = (xmin + delta) >> shift;
+    xmax = (xmax + delta) >> shift;
+    ymin = (ymin + delta) >> shift;
+    ymax = (ymax + delta) >> shift;
+    if (npts < 3 || xmax < 0 || ymax < 0 || xmin >= W || ymin >= H) return;
+    ymax = lane_min<int64_t>(ymax, H - 1);
+    struct Ed { int idx, di; int64_t x, dx, ye; } edge[2];
+    edge[0] = Ed{imin, 1, -XY_ONE, 0, ymin};
+    edge[1] = Ed{imin, npts - 1, -XY_ONE, 0, ymin};
+    int edges = npts;
+    int64_t y = ymin;
+    bool open = false;
+    int64_t run_y = 0, rx0 = 0, rd0 = 0, rx1 = 0, rd1 = 0;
+    do {
+        bool reinit = false;
+        for (int i = 0; i < 2; i++) {
+            if (y >= edge[i].ye) {
+                int idx0 = edge[i].idx, di = edge[i].di;
+                int idx = idx0 + di;
+                if (idx >= npts) idx -= npts;
+                for (; edges-- > 0;) {
+                    const int64_t ty = (v[idx].y + delta) >> shift;
+                    if (ty > y) {
+                        const int64_t xs = v[idx0].x << (XY_SHIFT - shift), xe = v[idx].x << (XY_SHIFT - shift);
+                        edge[i].ye = ty;
+                        edge[i].dx = ((xe - xs) * 2 + (ty - y)) / (2 * (ty - y));
+                        edge[i].x = xs;
+                        edge[i].idx = idx;
+                        reinit = true;
+                        break;
+                    }
+                    idx0 = idx;
+                    idx += di;
+                    if (idx >= npts) idx -= npts;
+                }
+            }
+        }
+        if (edges < 0) break;
+        if (reinit || !open) {
+            if (open && y - 1 >= 0 && y - 1 >= run_y) {          // close the run that ended on the row before
+                if (run_y < 0) { rx0 += -run_y * rd0; rx1 += -run_y * rd1; run_y = 0; }
+                e.trap(run_y, y - 1, rx0, rd0, rx1, rd1);
+            }
+            open = true;
+            run_y = y;
+            rx0 = edge[0].x; rd0 = edge[0].dx; rx1 = edge[1].x; rd1 = edge[1].dx;
+        }
+        edge[0].x += edge[0].dx;
+        edge[1].x += edge[1].dx;
+    } while (++y <= ymax);
+    if (open && y - 1 >= 0 && y - 1 >= run_y) {
+        if (run_y < 0) { rx0 += -run_y * rd0; rx1 += -run_y * rd1; run_y = 0; }
+        e.trap(run_y, y - 1, rx0, rd0, rx1, rd1);
+    }
+}
+
+// Circle(img, center, radius, color, fill = 1): the spans of the midpoint iteration (rows repeat; same colour)
+LANE_NO_EXEC_CHECK
+template <class E> LANE_HD inline void geo_circle(E &e, int64_t cx, int64_t cy, int radius)
+{
+    if (radius < 0) return;
+    int err = 0, dx = radius, dy = 0, plus = 1, minus = (radius << 1) - 1;
+    while (dx >= dy) {
+        e.span(cy - dy, cx - dx, cx + dx);
+        if (dy) e.span(cy + dy, cx - dx, cx + dx);
+        if (dx != dy) {
+            e.span(cy - dx, cx - dy, cx + dy);
+            if (dx) e.span(cy + dx, cx - dy, cx + dy);
+        }
+        dy++;
+        err += plus;
+        plus += 2;
+        const int mask = (err <= 0) - 1;
+        err -= minus & mask;
+        dx += mask;
+        minus -= mask & 2;
+    }
+}
+
+// ThickLine(img, p0, p1, color, thickness, LINE_8, flags, shift = 0)
+LANE_NO_EXEC_CHECK
+template <class E> LANE_HD inline void geo_thick_line(E &e, Pt p0, Pt p1, int thickness, int flags)
+{
+    if (thickness > 1) {          // OpenCV 4.13: a thick segment is first clipped against the image grown by `thickness`
+        const int64_t m = thickness;
+        Pt a{p0.x + m, p0.y + m}, b{p1.x + m, p1.y + m};
+        if (!clip_line(e.W + 2 * m, e.H + 2 * m, a, b)) return;
+        p0 = Pt{a.x - m, a.y - m};
+        p1 = Pt{b.x - m, b.y - m};
+    }
+    p0.x <<= XY_SHIFT; p0.y <<= XY_SHIFT; p1.x <<= XY_SHIFT; p1.y <<= XY_SHIFT;
+    if (thickness <= 1) {
+        geo_line8(e, Pt{(p0.x + HALF) >> XY_SHIFT, (p0.y + HALF) >> XY_SHIFT}, Pt{(p1.x + HALF) >> XY_SHIFT, (p1.y + HALF) >> XY_SHIFT});
+        return;
+    }
+    const double inv = 1. / (double)XY_ONE;
+    const double dx = (double)(p0.x - p1.x) * inv, dy = (double)(p1.y - p0.y) * inv;
+    double r = sum_sq(dx, dy);
+    const int odd = thickness & 1;
+    thickness <<= XY_SHIFT - 1;
+    if (fabs(r) > 2.220446049250313e-16) {
+        r = ((double)thickness + (double)odd * (double)XY_ONE * 0.5) / sqrt(r);
+        const int64_t dpx = (int64_t)nearbyint(dy * r), dpy = (int64_t)nearbyint(dx * r);
+        const Pt q[4] = {{p0.x + dpx, p0.y + dpy}, {p0.x - dpx, p0.y - dpy}, {p1.x - dpx, p1.y - dpy}, {p1.x + dpx, p1.y + dpy}};
+        geo_fill_convex(e, q, 4, XY_SHIFT);
+    }
+    for (int i = 0; i < 2; i++) {
+        if (flags & (i + 1))
+            geo_circle(e, (p0.x + HALF) >> XY_SHIFT, (p0.y + HALF) >> XY_SHIFT, (int)((thickness + HALF) >> XY_SHIFT));
+        p0 = p1;
+    }
+}
+
+// One polygon edge of cv2.fillPoly (CollectPolyEdges, LINE_8, shift 0) from vertex a to vertex b: the outline segment
+// Line() draws (t0, t1) and, unless the edge is horizontal, its scan-conversion record built from the CLIPPED end points
+struct PolyEdge { int64_t y0, y1, x, dx; };
+LANE_HD inline bool geo_poly_edge(int W, int H, Pt a, Pt b, Pt &t0, Pt &t1, PolyEdge &out)
+{
+    const Pt pt0{a.x << XY_SHIFT, a.y}, pt1{b.x << XY_SHIFT, b.y};
+    t0 = Pt{(pt0.x + HALF) >> XY_SHIFT, pt0.y};
+    t1 = Pt{(pt1.x + HALF) >> XY_SHIFT, pt1.y};
+    Pt c0 = t0, c1 = t1, pt0c = pt0, pt1c = pt1;
+    if ((uint64_t)c0.x >= (uint64_t)W || (uint64_t)c1.x >= (uint64_t)W || (uint64_t)c0.y >= (uint64_t)H ||
+        (uint64_t)c1.y >= (uint64_t)H) {
+        clip_line(W, H, c0, c1);
+        pt0c.x = c0.x << XY_SHIFT;
+        pt1c.x = c1.x << XY_SHIFT;
+        if (c0.y != c1.y) { pt0c.y = c0.y; pt1c.y = c1.y; }
+    }
+    if (pt0.y == pt1.y) return false;
+    out.dx = (pt1c.x - pt0c.x) / (pt1c.y - pt0c.y);
+    if (pt0.y < pt1.y) { out.y0 = pt0.y; out.y1 = pt1.y; out.x = pt0c.x + (pt0.y - pt0c.y) * out.dx; }
+    else { out.y0 = pt1.y; out.y1 = pt0.y; out.x = pt1c.x + (pt1.y - pt1c.y) * out.dx; }
+    return true;
+}
+
+// ------------------------------------------------------------------------------------------------ host side: cv2 -> primitives
 struct Builder {
     int H, W;
+    uint32_t cur = 0;                // colour of the calls being expanded (the emitter methods below use it)
     std::vector<Prim> prims;
     std::vector<int64_t> side;
     std::vector<int64_t> begin;      // per frame
@@ -88,195 +323,35 @@ struct Builder {
         if (y0 > y1 && op != P_MASK_BEGIN && op != P_MASK_BLEND) return;
         prims.push_back(Prim{op, y0, y1, color, a, b, c, d});
     }
-    void span(int64_t y, int64_t x1, int64_t x2, uint32_t color)      // pixels x1..x2 of row y (clipped here)
+    // ---- emitter interface of the geometry core
+    void span(int64_t y, int64_t x1, int64_t x2)
     {
         if (y < 0 || y >= H || x2 < 0 || x1 >= W || x1 > x2) return;
         x1 = std::max<int64_t>(x1, 0);
         x2 = std::min<int64_t>(x2, W - 1);
-        push(P_TRAP, (int)y, (int)y, color, x1 << XY_SHIFT, 0, x2 << XY_SHIFT, 0);
+        push(P_TRAP, (int)y, (int)y, cur, x1 << XY_SHIFT, 0, x2 << XY_SHIFT, 0);
     }
-
-    // Line(img, p1, p2, color, 8): LineIterator, left to right
-    void line8(Pt p1, Pt p2, uint32_t color)
+    void line8(int64_t x1, int64_t y1, int64_t dmaj, int64_t dmin, bool vert, int sy)
     {
-        if ((uint64_t)p1.x >= (uint64_t)W || (uint64_t)p2.x >= (uint64_t)W || (uint64_t)p1.y >= (uint64_t)H ||
-            (uint64_t)p2.y >= (uint64_t)H)
-            if (!clip_line(W, H, p1, p2)) return;
-        int64_t dx = p2.x - p1.x, dy = p2.y - p1.y;
-        if (dx < 0) { dx = -dx; dy = -dy; p1 = p2; }
-        int sy = 1;
-        if (dy < 0) { dy = -dy; sy = -1; }
-        const bool vert = dy > dx;
-        if (vert) std::swap(dx, dy);
-        if (!vert && dy == 0) { span(p1.y, p1.x, p1.x + dx, color); return; }
-        const int64_t ye = vert ? p1.y + sy * dx : p1.y + sy * dy;
-        push(P_LINE8, (int)std::min(p1.y, ye), (int)std::max(p1.y, ye), color, pack2(p1.x, p1.y), pack2(dx, dy),
-             (vert ? 1 : 0) | (sy < 0 ? 2 : 0), 0);
+        const int64_t ye = vert ? y1 + sy * dmaj : y1 + sy * dmin;
+        push(P_LINE8, (int)std::min(y1, ye), (int)std::max(y1, ye), cur, pack2(x1, y1), pack2(dmaj, dmin), (vert ? 1 : 0) | (sy < 0 ? 2 : 0), 0);
     }
-
-    // Line2(img, p1, p2, color): 16.16 end points (the outline FillConvexPoly draws when shift != 0)
-    void line2(Pt p1, Pt p2, uint32_t color)
+    void line2(bool xmajor, int64_t major0, int64_t count, int64_t minor0, int64_t step)
     {
-        if (!clip_line((int64_t)W << XY_SHIFT, (int64_t)H << XY_SHIFT, p1, p2)) return;
-        int64_t dx = p2.x - p1.x, dy = p2.y - p1.y;
-        const int64_t ax = dx < 0 ? -dx : dx, ay = dy < 0 ? -dy : dy;
-        int64_t step, ecount;
-        const bool xmajor = ax > ay;
         if (xmajor) {
-            if (dx < 0) { dy = -dy; std::swap(p1, p2); }
-            step = dy * XY_ONE / (ax | 1);
-            ecount = (p2.x - p1.x) >> XY_SHIFT;
+            const int64_t ya = minor0 >> XY_SHIFT, yb = (minor0 + (count - 1) * step) >> XY_SHIFT;
+            push(P_LINE2, (int)std::min(ya, yb), (int)std::max(ya, yb), cur, pack2(major0, count), minor0, step, 1);
         } else {
-            if (dy < 0) { dx = -dx; std::swap(p1, p2); }
-            step = dx * XY_ONE / (ay | 1);
-            ecount = (p2.y - p1.y) >> XY_SHIFT;
-        }
-        p1.x += HALF;
-        p1.y += HALF;
-        span((p2.y + HALF) >> XY_SHIFT, (p2.x + HALF) >> XY_SHIFT, (p2.x + HALF) >> XY_SHIFT, color);
-        if (ecount < 0) return;
-        if (xmajor) {
-            const int64_t ya = p1.y >> XY_SHIFT, yb = (p1.y + ecount * step) >> XY_SHIFT;
-            push(P_LINE2, (int)std::min(ya, yb), (int)std::max(ya, yb), color, pack2(p1.x >> XY_SHIFT, ecount + 1), p1.y, step, 1);
-        } else {
-            const int64_t y0 = p1.y >> XY_SHIFT;
-            push(P_LINE2, (int)y0, (int)(y0 + ecount), color, pack2(y0, ecount + 1), p1.x, step, 0);
+            push(P_LINE2, (int)major0, (int)(major0 + count - 1), cur, pack2(major0, count), minor0, step, 0);
         }
     }
+    void trap(int64_t y0, int64_t y1, int64_t xl0, int64_t dxl, int64_t xr0, int64_t dxr) { push(P_TRAP, (int)y0, (int)y1, cur, xl0, dxl, xr0, dxr); }
 
-    // FillConvexPoly(img, v, npts, color, LINE_8, shift)
-    void fill_convex(const Pt *v, int npts, uint32_t color, int shift)
-    {
-        const int64_t delta = ((int64_t)1 << shift) >> 1;
-        Pt p0{v[npts - 1].x << (XY_SHIFT - shift), v[npts - 1].y << (XY_SHIFT - shift)};
-        int64_t xmin = v[0].x, xmax = v[0].x, ymin = v[0].y, ymax = v[0].y;
-        int imin = 0;
-        for (int i = 0; i < npts; i++) {
-            Pt p = v[i];
-            if (p.y < ymin) { ymin = p.y; imin = i; }
-            ymax = std::max(ymax, p.y);
-            xmax = std::max(xmax, p.x);
-            xmin = std::min(xmin, p.x);
-            p.x <<= XY_SHIFT - shift;
-            p.y <<= XY_SHIFT - shift;
-            if (shift == 0) line8(Pt{p0.x >> XY_SHIFT, p0.y >> XY_SHIFT}, Pt{p.x >> XY_SHIFT, p.y >> XY_SHIFT}, color);
-            else line2(p0, p, color);
-            p0 = p;
-        }
-        xmin = (xmin + delta) >> shift;
-        xmax = (xmax + delta) >> shift;
-        ymin = (ymin + delta) >> shift;
-        ymax = (ymax + delta) >> shift;
-        if (npts < 3 || xmax < 0 || ymax < 0 || xmin >= W || ymin >= H) return;
-        ymax = std::min<int64_t>(ymax, H - 1);
-        struct E { int idx, di; int64_t x, dx, ye; } edge[2];
-        edge[0] = E{imin, 1, -XY_ONE, 0, ymin};
-        edge[1] = E{imin, npts - 1, -XY_ONE, 0, ymin};
-        int edges = npts;
-        int64_t y = ymin;
-        bool open = false;
-        int64_t run_y = 0, rx0 = 0, rd0 = 0, rx1 = 0, rd1 = 0;
-        auto flush = [&](int64_t y_last) {
-            if (!open) return;
-            open = false;
-            if (y_last < 0 || y_last < run_y) return;
-            if (run_y < 0) { rx0 += -run_y * rd0; rx1 += -run_y * rd1; run_y = 0; }
-            push(P_TRAP, (int)run_y, (int)y_last, color, rx0, rd0, rx1, rd1);
-        };
-        do {
-            bool reinit = false;
-            for (int i = 0; i < 2; i++) {
-                if (y >= edge[i].ye) {
-                    int idx0 = edge[i].idx, di = edge[i].di;
-                    int idx = idx0 + di;
-                    if (idx >= npts) idx -= npts;
-                    for (; edges-- > 0;) {
-                        const int64_t ty = (v[idx].y + delta) >> shift;
-                        if (ty > y) {
-                            const int64_t xs = v[idx0].x << (XY_SHIFT - shift), xe = v[idx].x << (XY_SHIFT - shift);
-                            edge[i].ye = ty;
-                            edge[i].dx = ((xe - xs) * 2 + (ty - y)) / (2 * (ty - y));
-                            edge[i].x = xs;
-                            edge[i].idx = idx;
-                            reinit = true;
-                            break;
-                        }
-                        idx0 = idx;
-                        idx += di;
-                        if (idx >= npts) idx -= npts;
-                    }
-                }
-            }
-            if (edges < 0) break;
-            if (reinit || !open) {
-                flush(y - 1);
-                open = true;
-                run_y = y;
-                rx0 = edge[0].x; rd0 = edge[0].dx; rx1 = edge[1].x; rd1 = edge[1].dx;
-            }
-            edge[0].x += edge[0].dx;
-            edge[1].x += edge[1].dx;
-        } while (++y <= ymax);
-        flush(y - 1);
-    }
-
-    // Circle(img, center, radius, color, fill = 1): the union of the spans is one centred span per row
-    void circle_filled(int64_t cx, int64_t cy, int radius, uint32_t color)
-    {
-        if (radius < 0) return;
-        std::vector<int> hw(2 * radius + 1, -1);
-        int err = 0, dx = radius, dy = 0, plus = 1, minus = (radius << 1) - 1;
-        while (dx >= dy) {
-            hw[radius - dy] = std::max(hw[radius - dy], dx);
-            hw[radius + dy] = std::max(hw[radius + dy], dx);
-            hw[radius - dx] = std::max(hw[radius - dx], dy);
-            hw[radius + dx] = std::max(hw[radius + dx], dy);
-            dy++;
-            err += plus;
-            plus += 2;
-            const int mask = (err <= 0) - 1;
-            err -= minus & mask;
-            dx += mask;
-            minus -= mask & 2;
-        }
-        for (int r = 0; r <= 2 * radius; r++)
-            if (hw[r] >= 0) span(cy - radius + r, cx - hw[r], cx + hw[r], color);
-    }
-
-    // ThickLine(img, p0, p1, color, thickness, LINE_8, flags, shift = 0)
-    void thick_line(Pt p0, Pt p1, uint32_t color, int thickness, int flags)
-    {
-        if (thickness > 1) {          // OpenCV 4.13: a thick segment is first clipped against the image grown by `thickness`
-            const int64_t m = thickness;
-            Pt a{p0.x + m, p0.y + m}, b{p1.x + m, p1.y + m};
-            if (!clip_line(W + 2 * m, H + 2 * m, a, b)) return;
-            p0 = Pt{a.x - m, a.y - m};
-            p1 = Pt{b.x - m, b.y - m};
-        }
-        p0.x <<= XY_SHIFT; p0.y <<= XY_SHIFT; p1.x <<= XY_SHIFT; p1.y <<= XY_SHIFT;
-        if (thickness <= 1) {
-            line8(Pt{(p0.x + HALF) >> XY_SHIFT, (p0.y + HALF) >> XY_SHIFT}, Pt{(p1.x + HALF) >> XY_SHIFT, (p1.y + HALF) >> XY_SHIFT},
-                  color);
-            return;
-        }
-        const double inv = 1. / (double)XY_ONE;
-        const double dx = (double)(p0.x - p1.x) * inv, dy = (double)(p1.y - p0.y) * inv;
-        volatile double dx2 = dx * dx, dy2 = dy * dy;       // separate roundings (no contraction), as the OpenCV build
-        double r = dx2 + dy2;
-        const int odd = thickness & 1;
-        thickness <<= XY_SHIFT - 1;
-        if (fabs(r) > 2.220446049250313e-16) {
-            r = ((double)thickness + (double)odd * (double)XY_ONE * 0.5) / sqrt(r);
-            const int64_t dpx = (int64_t)nearbyint(dy * r), dpy = (int64_t)nearbyint(dx * r);
-            const Pt q[4] = {{p0.x + dpx, p0.y + dpy}, {p0.x - dpx, p0.y - dpy}, {p1.x - dpx, p1.y - dpy}, {p1.x + dpx, p1.y + dpy}};
-            fill_convex(q, 4, color, XY_SHIFT);
-        }
-        for (int i = 0; i < 2; i++) {
-            if (flags & (i + 1))
-                circle_filled((p0.x + HALF) >> XY_SHIFT, (p0.y + HALF) >> XY_SHIFT, (int)((thickness + HALF) >> XY_SHIFT), color);
-            p0 = p1;
-        }
-    }
+    // ---- cv2-level calls
+    void line8(Pt p1, Pt p2, uint32_t color) { cur = color; geo_line8(*this, p1, p2); }
+    void fill_convex(const Pt *v, int npts, uint32_t color, int shift) { cur = color; geo_fill_convex(*this, v, npts, shift); }
+    void circle_filled(int64_t cx, int64_t cy, int radius, uint32_t color) { cur = color; geo_circle(*this, cx, cy, radius); }
+    void thick_line(Pt p0, Pt p1, uint32_t color, int thickness, int flags) { cur = color; geo_thick_line(*this, p0, p1, thickness, flags); }
 
     void polylines(const Pt *v, int count, bool closed, uint32_t color, int thickness)
     {
@@ -302,27 +377,14 @@ struct Builder {
     void fill_poly(const Pt *v, int count, uint32_t color)
     {
         if (count <= 0) return;
-        struct Edge { int64_t y0, y1, x, dx; };
+        typedef PolyEdge Edge;
         std::vector<Edge> edges;
         for (int i = 0; i < count; i++) {
-            const Pt &vp = v[i ? i - 1 : count - 1];
-            const Pt pt0{vp.x << XY_SHIFT, vp.y}, pt1{v[i].x << XY_SHIFT, v[i].y};
-            Pt t0{(pt0.x + HALF) >> XY_SHIFT, pt0.y}, t1{(pt1.x + HALF) >> XY_SHIFT, pt1.y};
-            line8(t0, t1, color);
-            Pt pt0c = pt0, pt1c = pt1;
-            if ((uint64_t)t0.x >= (uint64_t)W || (uint64_t)t1.x >= (uint64_t)W || (uint64_t)t0.y >= (uint64_t)H ||
-                (uint64_t)t1.y >= (uint64_t)H) {
-                clip_line(W, H, t0, t1);
-                pt0c.x = t0.x << XY_SHIFT;
-                pt1c.x = t1.x << XY_SHIFT;
-                if (t0.y != t1.y) { pt0c.y = t0.y; pt1c.y = t1.y; }
-            }
-            if (pt0.y == pt1.y) continue;
+            Pt t0, t1;
             Edge e;
-            e.dx = (pt1c.x - pt0c.x) / (pt1c.y - pt0c.y);
-            if (pt0.y < pt1.y) { e.y0 = pt0.y; e.y1 = pt1.y; e.x = pt0c.x + (pt0.y - pt0c.y) * e.dx; }
-            else { e.y0 = pt1.y; e.y1 = pt0.y; e.x = pt1c.x + (pt1.y - pt1c.y) * e.dx; }
-            edges.push_back(e);
+            const bool has = geo_poly_edge(W, H, v[i ? i - 1 : count - 1], v[i], t0, t1, e);
+            line8(t0, t1, color);
+            if (has) edges.push_back(e);
         }
         if (edges.size() < 2) return;
         int64_t y_min = INT64_MAX, y_max = INT64_MIN, x_min = INT64_MAX, x_max = INT64_MIN;
@@ -348,7 +410,7 @@ struct Builder {
                 for (const Edge &e : edges)
                     if (e.y0 <= y && y < e.y1) xs.push_back(e.x + (y - e.y0) * e.dx);
                 std::sort(xs.begin(), xs.end());
-                for (size_t k = 0; k + 1 < xs.size(); k += 2) span(y, (xs[k] + XY_ONE - 1) >> XY_SHIFT, xs[k + 1] >> XY_SHIFT, color);
+                for (size_t k = 0; k + 1 < xs.size(); k += 2) { cur = color; span(y, (xs[k] + XY_ONE - 1) >> XY_SHIFT, xs[k + 1] >> XY_SHIFT); }
             }
         }
     }

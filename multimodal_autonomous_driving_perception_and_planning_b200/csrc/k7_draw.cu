@@ -122,6 +122,75 @@ __device__ __forceinline__ void clipped_span(const Target &t, int y, long x1, lo
     }
 }
 
+// fillPoly's scan conversion of rows ya..yb: a warp per row gathers the active edges (y0 <= y < y1), orders their
+// x = x0 + (y - y0) * dx and fills [ceil(x_a), floor(x_b)] for every pair.  edges: (y0, y1, x, dx) per edge.
+__device__ void polyfill_rows(const Target &t, const int64_t *edges, int ne, int ya, int yb, uint32_t color, int warp, int nwarps,
+                              int lane, int64_t *row_x)
+{
+    for (int y = ya + warp; y <= yb; y += nwarps) {
+        int n = 0;
+        for (int e0 = 0; e0 < ne; e0 += 32) {
+            const int e = e0 + lane;
+            bool act = false;
+            int64_t x = 0;
+            if (e < ne) {
+                const int64_t ey0 = edges[4 * e], ey1 = edges[4 * e + 1];
+                act = ey0 <= y && y < ey1;
+                if (act) x = edges[4 * e + 2] + (y - ey0) * edges[4 * e + 3];
+            }
+            const unsigned m = __ballot_sync(0xffffffffu, act);
+            const int pos = n + __popc(m & ((1u << lane) - 1));
+            if (act && pos < MAX_ROW_EDGES) row_x[pos] = x;
+            n += __popc(m);
+        }
+        n = min(n, MAX_ROW_EDGES);
+        __syncwarp();
+        // rank sort (n is 2 for a simple polygon)
+        int64_t mine[MAX_ROW_EDGES / 32];
+        int rank[MAX_ROW_EDGES / 32];
+#pragma unroll
+        for (int j = 0; j < MAX_ROW_EDGES / 32; j++) {
+            const int i = lane + 32 * j;
+            rank[j] = 0;
+            if (i < n) {
+                mine[j] = row_x[i];
+                for (int k = 0; k < n; k++) {
+                    const int64_t o = row_x[k];
+                    rank[j] += (o < mine[j]) || (o == mine[j] && k < i);
+                }
+            }
+        }
+        __syncwarp();
+#pragma unroll
+        for (int j = 0; j < MAX_ROW_EDGES / 32; j++)
+            if (lane + 32 * j < n) row_x[rank[j]] = mine[j];
+        __syncwarp();
+        for (int k = 0; k + 1 < n; k += 2)
+            clipped_span(t, y, (long)((row_x[k] + XY_ONE - 1) >> XY_SHIFT), (long)(row_x[k + 1] >> XY_SHIFT), color, lane);
+        __syncwarp();
+    }
+}
+
+// cv2.addWeighted(img, alpha, overlay, beta, gamma) on rows ya..yb, columns x0..x1: overlay = color where the band mask is set
+__device__ void mask_blend(const Target &t, int ya, int yb, int x0, int x1, uint32_t color, float alpha, float beta, float gamma,
+                           bool outside_too, int tid)
+{
+    const int bw = x1 - x0 + 1, total = (yb - ya + 1) * bw;
+    for (int i = tid; i < total; i += DRAW_THREADS) {
+        const int y = ya + i / bw, x = x0 + i % bw;
+        const bool in = (t.mask[(size_t)(y - t.by0) * t.WW + (x >> 5)] >> (x & 31)) & 1;
+        if (!in && !outside_too) continue;
+        uint8_t *px = t.frame + ((size_t)y * t.W + x) * 3;
+#pragma unroll
+        for (int ch = 0; ch < 3; ch++) {
+            const float a = (float)px[ch];
+            const float o = in ? (float)((color >> (8 * ch)) & 255) : a;
+            const int r = __float2int_rn(fmaf(a, alpha, fmaf(o, beta, gamma)));
+            px[ch] = (uint8_t)min(255, max(0, r));
+        }
+    }
+}
+
 __global__ void __launch_bounds__(DRAW_THREADS) k7_draw(uint8_t *frames, const Prim *prims, const int64_t *band_begin,
                                                        const int32_t *band_idx, const int64_t *side, int H, int W)
 {
@@ -152,26 +221,9 @@ __global__ void __launch_bounds__(DRAW_THREADS) k7_draw(uint8_t *frames, const P
         if (p.op == P_MASK_BLEND) {
             __syncthreads();
             t.to_mask = false;
-            if (ya <= yb) {
-                const float alpha = __int_as_float((int)(uint32_t)p.a), beta = __int_as_float((int)(uint32_t)(p.a >> 32));
-                const float gamma = __int_as_float((int)(uint32_t)p.b);
-                const bool outside_too = (p.b >> 32) & 1;
-                const int x0 = (int)p.c, x1 = (int)p.d, bw = x1 - x0 + 1;
-                const int total = (yb - ya + 1) * bw;
-                for (int i = tid; i < total; i += DRAW_THREADS) {
-                    const int y = ya + i / bw, x = x0 + i % bw;
-                    const bool in = (t.mask[(size_t)(y - t.by0) * t.WW + (x >> 5)] >> (x & 31)) & 1;
-                    if (!in && !outside_too) continue;
-                    uint8_t *px = t.frame + ((size_t)y * W + x) * 3;
-#pragma unroll
-                    for (int ch = 0; ch < 3; ch++) {
-                        const float a = (float)px[ch];
-                        const float o = in ? (float)((p.color >> (8 * ch)) & 255) : a;
-                        const int r = __float2int_rn(fmaf(a, alpha, fmaf(o, beta, gamma)));
-                        px[ch] = (uint8_t)min(255, max(0, r));
-                    }
-                }
-            }
+            if (ya <= yb)
+                mask_blend(t, ya, yb, (int)p.c, (int)p.d, p.color, __int_as_float((int)(uint32_t)p.a),
+                           __int_as_float((int)(uint32_t)(p.a >> 32)), __int_as_float((int)(uint32_t)p.b), (p.b >> 32) & 1, tid);
             __syncthreads();
             continue;
         }
@@ -211,53 +263,9 @@ __global__ void __launch_bounds__(DRAW_THREADS) k7_draw(uint8_t *frames, const P
             }
             break;
         }
-        case P_POLYFILL: {
-            const int64_t *edges = side + p.a;      // (y0, y1, x, dx) per edge
-            const int ne = (int)p.b;
-            for (int y = ya + warp; y <= yb; y += nwarps) {
-                int n = 0;
-                for (int e0 = 0; e0 < ne; e0 += 32) {
-                    const int e = e0 + lane;
-                    bool act = false;
-                    int64_t x = 0;
-                    if (e < ne) {
-                        const int64_t ey0 = edges[4 * e], ey1 = edges[4 * e + 1];
-                        act = ey0 <= y && y < ey1;
-                        if (act) x = edges[4 * e + 2] + (y - ey0) * edges[4 * e + 3];
-                    }
-                    const unsigned m = __ballot_sync(0xffffffffu, act);
-                    const int pos = n + __popc(m & ((1u << lane) - 1));
-                    if (act && pos < MAX_ROW_EDGES) row_x[pos] = x;
-                    n += __popc(m);
-                }
-                n = min(n, MAX_ROW_EDGES);
-                __syncwarp();
-                // rank sort (n is 2 for a simple polygon)
-                int64_t mine[MAX_ROW_EDGES / 32];
-                int rank[MAX_ROW_EDGES / 32];
-#pragma unroll
-                for (int j = 0; j < MAX_ROW_EDGES / 32; j++) {
-                    const int i = lane + 32 * j;
-                    rank[j] = 0;
-                    if (i < n) {
-                        mine[j] = row_x[i];
-                        for (int k = 0; k < n; k++) {
-                            const int64_t o = row_x[k];
-                            rank[j] += (o < mine[j]) || (o == mine[j] && k < i);
-                        }
-                    }
-                }
-                __syncwarp();
-#pragma unroll
-                for (int j = 0; j < MAX_ROW_EDGES / 32; j++)
-                    if (lane + 32 * j < n) row_x[rank[j]] = mine[j];
-                __syncwarp();
-                for (int k = 0; k + 1 < n; k += 2)
-                    clipped_span(t, y, (long)((row_x[k] + XY_ONE - 1) >> XY_SHIFT), (long)(row_x[k + 1] >> XY_SHIFT), p.color, lane);
-                __syncwarp();
-            }
+        case P_POLYFILL:
+            polyfill_rows(t, side + p.a, (int)p.b, ya, yb, p.color, warp, nwarps, lane, row_x);
             break;
-        }
         case P_BITMAP: {
             const uint32_t *bits = (const uint32_t *)(side + p.a);
             const int bx = (int)(p.b >> 32), by = (int)(uint32_t)p.b, bw = (int)(p.c >> 32), bh = (int)(uint32_t)p.c;
@@ -275,6 +283,161 @@ __global__ void __launch_bounds__(DRAW_THREADS) k7_draw(uint8_t *frames, const P
             break;
         }
         default: break;
+        }
+        __syncthreads();
+    }
+}
+
+// ---- k7_lanes: LaneDetector.draw_lanes for a batch without any host expansion ------------------------------------------
+// The overlay of one frame is 100 polygon edges and 98 thick segments.  A CTA (band of rows, frame) reads the frame's two
+// 50-point polylines (from the lane records on the device, or from an uploaded copy of LaneLine.points), and every thread
+// runs OpenCV's arithmetic for ONE edge / segment with the geometry core of draw_prims.h -- the same template functions
+// the host half expands primitives with -- and rasterises what falls into its band directly:
+//   1. polygon outline (Line per edge) and scan conversion (edge table in shared memory, a warp per row) into the band's
+//      coverage mask, then one addWeighted blend per covered pixel;
+//   2. the left polyline's segments (quadrilateral by FillConvexPoly's row runs, its DDA outline, the end caps), all one
+//      colour, so no ordering between threads; 3. a barrier, then the right polyline's.
+// Three barriers per band instead of one per primitive, and 800 bytes per frame instead of 75 KB of primitive lists.
+struct LaneSrc {                     // where the points / validity flags of frame f, side s live
+    const char *base;
+    size_t frame_stride, pts_off[2], valid_off[2];
+    int valid_bytes;                 // 1: uint8 flags, 4: int32 (lane_side.valid)
+};
+
+struct DevEmit {                     // emitter of the geometry core: rasterise into this CTA's band (or its mask)
+    Target t;
+    uint32_t color;
+    int W, H;
+    __device__ void span(int64_t y, int64_t x1, int64_t x2)
+    {
+        if (y < t.by0 || y > t.by1 || x2 < 0 || x1 >= W || x1 > x2) return;
+        if (x1 < 0) x1 = 0;
+        if (x2 >= W) x2 = W - 1;
+        for (int64_t x = x1; x <= x2; x++) plot(t, (int)x, (int)y, color);
+    }
+    __device__ void line8(int64_t x1, int64_t y1, int64_t dmaj, int64_t dmin, bool vert, int sy)
+    {
+        for (int64_t i = 0; i <= dmaj; i++) {
+            const int64_t k = dmaj ? (2 * dmin * i + dmaj - 1) / (2 * dmaj) : 0;
+            if (vert) plot(t, (int)(x1 + k), (int)(y1 + sy * i), color);
+            else plot(t, (int)(x1 + i), (int)(y1 + sy * k), color);
+        }
+    }
+    __device__ void line2(bool xmajor, int64_t major0, int64_t count, int64_t minor0, int64_t step)
+    {
+        for (int64_t i = 0; i < count; i++) {
+            const int64_t minor = (minor0 + i * step) >> XY_SHIFT;
+            if (minor < 0 || minor >= 32768) continue;          // outside any supported frame
+            if (xmajor) plot(t, (int)(major0 + i), (int)minor, color);
+            else plot(t, (int)minor, (int)(major0 + i), color);
+        }
+    }
+    __device__ void trap(int64_t y0, int64_t y1, int64_t xl0, int64_t dxl, int64_t xr0, int64_t dxr)
+    {
+        const int64_t ya = y0 > t.by0 ? y0 : t.by0, yb = y1 < t.by1 ? y1 : t.by1;
+        for (int64_t y = ya; y <= yb; y++) {
+            int64_t l = xl0 + (y - y0) * dxl, r = xr0 + (y - y0) * dxr;
+            if (l > r) { const int64_t s = l; l = r; r = s; }
+            span(y, (l + HALF) >> XY_SHIFT, (r + HALF) >> XY_SHIFT);
+        }
+    }
+};
+
+constexpr int LANE_PTS = 50;
+
+__global__ void __launch_bounds__(DRAW_THREADS) k7_lanes(uint8_t *frames, LaneSrc src, int H, int W, int fill_lane, uint32_t fill_color,
+                                                        uint32_t left_color, uint32_t right_color, float alpha, float beta)
+{
+    extern __shared__ uint32_t smem[];
+    __shared__ int32_t s_pts[2][LANE_PTS][2];
+    __shared__ int s_valid[2];
+    __shared__ __align__(8) int64_t s_edges[2 * LANE_PTS][4];
+    __shared__ int s_fill[7];        // blend here?, its rows ya..yb and columns x0..x1, scan-conversion rows
+    const int f = blockIdx.y, band = blockIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = DRAW_THREADS / 32;
+    Target t;
+    t.frame = frames + (size_t)f * H * W * 3;
+    t.H = H; t.W = W; t.WW = (W + 31) >> 5;
+    t.by0 = band * BAND_ROWS;
+    t.by1 = min(H, t.by0 + BAND_ROWS) - 1;
+    t.mask = smem;
+    t.to_mask = false;
+    int64_t *row_x = (int64_t *)(smem + (size_t)BAND_ROWS * t.WW + (((size_t)BAND_ROWS * t.WW) & 1)) + warp * MAX_ROW_EDGES;
+    const char *rec = src.base + (size_t)f * src.frame_stride;
+    if (tid < 2) s_valid[tid] = src.valid_bytes == 1 ? (int)*(const uint8_t *)(rec + src.valid_off[tid]) : *(const int32_t *)(rec + src.valid_off[tid]);
+    for (int i = tid; i < 2 * LANE_PTS * 2; i += DRAW_THREADS) {
+        const int s = i / (LANE_PTS * 2), k = i - s * LANE_PTS * 2;
+        (&s_pts[s][0][0])[k] = ((const int32_t *)(rec + src.pts_off[s]))[k];
+    }
+    __syncthreads();
+    const bool lv = s_valid[0] != 0, rv = s_valid[1] != 0;
+    auto vertex = [&](int i) {       // pts = vstack([left.points, right.points[::-1]])   lane_detector.py:242
+        return i < LANE_PTS ? Pt{s_pts[0][i][0], s_pts[0][i][1]} : Pt{s_pts[1][2 * LANE_PTS - 1 - i][0], s_pts[1][2 * LANE_PTS - 1 - i][1]};
+    };
+    if (fill_lane && lv && rv) {
+        // the polygon's bounding box decides whether this band has anything to blend (the blend leaves other pixels alone)
+        if (tid == 0) {
+            int64_t y0 = INT64_MAX, y1 = INT64_MIN, x0 = INT64_MAX, x1 = INT64_MIN;
+            for (int i = 0; i < 2 * LANE_PTS; i++) {
+                const Pt v = vertex(i);
+                y0 = lane_min(y0, v.y); y1 = lane_max(y1, v.y); x0 = lane_min(x0, v.x); x1 = lane_max(x1, v.x);
+            }
+            y0 = lane_max<int64_t>(y0, t.by0); y1 = lane_min<int64_t>(y1, t.by1);
+            x0 = lane_max<int64_t>(x0, 0); x1 = lane_min<int64_t>(x1, W - 1);
+            s_fill[0] = y0 <= y1 && x0 <= x1;
+            s_fill[1] = (int)y0; s_fill[2] = (int)y1; s_fill[3] = (int)x0; s_fill[4] = (int)x1;
+        }
+        __syncthreads();
+        if (s_fill[0]) {
+            for (int i = tid; i < BAND_ROWS * t.WW; i += DRAW_THREADS) t.mask[i] = 0;
+            __syncthreads();
+            t.to_mask = true;
+            if (tid < 2 * LANE_PTS) {            // CollectPolyEdges: the outline into the mask, the edge record into shared memory
+                Pt t0, t1;
+                PolyEdge e;
+                const bool has = geo_poly_edge(W, H, vertex(tid ? tid - 1 : 2 * LANE_PTS - 1), vertex(tid), t0, t1, e);
+                DevEmit em{t, fill_color, W, H};
+                geo_line8(em, t0, t1);
+                s_edges[tid][0] = has ? e.y0 : 0; s_edges[tid][1] = has ? e.y1 : 0;      // y0 == y1: never active
+                s_edges[tid][2] = e.x; s_edges[tid][3] = e.dx;
+                if (!has) { s_edges[tid][2] = 0; s_edges[tid][3] = 0; }
+            }
+            __syncthreads();
+            if (tid == 0) {                      // FillEdgeCollection's early-outs and row range
+                int total = 0;
+                int64_t y_min = INT64_MAX, y_max = INT64_MIN, x_min = INT64_MAX, x_max = INT64_MIN;
+                for (int i = 0; i < 2 * LANE_PTS; i++) {
+                    if (s_edges[i][0] == s_edges[i][1]) continue;
+                    total++;
+                    const int64_t xe = s_edges[i][2] + (s_edges[i][1] - s_edges[i][0]) * s_edges[i][3];
+                    y_min = lane_min(y_min, s_edges[i][0]); y_max = lane_max(y_max, s_edges[i][1]);
+                    x_min = lane_min(x_min, lane_min(s_edges[i][2], xe)); x_max = lane_max(x_max, lane_max(s_edges[i][2], xe));
+                }
+                bool run = total >= 2 && !(y_max < 0 || y_min >= H || x_max < 0 || x_min >= ((int64_t)W << XY_SHIFT));
+                const int64_t ya = lane_max<int64_t>(lane_max<int64_t>(y_min, 0), t.by0), yb = lane_min<int64_t>(lane_min<int64_t>(y_max, H) - 1, t.by1);
+                s_fill[0] = run && ya <= yb ? 1 : 2;                 // 2: outline only
+                s_fill[5] = (int)ya; s_fill[6] = (int)yb;
+            }
+            __syncthreads();
+            if (s_fill[0] == 1)
+                polyfill_rows(t, &s_edges[0][0], 2 * LANE_PTS, s_fill[5], s_fill[6], fill_color, warp, nwarps, lane, row_x);
+            __syncthreads();
+            t.to_mask = false;
+            mask_blend(t, s_fill[1], s_fill[2], s_fill[3], s_fill[4], fill_color, alpha, beta, 0.0f, false, tid);
+        }
+        __syncthreads();
+    }
+    // cv2.polylines(frame, [points], False, colour, 3): segment s is ThickLine(p[s], p[s+1], 3, flags = 3 for the first, else 2)
+    for (int side = 0; side < 2; side++) {
+        if (side == 0 ? lv : rv) {
+            if (tid < LANE_PTS - 1) {
+                const Pt p0{s_pts[side][tid][0], s_pts[side][tid][1]}, p1{s_pts[side][tid + 1][0], s_pts[side][tid + 1][1]};
+                const int64_t lo = lane_min(p0.y, p1.y) - 4, hi = lane_max(p0.y, p1.y) + 4;      // half width 2 + cap radius 1
+                if (hi >= t.by0 && lo <= t.by1) {
+                    DevEmit em{t, side == 0 ? left_color : right_color, W, H};
+                    geo_thick_line(em, p0, p1, 3, tid == 0 ? 3 : 2);
+                }
+            }
         }
         __syncthreads();
     }
@@ -472,6 +635,38 @@ extern "C" int lane_draw_commands(uint8_t *frames, int on_device, int n, int hei
                        });
 }
 
+namespace {
+
+struct LaneItem {                    // what k7_lanes reads per frame when the lanes come from the host
+    int32_t pts[2][LANE_PTS][2];
+    int32_t valid[2];
+};
+
+int launch_lanes(uint8_t *d_frames, const LaneSrc &src, int n, int H, int W, int fill_lane, cudaStream_t st, int device)
+{
+    const int bands = (H + BAND_ROWS - 1) / BAND_ROWS, WW = (W + 31) >> 5;
+    const size_t mask_words = (size_t)BAND_ROWS * WW;
+    const size_t smem = (mask_words + (mask_words & 1)) * 4 + (size_t)(DRAW_THREADS / 32) * MAX_ROW_EDGES * 8;
+    static bool configured[LANE_MAX_DEVICES];
+    if (smem > 44 * 1024 && !configured[device & (LANE_MAX_DEVICES - 1)]) {
+        cudaFuncSetAttribute(k7_lanes, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        configured[device & (LANE_MAX_DEVICES - 1)] = true;
+    }
+    if (smem > 200 * 1024) return LANE_ERR_UNSUPPORTED;
+    // (0, 255, 100) at weight 0.3 over 0.7 (lane_detector.py:243-244), left (255, 0, 0) :248, right (0, 0, 255) :251
+    k7_lanes<<<dim3(bands, n), DRAW_THREADS, smem, st>>>(d_frames, src, H, W, fill_lane, 0u | 255u << 8 | 100u << 16, 255u, 255u << 16,
+                                                        0.7f, 0.3f);
+    return cudaGetLastError() == cudaSuccess ? LANE_OK : LANE_ERR_CUDA;
+}
+
+bool lanes_by_primitives()           // LANE_B200_DRAW_LANES=prims: the host-expanded primitive lists (A/B, and the tests run both)
+{
+    const char *e = getenv("LANE_B200_DRAW_LANES");
+    return e && !strcmp(e, "prims");
+}
+
+}  // namespace
+
 extern "C" int lane_draw_lanes_batch(uint8_t *frames, int on_device, int n, int height, int width, const int32_t *left_points,
                                      const uint8_t *left_valid, const int32_t *right_points, const uint8_t *right_valid,
                                      int fill_lane, int device, void *cuda_stream, float *device_ms)
@@ -481,12 +676,75 @@ extern "C" int lane_draw_lanes_batch(uint8_t *frames, int on_device, int n, int 
         return fail(LANE_ERR_INVALID, "lane_draw_lanes_batch: bad arguments");
     if (height > 32767 || width > 32767) return fail(LANE_ERR_UNSUPPORTED, "lane_draw_lanes_batch: frame larger than 32767 px");
     if (int rc = prepare_device(device)) return rc;
-    return draw_driver(frames, on_device, n, height, width, device, (cudaStream_t)cuda_stream, device_ms,
-                       [&](Builder &b, int f, const char **) {
-                           build_draw_lanes_frame(b, left_points + (size_t)f * LANE_NUM_POINTS * 2, left_valid[f],
-                                                  right_points + (size_t)f * LANE_NUM_POINTS * 2, right_valid[f], fill_lane);
-                           return true;
-                       });
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    if (lanes_by_primitives())
+        return draw_driver(frames, on_device, n, height, width, device, st, device_ms,
+                           [&](Builder &b, int f, const char **) {
+                               build_draw_lanes_frame(b, left_points + (size_t)f * LANE_NUM_POINTS * 2, left_valid[f],
+                                                      right_points + (size_t)f * LANE_NUM_POINTS * 2, right_valid[f], fill_lane);
+                               return true;
+                           });
+    // default: the geometry runs on the device (k7_lanes); only the 100 points per frame are uploaded
+    const size_t item_bytes = (size_t)n * sizeof(LaneItem), frame_bytes = (size_t)n * height * width * 3;
+    std::lock_guard<std::mutex> lk(g_draw_mutex);
+    DrawCache &c = g_draw_cache[device & (LANE_MAX_DEVICES - 1)];
+    if (c.cap < item_bytes) {
+        if (c.d) cudaFree(c.d);
+        if (c.h) cudaFreeHost(c.h);
+        c = DrawCache{};
+        const size_t cap = std::max(item_bytes * 2, (size_t)1 << 20);
+        if (cudaMalloc(&c.d, cap) != cudaSuccess || cudaHostAlloc(&c.h, cap, cudaHostAllocWriteCombined) != cudaSuccess) {
+            if (c.d) cudaFree(c.d);
+            c = DrawCache{};
+            cudaGetLastError();
+            return fail(LANE_ERR_CUDA, "lane_draw_lanes_batch: staging allocation failed");
+        }
+        c.cap = cap;
+    }
+    LaneItem *items = (LaneItem *)c.h;
+    for (int f = 0; f < n; f++) {
+        memcpy(items[f].pts[0], left_points + (size_t)f * LANE_PTS * 2, sizeof(items[f].pts[0]));
+        memcpy(items[f].pts[1], right_points + (size_t)f * LANE_PTS * 2, sizeof(items[f].pts[1]));
+        items[f].valid[0] = left_valid[f] != 0;
+        items[f].valid[1] = right_valid[f] != 0;
+    }
+    uint8_t *d_frames = frames;
+    if (!on_device) {
+        if (cudaMalloc((void **)&d_frames, frame_bytes) != cudaSuccess) { cudaGetLastError(); return fail(LANE_ERR_CUDA, "lane_draw_lanes_batch: device allocation failed"); }
+        cudaMemcpyAsync(d_frames, frames, frame_bytes, cudaMemcpyHostToDevice, st);
+    }
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    if (device_ms) { cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventRecord(e0, st); }
+    cudaMemcpyAsync(c.d, c.h, item_bytes, cudaMemcpyHostToDevice, st);
+    LaneSrc src{(const char *)c.d, sizeof(LaneItem), {offsetof(LaneItem, pts), offsetof(LaneItem, pts) + sizeof(items[0].pts[0])},
+                {offsetof(LaneItem, valid), offsetof(LaneItem, valid) + 4}, 4};
+    int rc = launch_lanes(d_frames, src, n, height, width, fill_lane, st, device);
+    if (device_ms) cudaEventRecord(e1, st);
+    cudaError_t e = cudaSuccess;
+    if (rc == LANE_OK && !on_device) cudaMemcpyAsync(frames, d_frames, frame_bytes, cudaMemcpyDeviceToHost, st);
+    e = cudaStreamSynchronize(st);
+    if (e == cudaSuccess && rc == LANE_OK && device_ms) cudaEventElapsedTime(device_ms, e0, e1);
+    if (e0) { cudaEventDestroy(e0); cudaEventDestroy(e1); }
+    if (!on_device) cudaFree(d_frames);
+    if (rc == LANE_ERR_UNSUPPORTED) return fail(rc, "lane_draw_lanes_batch: frame too wide for the band mask");
+    if (rc != LANE_OK || e != cudaSuccess) return fail(LANE_ERR_CUDA, cudaGetErrorString(e != cudaSuccess ? e : cudaGetLastError()));
+    return LANE_OK;
+}
+
+extern "C" int lane_draw_lanes_records(uint8_t *frames_dev, int n, int height, int width, const lane_record *records_dev,
+                                       int fill_lane, int device, void *cuda_stream)
+{
+    auto fail = [](int code, const char *msg) { lane_set_global_error(msg); return code; };
+    if (!frames_dev || !records_dev || n < 1 || height < 1 || width < 1) return fail(LANE_ERR_INVALID, "lane_draw_lanes_records: bad arguments");
+    if (height > 32767 || width > 32767) return fail(LANE_ERR_UNSUPPORTED, "lane_draw_lanes_records: frame larger than 32767 px");
+    if (int rc = prepare_device(device)) return rc;
+    LaneSrc src{(const char *)records_dev, sizeof(lane_record),
+                {offsetof(lane_record, side) + offsetof(lane_side, points), offsetof(lane_record, side) + sizeof(lane_side) + offsetof(lane_side, points)},
+                {offsetof(lane_record, side) + offsetof(lane_side, valid), offsetof(lane_record, side) + sizeof(lane_side) + offsetof(lane_side, valid)}, 4};
+    const int rc = launch_lanes(frames_dev, src, n, height, width, fill_lane, (cudaStream_t)cuda_stream, device);
+    if (rc == LANE_ERR_UNSUPPORTED) return fail(rc, "lane_draw_lanes_records: frame too wide for the band mask");
+    if (rc != LANE_OK) return fail(LANE_ERR_CUDA, "k7_lanes launch failed");
+    return LANE_OK;
 }
 
 extern "C" int lane_generate_frames(uint8_t *frames, int on_device, int n, int height, int width, int64_t frame_count0,

@@ -97,6 +97,23 @@ def draw_lanes_arrays(frames, left_points, left_valid, right_points, right_valid
     return (frames, ms.value) if return_ms else frames
 
 
+def draw_lanes_records(frames, records_device_ptr: int, fill_lane: bool = True):
+    """``draw_lanes`` for a batch straight from the lane records ON THE DEVICE (``LaneContext.records_device_ptr()`` after a
+    collect, i.e. ``lane_ctx_records_device``): neither the lanes nor the frames touch the host.  ``frames``: contiguous
+    CUDA uint8 tensor ``[N, H, W, 3]``, drawn in place on torch's current stream (no synchronisation)."""
+    import torch
+    lib = _native.lib()
+    if not frames.is_cuda or frames.dtype != torch.uint8 or not frames.is_contiguous() or len(frames.shape) != 4 or frames.shape[3] != 3:
+        raise cv2.error("draw_lanes_records: frames must be a contiguous CUDA uint8 tensor [N, H, W, 3]")
+    n, h, w = int(frames.shape[0]), int(frames.shape[1]), int(frames.shape[2])
+    stream = torch.cuda.current_stream(frames.device).cuda_stream
+    rc = lib.lane_draw_lanes_records(C.c_void_p(frames.data_ptr()), n, h, w, C.c_void_p(records_device_ptr), int(bool(fill_lane)),
+                                     frames.device.index, C.c_void_p(stream))
+    if rc:
+        raise _native.LaneError(rc, (lib.lane_last_error(None) or b"").decode())
+    return frames
+
+
 class OverlayRenderer:
     """The lane part of the reference's ``OverlayRenderer`` (src/visualization/overlays.py:16-24, :103-148), batched."""
 

@@ -239,3 +239,44 @@ def test_polygons_with_more_edges_than_a_warp_orders_and_far_away_vertices():
         mine = img.copy()[None]
         dl.execute(mine)
         assert np.array_equal(ref, mine[0]), t
+
+
+def test_lane_overlay_kernel_and_primitive_lists_agree_and_records_on_the_device():
+    """draw_lanes_batch runs k7_lanes (geometry on the device) by default; LANE_B200_DRAW_LANES=prims takes the host-expanded
+    primitive lists.  Both must give cv2's pixels; and the overlay can be drawn straight from the device records."""
+    import os
+    import subprocess
+    import sys
+    import torch
+    from multimodal_autonomous_driving_perception_and_planning_b200.visualization import draw_lanes_records
+    w, h, n = 1280, 720, 40
+    frames = SyntheticDataGenerator(w, h).generate_batch_device(n, start_frame=0)
+    det = LaneDetector(max_batch=n)
+    lanes = det.detect_batch(frames)
+    by_kernel = det.draw_lanes_batch(frames.clone(), lanes)
+    host = frames.cpu().numpy()
+    for i, (l, r) in enumerate(lanes):
+        ref = cv2_draw_lanes(host[i].copy(), None if l is None else l.points, None if r is None else r.points)
+        assert np.array_equal(ref, by_kernel[i].cpu().numpy()), i
+    from_records = draw_lanes_records(frames.clone(), det._ctx.records_device_ptr())
+    torch.cuda.synchronize()
+    assert torch.equal(from_records, by_kernel)
+    no_fill = draw_lanes_records(frames.clone(), det._ctx.records_device_ptr(), fill_lane=False)
+    assert torch.equal(no_fill, det.draw_lanes_batch(frames.clone(), lanes, fill_lane=False))
+    # the primitive-list path in a child process (the switch is read once per process)
+    code = ("import sys, numpy as np, torch; sys.path.insert(0, '.'); sys.path.insert(0, 'tests'); sys.path.insert(0, 'tests/golden')\n"
+            "from draw_cases import N_RANDOM, random_case\nfrom draw_util import draw_golden, h16\n"
+            "from multimodal_autonomous_driving_perception_and_planning_b200.visualization.overlays import draw_lanes_arrays\n"
+            "g = draw_golden()\n"
+            "for seed in range(N_RANDOM):\n"
+            "    frame, pts, valid, off = random_case(seed)\n"
+            "    for fill, col in ((True, 0), (False, 1)):\n"
+            "        mine = frame.copy()[None]\n"
+            "        draw_lanes_arrays(mine, pts[None, 0], valid[None, 0], pts[None, 1], valid[None, 1], fill)\n"
+            "        assert h16(mine[0]) == g['random_hash'][seed][col], (seed, fill)\n"
+            "print('prims ok')\n")
+    env = dict(os.environ, LANE_B200_DRAW_LANES="prims")
+    out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True,
+                         cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    assert out.returncode == 0 and "prims ok" in out.stdout, out.stderr[-2000:]
+    det.close()
