@@ -507,7 +507,7 @@ __global__ void __launch_bounds__(NT2) k4_ppht_v2(uint32_t *__restrict__ points_
 // 64-bit word per CTA per batch (first triggering point) and one per trigger (arg-max), exchanged
 // through DSMEM slots with a sequence number -- no cluster barrier on the hot path.
 constexpr int BATCH3 = 64;
-constexpr int LIST_CAP3 = 3072;      // points of a frame kept in shared memory
+constexpr int LIST_CAP3 = 3072;      // points of a frame kept in shared memory (the plan may settle for less to fit a smaller cluster)
 constexpr int OVER_CAP3 = 13312;     // further points kept in a private global (L2) extension of the list
 
 struct XchgSlots {
@@ -587,7 +587,7 @@ __global__ void k4_prof_dump(int n)
 __global__ void __launch_bounds__(416, 2) k4_ppht_v3(const uint32_t *__restrict__ points_all, const int *__restrict__ n_points,
                            const uint32_t *__restrict__ pmask_all, uint32_t *__restrict__ pmask_work,
                            uint32_t *__restrict__ over_all,
-                           const int2 *__restrict__ win, int cells_max, int G, int nvw, int tpa,
+                           const int2 *__restrict__ win, int cells_max, int list_cap, int G, int nvw, int tpa,
                            int32_t *__restrict__ lines_all, int *__restrict__ n_lines, LaneGeom g, LaneHoughParams hp, int prof,
                            const int *__restrict__ order)
 {
@@ -642,16 +642,16 @@ __global__ void __launch_bounds__(416, 2) k4_ppht_v3(const uint32_t *__restrict_
     if (tid < 32) { s_slots.v[0][tid & 15] = 0; s_slots.v[1][tid & 15] = 0; }
     const int count0 = n_points[f];
     const uint32_t *glist = points_all + (size_t)f * g.max_points;
-    // The list lives in shared memory up to LIST_CAP3 points; a longer one (every 4K generator frame: 3.3 k points)
+    // The list lives in shared memory up to list_cap points; a longer one (every 4K generator frame: 3.3 k points)
     // continues in this CTA's private global extension.  Swap-remove only ever touches a random index and the current
-    // tail, so once the list has shrunk below LIST_CAP3 everything is in shared memory again.
+    // tail, so once the list has shrunk below list_cap everything is in shared memory again.
     uint32_t *over = over_all + ((size_t)f * G + rank) * OVER_CAP3;
-    const bool dense = count0 > LIST_CAP3 + OVER_CAP3 || (count0 > LIST_CAP3 && !over_all);   // left to v2
+    const bool dense = count0 > list_cap + OVER_CAP3 || (count0 > list_cap && !over_all);   // left to v2
     if (!dense) {
-        for (int i = tid; i < min(count0, LIST_CAP3); i += blockDim.x) s_list[i] = glist[i];
-        for (int i = LIST_CAP3 + tid; i < count0; i += blockDim.x) __stcg(&over[i - LIST_CAP3], glist[i]);
+        for (int i = tid; i < min(count0, list_cap); i += blockDim.x) s_list[i] = glist[i];
+        for (int i = list_cap + tid; i < count0; i += blockDim.x) __stcg(&over[i - list_cap], glist[i]);
     }
-    const bool has_over = !dense && count0 > LIST_CAP3;
+    const bool has_over = !dense && count0 > list_cap;
     const int n_batches = (count0 + BATCH3 - 1) / BATCH3;
     uint64_t rng = 0xFFFFFFFFFFFFFFFFull;
     int remaining = count0, nl = 0;
@@ -685,11 +685,11 @@ __global__ void __launch_bounds__(416, 2) k4_ppht_v3(const uint32_t *__restrict_
         // OVER = false (the usual case) keeps the list accesses plain shared-memory loads and stores
         constexpr bool OVER = decltype(over_tag)::value;
         auto lget = [&](int i) -> uint32_t {
-            if constexpr (OVER) return i < LIST_CAP3 ? s_list[i] : __ldcg(&over[i - LIST_CAP3]);
+            if constexpr (OVER) return i < list_cap ? s_list[i] : __ldcg(&over[i - list_cap]);
             else return s_list[i];
         };
         auto lset = [&](int i, uint32_t v) {
-            if constexpr (OVER) { if (i < LIST_CAP3) s_list[i] = v; else __stcg(&over[i - LIST_CAP3], v); }
+            if constexpr (OVER) { if (i < list_cap) s_list[i] = v; else __stcg(&over[i - list_cap], v); }
             else s_list[i] = v;
         };
         const int P = remaining < BATCH3 ? remaining : BATCH3;
@@ -1103,7 +1103,7 @@ void launch_ppht_v2(uint32_t *points, const int *n_points, uint32_t *pmask, uint
 
 // v3 launch: false if the geometry does not fit (caller uses v2)
 bool launch_ppht_v3(const uint32_t *points, const int *n_points, const uint32_t *pmask, uint32_t *pmask_work,
-                    uint32_t *list_over, const int2 *win3, int cells_max, int G, int32_t *lines, int *n_lines, LaneGeom g,
+                    uint32_t *list_over, const int2 *win3, int cells_max, int list_cap, int G, int32_t *lines, int *n_lines, LaneGeom g,
                     LaneHoughParams hp, int n, cudaStream_t st, int *launches, int *order)
 {
     if (G < 1 || (g.bh * ((g.W + 31) / 32)) % 4 != 0 || ((uintptr_t)pmask % 16) != 0) return false;
@@ -1115,7 +1115,7 @@ bool launch_ppht_v3(const uint32_t *points, const int *n_points, const uint32_t 
     int tpa = 384 / angles;                      // aim at ~12 voter warps per CTA
     tpa = tpa < 1 ? 1 : (tpa > 8 ? 8 : tpa);
     const int nvw = (angles * tpa + 31) / 32;
-    const size_t smem = (((size_t)cells_max * 2 + 15) & ~(size_t)15) + sizeof(uint32_t) * LIST_CAP3;
+    const size_t smem = (((size_t)cells_max * 2 + 15) & ~(size_t)15) + sizeof(uint32_t) * (size_t)list_cap;
     static bool configured[LANE_MAX_DEVICES];
     if (!configured[lane_cur_device()]) {
         cudaFuncSetAttribute(k4_ppht_v3, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
@@ -1132,7 +1132,7 @@ bool launch_ppht_v3(const uint32_t *points, const int *n_points, const uint32_t 
     attr[0].val.clusterDim.x = G; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    cudaError_t e = cudaLaunchKernelEx(&cfg, k4_ppht_v3, points, n_points, pmask, pmask_work, list_over, win3, cells_max, G, nvw, tpa,
+    cudaError_t e = cudaLaunchKernelEx(&cfg, k4_ppht_v3, points, n_points, pmask, pmask_work, list_over, win3, cells_max, list_cap, G, nvw, tpa,
                                        lines, n_lines, g, hp, getenv("LANE_B200_PPHT_PROF") ? 1 : 0, (const int *)order);
     if (e != cudaSuccess) { cudaGetLastError(); return false; }
 #ifdef LANE_PPHT_PROF
@@ -1147,12 +1147,16 @@ int lane_ppht_over_cap_v3() { return OVER_CAP3; }
 
 // Plan the v3 layout: smallest cluster size whose per-CTA cell count fits shared memory.  win3[n] = (rmin_n,
 // first cell inside CTA n % G).  Returns G (0 if nothing fits) and *cells_max.
-int lane_ppht_plan_v3(const int2 *win, int cells_total, int2 *win3, int *cells_max)
+int lane_ppht_plan_v3(const int2 *win, int cells_total, int2 *win3, int *cells_max, int *list_cap)
 {
     int width[LANE_NUM_ANGLES];
     for (int n = 0; n < LANE_NUM_ANGLES; n++)
         width[n] = (n + 1 < LANE_NUM_ANGLES ? win[n + 1].y : cells_total) - win[n].y;
     const int forced = getenv("LANE_PPHT_G") ? atoi(getenv("LANE_PPHT_G")) : 0;      // tuning knob
+    // A smaller cluster means more frames in flight and fewer exchange partners, so a shorter shared point list is
+    // accepted when that is all a cluster size lacks (4K: 8 CTAs with 2560 list entries instead of 16 CTAs -- 37 frames in
+    // flight instead of 18, 1.76 ms against 3.6 ms per 128 frames; longer lists continue in the global extension).
+    static const int caps[3] = {LIST_CAP3, 2560, 2048};
     for (int pass = 0; pass < 2; pass++)
     for (int G = 1; G <= 16; G *= 2) {
         if (forced && G != forced) continue;
@@ -1165,7 +1169,8 @@ int lane_ppht_plan_v3(const int2 *win, int cells_total, int2 *win3, int *cells_m
         int mx = 0;
         for (int r = 0; r < G; r++) mx = off[r] > mx ? off[r] : mx;
         mx = (mx + 7) & ~7;
-        if ((size_t)mx * 2 + sizeof(uint32_t) * LIST_CAP3 + 4700 <= budget) { *cells_max = mx; return G; }
+        for (int cap : caps)
+            if ((size_t)mx * 2 + sizeof(uint32_t) * (size_t)cap + 4700 <= budget) { *cells_max = mx; *list_cap = cap; return G; }
     }
     return 0;
 }
