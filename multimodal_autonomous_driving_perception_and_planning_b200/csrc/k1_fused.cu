@@ -219,7 +219,6 @@ __global__ void __launch_bounds__(FWARPS * 32, MINB) k1_fused(FusedArgs A)
     uint32_t *tab = reinterpret_cast<uint32_t *>(ws + SM_TAB);
     uint16_t *Mring = reinterpret_cast<uint16_t *>(ws + SM_M) + 8;     // + slot * RS
     uint16_t *DXr = reinterpret_cast<uint16_t *>(ws + SM_DX), *DYr = reinterpret_cast<uint16_t *>(ws + SM_DY);
-    uint16_t *queue = reinterpret_cast<uint16_t *>(ws + SM_Q);
     uint32_t *kbits = reinterpret_cast<uint32_t *>(ws + SM_KB);
     uint32_t *qn = reinterpret_cast<uint32_t *>(ws + SM_QN);
     const int H = A.H, W = A.W, WW = A.WW;
