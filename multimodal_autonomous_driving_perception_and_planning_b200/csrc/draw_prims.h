@@ -1,8 +1,11 @@
-// Host half of K7 (k7_draw.cu): cv2-level drawing calls -> row-separable device primitives, in plain C++ (no CUDA), so
-// that the CPU test suite can exercise it without a GPU (tests/native/draw_emulator.cpp rasterises the primitives on the
-// CPU as the kernel does and tests/test_draw_host.py compares the result with cv2 itself).
-// The arithmetic restated here is OpenCV 4.13's modules/imgproc/src/drawing.cpp for uint8 images, LINE_8, shift 0;
-// oracle/draw.py holds the same restatement in Python, pinned against cv2.
+// Host half of K7 (k7_draw.cu) and the geometry both halves share, in plain C++ (CUDA only where a function is also
+// compiled for the device), so that the CPU test suite can exercise it without a GPU: tests/native/draw_emulator.cpp
+// rasterises the primitives on the CPU as the kernel does and tests/test_draw_host.py compares the result with cv2 itself.
+//   geometry core   OpenCV 4.13's modules/imgproc/src/drawing.cpp for uint8 images, LINE_8, shift 0, as __host__ __device__
+//                   templates over an emitter (clipLine, Line, Line2, FillConvexPoly, Circle, ThickLine, fillPoly's edges);
+//                   oracle/draw.py holds the same restatement in Python, pinned against cv2
+//   Builder         the host emitter: appends device primitives (Prim) per frame; cv2-level calls and the command parser
+//   scene code      LaneDetector.draw_lanes and the synthetic generator's frame (NumPy legacy RandomState included)
 #pragma once
 #include <math.h>
 #include <stdint.h>

@@ -8,7 +8,7 @@
 //   SyntheticDataGenerator.generate_frame_with_vehicles (bytecode only)
 //       cv2.line (thickness 1 and 2), cv2.rectangle, cv2.fillPoly, filled cv2.circle
 //
-// Two layers.  The host layer (this file, plain C++) turns cv2-level calls into row-separable device primitives with
+// Two layers.  The host layer (draw_prims.h, plain C++) turns cv2-level calls into row-separable device primitives with
 // OpenCV 4.13's own integer / double arithmetic (clipLine's truncating double division, Bresenham end points, the
 // 16.16 DDA that outlines FillConvexPoly, FillConvexPoly's rounded edge steps, the pre-clip of thick segments against the
 // image grown by `thickness`, ThickLine's cvRound'ed normal, the midpoint circle, fillPoly's edge table built from the
@@ -24,6 +24,9 @@
 //             of writing pixels; MASK_BLEND then applies cv2.addWeighted's float32 fma(a, alpha, fma(b, beta, gamma))
 //             once per covered pixel (a pixel on the polygon outline AND inside it is blended once, as cv2's overlay is)
 //   BITMAP    1-bit mask blit (text)
+// The lane overlay has its own kernel (k7_lanes, below) that needs no primitive lists: the geometry core of draw_prims.h
+// is host/device code, and a thread runs it for one polygon edge or thick segment and rasterises directly.
+// Entry points: lane_draw_commands, lane_draw_lanes_batch, lane_draw_lanes_records, lane_generate_frames.
 // HBM-bound byte work: no tensor cores, no GEMM shapes.
 #include <math.h>
 #include <stdio.h>

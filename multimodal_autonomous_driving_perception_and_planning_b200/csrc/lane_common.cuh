@@ -11,6 +11,8 @@
 // Adjacent rows:
 //   K0  k0_resize.cu      cv2.resize of VideoDataLoader.read_frame (data/loaders/video_loader.py:108,128)
 //   K6  k6_frame_stats.cu mean / Laplacian variance / HSV green ratio of SceneClassifier (src/tagging/scene_classifier.py)
+//   K7  k7_draw.cu        cv2-exact rasteriser: draw_lanes (:220-251), draw_lane_offset_indicator (visualization/overlays.py:103-148),
+//                         the synthetic generator's frames (draw_prims.h: host expansion + the geometry shared with the device)
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
