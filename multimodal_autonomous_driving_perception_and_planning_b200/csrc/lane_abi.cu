@@ -563,7 +563,12 @@ int lane_ctx_create(int device, int height, int width, int max_batch, int max_se
     {
         int lo = 0, hi = 0;                          // the back half first: its clusters keep their slots, the edge kernels fill in
         cudaDeviceGetStreamPriorityRange(&lo, &hi);
-        CUB(cudaStreamCreateWithPriority(&ctx->st2, cudaStreamNonBlocking, hi));
+        const char *pr = getenv("LANE_B200_BACK_PRIORITY");          // A/B knob: "low" = the edge kernels first
+        CUB(cudaStreamCreateWithPriority(&ctx->st2, cudaStreamNonBlocking, pr && !strcmp(pr, "low") ? lo : hi));
+        if (pr && !strcmp(pr, "low")) {                              // then the edge stream gets the high priority
+            cudaStreamDestroy(ctx->st);
+            CUB(cudaStreamCreateWithPriority(&ctx->st, cudaStreamNonBlocking, hi));
+        }
         for (auto &e : ctx->edge_done) CUB(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
         const char *ov = getenv("LANE_B200_OVERLAP");
         ctx->overlap_ok = !(ov && !strcmp(ov, "0"));
