@@ -508,7 +508,7 @@ __global__ void __launch_bounds__(NT2) k4_ppht_v2(uint32_t *__restrict__ points_
 // through DSMEM slots with a sequence number -- no cluster barrier on the hot path.
 constexpr int BATCH3 = 64;
 constexpr int LIST_CAP3 = 3072;      // points of a frame kept in shared memory (the plan may settle for less to fit a smaller cluster)
-constexpr int OVER_CAP3 = 13312;     // further points kept in a private global (L2) extension of the list
+constexpr int OVER_CAP3 = 131072;    // most points a frame may keep in the private global (L2) extension of its list
 
 struct XchgSlots {
     unsigned long long v[2][16];   // [seq parity][source rank] = seq << 32 | payload
@@ -587,7 +587,7 @@ __global__ void k4_prof_dump(int n)
 __global__ void __launch_bounds__(416, 2) k4_ppht_v3(const uint32_t *__restrict__ points_all, const int *__restrict__ n_points,
                            const uint32_t *__restrict__ pmask_all, uint32_t *__restrict__ pmask_work,
                            uint32_t *__restrict__ over_all,
-                           const int2 *__restrict__ win, int cells_max, int list_cap, int G, int nvw, int tpa,
+                           const int2 *__restrict__ win, int cells_max, int list_cap, int over_cap, int G, int nvw, int tpa,
                            int32_t *__restrict__ lines_all, int *__restrict__ n_lines, LaneGeom g, LaneHoughParams hp, int prof,
                            const int *__restrict__ order)
 {
@@ -645,8 +645,8 @@ __global__ void __launch_bounds__(416, 2) k4_ppht_v3(const uint32_t *__restrict_
     // The list lives in shared memory up to list_cap points; a longer one (every 4K generator frame: 3.3 k points)
     // continues in this CTA's private global extension.  Swap-remove only ever touches a random index and the current
     // tail, so once the list has shrunk below list_cap everything is in shared memory again.
-    uint32_t *over = over_all + ((size_t)f * G + rank) * OVER_CAP3;
-    const bool dense = count0 > list_cap + OVER_CAP3 || (count0 > list_cap && !over_all);   // left to v2
+    uint32_t *over = over_all + ((size_t)f * G + rank) * over_cap;
+    const bool dense = count0 > list_cap + over_cap || (count0 > list_cap && !over_all);   // left to v2
     if (!dense) {
         for (int i = tid; i < min(count0, list_cap); i += blockDim.x) s_list[i] = glist[i];
         for (int i = list_cap + tid; i < count0; i += blockDim.x) __stcg(&over[i - list_cap], glist[i]);
@@ -1103,7 +1103,7 @@ void launch_ppht_v2(uint32_t *points, const int *n_points, uint32_t *pmask, uint
 
 // v3 launch: false if the geometry does not fit (caller uses v2)
 bool launch_ppht_v3(const uint32_t *points, const int *n_points, const uint32_t *pmask, uint32_t *pmask_work,
-                    uint32_t *list_over, const int2 *win3, int cells_max, int list_cap, int G, int32_t *lines, int *n_lines, LaneGeom g,
+                    uint32_t *list_over, const int2 *win3, int cells_max, int list_cap, int over_cap, int G, int32_t *lines, int *n_lines, LaneGeom g,
                     LaneHoughParams hp, int n, cudaStream_t st, int *launches, int *order)
 {
     if (G < 1 || (g.bh * ((g.W + 31) / 32)) % 4 != 0 || ((uintptr_t)pmask % 16) != 0) return false;
@@ -1132,7 +1132,7 @@ bool launch_ppht_v3(const uint32_t *points, const int *n_points, const uint32_t 
     attr[0].val.clusterDim.x = G; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    cudaError_t e = cudaLaunchKernelEx(&cfg, k4_ppht_v3, points, n_points, pmask, pmask_work, list_over, win3, cells_max, list_cap, G, nvw, tpa,
+    cudaError_t e = cudaLaunchKernelEx(&cfg, k4_ppht_v3, points, n_points, pmask, pmask_work, list_over, win3, cells_max, list_cap, over_cap, G, nvw, tpa,
                                        lines, n_lines, g, hp, getenv("LANE_B200_PPHT_PROF") ? 1 : 0, (const int *)order);
     if (e != cudaSuccess) { cudaGetLastError(); return false; }
 #ifdef LANE_PPHT_PROF

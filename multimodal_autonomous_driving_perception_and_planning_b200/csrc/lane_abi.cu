@@ -81,7 +81,7 @@ struct lane_ctx {
     int2 *d_win3 = nullptr;           // v3 layout: (rmin, first cell inside the owning CTA)
     uint32_t *d_pmask_work = nullptr; // [B][G3][bh][WW] private mask copies of the v3 cluster CTAs
     uint32_t *d_list_over = nullptr;  // [B][G3][over_cap] private extensions of the v3 point list (ROIs with many pixels)
-    int G3 = 0, cells_max3 = 0, list_cap3 = 0;
+    int G3 = 0, cells_max3 = 0, list_cap3 = 0, over_cap3 = 0;   // v3 plan: cluster size, cells / shared list entries per CTA, list extension
     LaneFitScratch fit{};
     int *d_stream_id = nullptr;
     double *d_prev_fit = nullptr;
@@ -361,7 +361,7 @@ int run_stages(lane_ctx *c, const uint8_t *frames_dev, int off, int m, const int
         // up the frames v3 flagged (point list larger than its shared-memory list), or runs alone if v3 cannot launch.
         bool v3 = !c->ppht_v2 && c->G3 > 0 &&
                   launch_ppht_v3(points, n_points, pmask_bits, c->d_pmask_work + o * c->G3 * std::max(g.bh, 1) * WW,
-                                 c->d_list_over ? c->d_list_over + o * c->G3 * lane_ppht_over_cap_v3() : nullptr, c->d_win3, c->cells_max3, c->list_cap3, c->G3, lines, n_lines, g, c->hp, m, hs, &L[LANE_STAGE_PPHT],
+                                 c->d_list_over ? c->d_list_over + o * c->G3 * (size_t)c->over_cap3 : nullptr, c->d_win3, c->cells_max3, c->list_cap3, c->over_cap3, c->G3, lines, n_lines, g, c->hp, m, hs, &L[LANE_STAGE_PPHT],
                                  c->k4_lpt ? c->d_order + o : nullptr);
         launch_ppht_v2(points, n_points, pmask_bits, c->d_accum16 + o * (c->cells_per_frame / 2), c->d_win,
                        c->cells_per_frame, lines, n_lines, g, c->hp, m, hs, &L[LANE_STAGE_PPHT], v3 ? 1 : 0);
@@ -698,8 +698,14 @@ int lane_set_roi_mask(lane_ctx *c, const uint8_t *mask)
         c->d_list_over = nullptr;
         if (c->G3 > 0) {
             CU(dalloc(&c->d_pmask_work, (size_t)c->max_batch * c->G3 * std::max(g.bh, 1) * WW));
-            if (cnt > c->list_cap3)                  // the ROI can hold more edge pixels than the shared-memory list
-                CU(dalloc(&c->d_list_over, (size_t)c->max_batch * c->G3 * lane_ppht_over_cap_v3()));
+            // the ROI can hold more edge pixels than the shared-memory list: every CTA of a cluster gets a private global
+            // extension, sized by the ROI up to lane_ppht_over_cap_v3() points (busier frames go to the global-memory kernel)
+            c->over_cap3 = 0;
+            if (cnt > c->list_cap3) {
+                c->over_cap3 = (int)std::min<long long>((long long)cnt - c->list_cap3, lane_ppht_over_cap_v3());
+                c->over_cap3 = (c->over_cap3 + 63) & ~63;
+                CU(dalloc(&c->d_list_over, (size_t)c->max_batch * c->G3 * (size_t)c->over_cap3));
+            }
         }
     }
     CU(dalloc(&c->d_pmask_bits, 2 * (size_t)c->max_batch * std::max(g.bh, 1) * WW));      // per result slot

@@ -134,7 +134,7 @@ int lane_ppht_list_cap_v3();
 int lane_ppht_over_cap_v3();
 // list_over: [n][G][lane_ppht_over_cap_v3()] private list extensions (null = frames above the shared list go to v2)
 bool launch_ppht_v3(const uint32_t *points, const int *n_points, const uint32_t *pmask_bits, uint32_t *pmask_work,
-                    uint32_t *list_over, const int2 *win3, int cells_max, int list_cap, int G, int32_t *lines, int *n_lines, LaneGeom g,
+                    uint32_t *list_over, const int2 *win3, int cells_max, int list_cap, int over_cap, int G, int32_t *lines, int *n_lines, LaneGeom g,
                     LaneHoughParams hp, int n, cudaStream_t st, int *launches, int *order);
 
 // ---- K5 ---------------------------------------------------------------------------------
