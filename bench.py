@@ -228,6 +228,7 @@ def main():
         fps = sum(v[1] for v in vals) / sum(v[2] for v in vals)
         sample = (f"{vals[0][1]} frames/step ({vals[0][1] // cores} per core) of the same 1080p generator streams, "
                   f"{cores} processes x cv2.setNumThreads(1), sequential detect() per stream")
+        base["data"] = "synthetic (SyntheticDataGenerator 1920x1080, per-stream phase 1000, drawn by cv2 on the host: the same frames)"
         out = dict(base, impl="reference", value=fps, ms_per_step=1e3 * sum(v[2] for v in vals) / args.steps,
                    dtype="u8/int32/f64", config={"workload": workload, "host": cpu_info()},
                    cpu_baseline={"value": fps, "unit": "frames/s", "cores": cores, "kind": "port", "sample": sample},
