@@ -211,9 +211,15 @@ __global__ void __launch_bounds__(DRAW_THREADS) k7_draw(uint8_t *frames, const P
 
     // the primitives of this frame that touch this band, in drawing order (binned on the host)
     const int64_t p_end = band_begin[(size_t)f * gridDim.x + band + 1];
+    // Painter's order only matters between primitives that may write DIFFERENT values to one pixel: a run of primitives of
+    // one colour (the ~14 pieces of a thick segment, a polygon's outline and interior) commutes, and so does anything that
+    // only sets mask bits.  `pending` = colour drawn since the last barrier (NO_COLOUR: nothing, MIXED: per-row colours).
+    constexpr uint32_t NO_COLOUR = 0xFFFFFFFFu, MIXED = 0xFFFFFFFEu;
+    uint32_t pending = NO_COLOUR;
     for (int64_t pi = band_begin[(size_t)f * gridDim.x + band]; pi < p_end; pi++) {
         const Prim p = prims[band_idx[pi]];
         if (p.op == P_MASK_BEGIN) {              // band-uniform state: no row test
+            pending = NO_COLOUR;
             __syncthreads();
             for (int i = tid; i < BAND_ROWS * t.WW; i += DRAW_THREADS) t.mask[i] = 0;
             t.to_mask = true;
@@ -222,6 +228,7 @@ __global__ void __launch_bounds__(DRAW_THREADS) k7_draw(uint8_t *frames, const P
         }
         const int ya = max(p.y0, t.by0), yb = min(p.y1, t.by1);
         if (p.op == P_MASK_BLEND) {
+            pending = NO_COLOUR;
             __syncthreads();
             t.to_mask = false;
             if (ya <= yb)
@@ -231,6 +238,11 @@ __global__ void __launch_bounds__(DRAW_THREADS) k7_draw(uint8_t *frames, const P
             continue;
         }
         if (ya > yb) continue;
+        if (!t.to_mask) {
+            const uint32_t mine = p.op == P_ROWS ? MIXED : p.color;
+            if (pending != NO_COLOUR && (pending != mine || mine == MIXED)) __syncthreads();
+            pending = mine;
+        }
         switch (p.op) {
         case P_TRAP:
             for (int y = ya + warp; y <= yb; y += nwarps) {
@@ -287,7 +299,6 @@ __global__ void __launch_bounds__(DRAW_THREADS) k7_draw(uint8_t *frames, const P
         }
         default: break;
         }
-        __syncthreads();
     }
 }
 
