@@ -122,8 +122,10 @@ class RecordGatherer:
         return self._finish(self.payload[k], to_host)
 
     def gather_device(self, records_ptr: int, to_host: bool = False):
-        """``records_ptr``: device address of ``n`` packed ``lane_record``s on ``self.device``; the caller orders
-        the producing stream before torch's current stream (and the buffer's reuse after the returned work)."""
+        """``records_ptr``: device address of ``n`` packed ``lane_record``s on ``self.device`` (the batch has been collected,
+        so its records are complete).  The collective is enqueued on torch's current stream; call
+        ``LaneContext.fence_records(torch.cuda.current_stream().cuda_stream)`` right after, so that the kernel that next
+        writes that result slot -- and only that kernel -- waits for it."""
         import torch
         src = torch.as_tensor(_DeviceBytes(records_ptr, self.nbytes), device=self.device)
         return self._finish(src, to_host)
